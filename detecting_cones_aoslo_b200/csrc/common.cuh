@@ -1,0 +1,229 @@
+// common.cuh -- shared declarations of libaoslo_b200 (sm_100a).
+//
+// Data layout in HBM:
+//   particles   double2[n]  rows [x, y]  (the reference's (n,2) float64 ndarray)
+//   stable      uint8[n]
+//   fields      T[H*W] row-major, gradient T[H*W*2] interleaved (T = float | double)
+//   cell list   count[ncell], start[ncell+1], sorted_pos double2[n], sorted_idx int[n]
+//   kNN table   idx int32[n*k], d2 double[n*k]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "aoslo_b200.h"
+
+namespace aoslo {
+
+int set_cuda_error(cudaError_t e, const char* where);
+
+#define AOSLO_CUDA(call)                                                         \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) return ::aoslo::set_cuda_error(e__, #call);      \
+    } while (0)
+#define AOSLO_TRY(call)                                                          \
+    do {                                                                         \
+        int s__ = (call);                                                        \
+        if (s__ != AOSLO_OK) return s__;                                         \
+    } while (0)
+#define AOSLO_LAUNCH_CHECK() AOSLO_CUDA(cudaGetLastError())
+
+constexpr int kThreads = 256;          // block size of the grid-stride kernels
+constexpr int kScanThreads = 1024;     // block size of the ordered-compaction kernels
+constexpr int kMaxScanBlocks = 1024;   // spine length of the 3-phase scan
+
+// Uniform-grid cell list over [0,W) x [0,H); cell edge = 1 << shift pixels.
+struct CellList {
+    int shift = 2;
+    int gw = 0, gh = 0, ncell = 0;
+    int* count = nullptr;        // [ncell]
+    int* start = nullptr;        // [ncell + 1]
+    int* slot = nullptr;         // [cap]   rank of the particle inside its cell
+    int* cell_of = nullptr;      // [cap]
+    int* sorted_idx = nullptr;   // [cap]
+    double2* sorted_pos = nullptr;  // [cap]
+    int cap = 0;
+};
+
+struct CellView {                // what kernels take by value
+    int shift, gw, gh;
+    const int* start;
+    const int* sorted_idx;
+    const double2* sorted_pos;
+};
+
+inline CellView view_of(const CellList& c) {
+    return CellView{c.shift, c.gw, c.gh, c.start, c.sorted_idx, c.sorted_pos};
+}
+
+// sklearn-order KD tree mirrored on the device (built on the host, kdtree_host.cpp)
+struct KdTreeDev {
+    int n = 0, n_nodes = 0;
+    int32_t* idx_array = nullptr;     // [cap]
+    int32_t* node_start = nullptr;    // [2*cap]
+    int32_t* node_end = nullptr;      // [2*cap]
+    double* node_bounds = nullptr;    // [2*cap*4] lo_x lo_y hi_x hi_y
+    // pinned host staging
+    double* h_points = nullptr;       // [cap*2]
+    int32_t* h_idx_array = nullptr;
+    int32_t* h_node_start = nullptr;
+    int32_t* h_node_end = nullptr;
+    double* h_node_bounds = nullptr;
+    int cap = 0;
+};
+
+}  // namespace aoslo
+
+struct aoslo_ctx {
+    int device = 0;
+    int H = 0, W = 0;
+    int cap = 0, gt_cap = 0;
+    int num_sms = 0;
+    int nb = 0;                       // blocks of the grid-stride kernels (multiple of the SM count)
+    int coop_blocks = 0;              // co-resident blocks of the cooperative deletion kernel
+    int* d_status = nullptr;
+    int* d_counters = nullptr;        // [32] device scalars (counts, round counters)
+    int* h_pinned = nullptr;          // [32] pinned readback
+    aoslo::CellList cl_p;             // particles
+    aoslo::CellList cl_g;             // ground truth
+    int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
+    double* d_knn_d2 = nullptr;
+    int* d_block_sums = nullptr;      // [kMaxScanBlocks + 1]
+    unsigned long long* d_touch = nullptr;  // [cap]
+    uint8_t* d_del = nullptr;         // [cap]
+    uint8_t* d_rowstate = nullptr;    // [cap]
+    double* d_force = nullptr;        // [cap*2]
+    double* d_pos[2] = {nullptr, nullptr};
+    uint8_t* d_stable[2] = {nullptr, nullptr};
+    double* d_dist_p2g = nullptr;     // [cap]
+    double* d_dist_g2p = nullptr;     // [gt_cap]
+    double* d_partials = nullptr;     // [4096] fp64 reduction partials
+    aoslo_metrics_record* d_record = nullptr;
+    aoslo_metrics_record* h_record = nullptr;   // pinned
+    double* d_lut = nullptr;          // [64*64]
+    double* d_field = nullptr;        // [H*W]
+    int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
+    aoslo::KdTreeDev kd;
+    cudaEvent_t ev[12] = {};
+};
+
+namespace aoslo {
+
+// ---------------------------------------------------------------------------------------
+// Ordered compaction / exclusive scan in three phases (count, spine, emit).  `Op` provides
+//   __device__ int  value(int i) const      -- the integer to be scanned (0/1 for a compaction)
+//   __device__ void emit(int i, int v, int exclusive_prefix) const
+// The element count may live on the device (d_m != nullptr) so that callers never
+// have to synchronise to learn it.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one int per thread; returns exclusive prefix, total in `total`
+__device__ __forceinline__ int block_excl_scan(int v, int* smem_warp /*[32]*/, int& total) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v);
+    if (lane == 31) smem_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int w = (lane < nw) ? smem_warp[lane] : 0;
+        int wi = warp_incl_scan(w);
+        smem_warp[lane] = wi - w;          // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = wi;  // total
+    }
+    __syncthreads();
+    int excl = incl - v + smem_warp[wid];
+    total = smem_warp[32];
+    __syncthreads();
+    return excl;
+}
+
+__device__ __forceinline__ void scan_span(int m, int& lo, int& hi) {
+    int per = (m + gridDim.x - 1) / gridDim.x;
+    per = ((per + blockDim.x - 1) / blockDim.x) * blockDim.x;
+    long long l = (long long)blockIdx.x * per;
+    lo = (int)(l < m ? l : m);
+    long long h = l + per;
+    hi = (int)(h < m ? h : m);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kScanThreads) scan_count_kernel(Op op, int m_host, const int* d_m,
+                                                                 int* block_sums) {
+    __shared__ int sw[33];
+    int m = d_m ? *d_m : m_host;
+    int lo, hi;
+    scan_span(m, lo, hi);
+    int acc = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += op.value(i);
+    int total;
+    block_excl_scan(acc, sw, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the block sums; writes total (+ base) to d_total
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
+                                                                  const int* d_base, int base_host,
+                                                                  int* d_total_added);
+
+template <class Op>
+__global__ void __launch_bounds__(kScanThreads) scan_emit_kernel(Op op, int m_host, const int* d_m,
+                                                                const int* block_sums) {
+    __shared__ int sw[33];
+    int m = d_m ? *d_m : m_host;
+    int lo, hi;
+    scan_span(m, lo, hi);
+    int carry = block_sums[blockIdx.x];
+    for (int base = lo; base < hi; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = (i < hi) ? op.value(i) : 0;
+        int total;
+        int excl = block_excl_scan(v, sw, total);
+        if (i < hi) op.emit(i, v, carry + excl);
+        carry += total;
+    }
+}
+
+int scan_blocks_for(int m_capacity);
+
+// host driver: runs the three phases on `stream`.
+//   d_total      <- base + sum(value)      (may be nullptr)
+//   d_total_added<- sum(value)             (may be nullptr)
+// `base` (offset added to every prefix handed to emit) comes from *d_base if non-null.
+template <class Op>
+int ordered_scan(aoslo_ctx* ctx, cudaStream_t s, Op op, int m_capacity, int m_host, const int* d_m,
+                 int* d_total, const int* d_base, int base_host, int* d_total_added) {
+    int nb = scan_blocks_for(m_capacity);
+    scan_count_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
+    AOSLO_LAUNCH_CHECK();
+    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(ctx->d_block_sums, nb, d_total, d_base, base_host, d_total_added);
+    AOSLO_LAUNCH_CHECK();
+    scan_emit_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// field element access (T = float | double), always widened to double for decisions
+template <typename T>
+__device__ __forceinline__ double fld(const T* p, long long i) {
+    return (double)p[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// stage entry points implemented in particles.cu / blobness.cu (host side, stream-ordered)
+// ---------------------------------------------------------------------------------------
+int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
+int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,
+              const int* d_nq, int k, int32_t* d_idx, double* d_d2, int n_points_host, const int* d_np);
+int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
+                int n_query, int k, int32_t* d_idx, double* d_d2);
+
+}  // namespace aoslo

@@ -1,0 +1,994 @@
+// particles.cu -- the particle system of the detection path on sm_100a (compiled with
+// -fmad=false: every FP64 product/sum is rounded separately, like the reference's NumPy code,
+// because the loop's decisions are discrete and amplify rounding differences).
+//
+// Kernels (reference file:line each one replaces):
+//   cell_count / cell_scatter        uniform-grid cell list (replaces sklearn KDTree.fit, utils.py:29, :218)
+//   knn_cells_kernel                 exact kNN, canonical (d^2, index) order          (utils.py:30, :219)
+//   knn_sklearn_kernel               exact kNN in sklearn's depth-first tie order     (same call sites)
+//   seed (ordered compaction)        utils.initialize_high_prop_location             (utils.py:359-375)
+//   delete_resolve_kernel            utils.del_close_particles greedy loop           (utils.py:249-263)
+//   keep-compaction                  utils.del_close_particles compaction            (utils.py:265-273)
+//   dist_lut_kernel                  utils.get_precomputed_dist_func                 (utils.py:95-109)
+//   gravity_field_kernel             utils.calc_gravity_field_optim                  (utils.py:310-333)
+//   window_argmin_kernel + append    utils.adding_particles                          (utils.py:336-356)
+//   dist_force_kernel                utils.calc_dist_energy_pit(_optim) / calc_dist_energy (utils.py:112-134, :43-58)
+//   move_kernel                      the move step                 (pipeline_with_delitions.py:215-245)
+//   metrics kernels                  calc_dist_to_neares x2, get_particles_in_image, calc_acc_metrics,
+//                                    calc_metrics('Chamfer'), calc_blob_energy (utils.py:214-242, :378-418, :137-144)
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace aoslo {
+
+// =======================================================================================
+// scan spine
+// =======================================================================================
+__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
+                                                                  const int* d_base, int base_host,
+                                                                  int* d_total_added) {
+    __shared__ int sw[33];
+    int base = d_base ? *d_base : base_host;
+    int v = (threadIdx.x < nblocks) ? block_sums[threadIdx.x] : 0;
+    int total;
+    int excl = block_excl_scan(v, sw, total);
+    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = base + excl;
+    if (threadIdx.x == 0) {
+        if (d_total) *d_total = base + total;
+        if (d_total_added) *d_total_added = total;
+    }
+}
+
+int scan_blocks_for(int m_capacity) {
+    int nb = (m_capacity + kScanThreads - 1) / kScanThreads;
+    if (nb < 1) nb = 1;
+    if (nb > kMaxScanBlocks) nb = kMaxScanBlocks;
+    return nb;
+}
+
+// =======================================================================================
+// cell list
+// =======================================================================================
+__device__ __forceinline__ int cell_coord(double v, int shift, int gmax, bool& bad) {
+    // positions must lie in [0, extent): anything else is reported (the reference would raise
+    // IndexError or silently wrap a negative index) and binned into the border cell
+    if (!(v >= 0.0)) { bad = true; return 0; }
+    int c = (int)v >> shift;       // v >= 0: trunc == floor
+    if (v >= 2147483000.0) { bad = true; return gmax - 1; }
+    if (c >= gmax) { c = gmax - 1; }
+    return c;
+}
+
+__global__ void __launch_bounds__(kThreads) cell_count_kernel(const double2* __restrict__ pos, int n_host,
+                                                              const int* d_n, int shift, int gw, int gh, int W,
+                                                              int H, int* count, int* cell_of, int* slot,
+                                                              int* status) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double2 p = pos[i];
+        bool bad = false;
+        int cx = cell_coord(p.x, shift, gw, bad);
+        int cy = cell_coord(p.y, shift, gh, bad);
+        if (p.x != p.x || p.y != p.y) atomicOr(status, AOSLO_DEV_NAN);
+        else if (bad || p.x >= (double)W || p.y >= (double)H) atomicOr(status, AOSLO_DEV_ESCAPED);
+        int c = cy * gw + cx;
+        cell_of[i] = c;
+        slot[i] = atomicAdd(&count[c], 1);
+    }
+}
+
+struct CellScanOp {
+    const int* count;
+    int* start;
+    __device__ int value(int i) const { return count[i]; }
+    __device__ void emit(int i, int, int excl) const { start[i] = excl; }
+};
+
+__global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double2* __restrict__ pos, int n_host,
+                                                                const int* d_n, const int* __restrict__ cell_of,
+                                                                const int* __restrict__ slot,
+                                                                const int* __restrict__ start, int* sorted_idx,
+                                                                double2* sorted_pos) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int dst = start[cell_of[i]] + slot[i];
+        sorted_idx[dst] = i;
+        sorted_pos[dst] = pos[i];
+    }
+}
+
+int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n) {
+    AOSLO_CUDA(cudaMemsetAsync(cl.count, 0, sizeof(int) * cl.ncell, s));
+    cell_count_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, cl.shift, cl.gw, cl.gh,
+                                                   ctx->W, ctx->H, cl.count, cl.cell_of, cl.slot, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    CellScanOp op{cl.count, cl.start};
+    // start[ncell] = total
+    AOSLO_TRY(ordered_scan(ctx, s, op, cl.ncell, cl.ncell, nullptr, cl.start + cl.ncell, nullptr, 0, nullptr));
+    cell_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, cl.cell_of, cl.slot,
+                                                     cl.start, cl.sorted_idx, cl.sorted_pos);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// =======================================================================================
+// exact kNN on the cell list, canonical (d^2, index) order
+// =======================================================================================
+template <int K>
+struct TopK {
+    double d2[K];
+    int idx[K];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < K; ++j) { d2[j] = INFINITY; idx[j] = 0x7fffffff; }
+    }
+    __device__ __forceinline__ void push(double d, int id) {
+        // strict total order (d2, idx); NaN distances never enter
+        if (!(d < d2[K - 1] || (d == d2[K - 1] && id < idx[K - 1]))) return;
+        d2[K - 1] = d; idx[K - 1] = id;
+#pragma unroll
+        for (int j = K - 1; j > 0; --j) {
+            bool less = d2[j] < d2[j - 1] || (d2[j] == d2[j - 1] && idx[j] < idx[j - 1]);
+            if (less) {
+                double td = d2[j]; d2[j] = d2[j - 1]; d2[j - 1] = td;
+                int ti = idx[j]; idx[j] = idx[j - 1]; idx[j - 1] = ti;
+            }
+        }
+    }
+};
+
+template <int K>
+__device__ __forceinline__ void knn_cells_query(const CellView& cl, double qx, double qy, TopK<K>& top) {
+    top.init();
+    const int c = 1 << cl.shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> cl.shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> cl.shift) : 0;
+    cx = min(cx, cl.gw - 1);
+    cy = min(cy, cl.gh - 1);
+    const int rmax = max(cl.gw, cl.gh);
+    for (int r = 0; r <= rmax; ++r) {
+        int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+        for (int y = max(ylo, 0); y <= min(yhi, cl.gh - 1); ++y) {
+            bool edge_row = (y == ylo) || (y == yhi);
+            if (edge_row) {
+                // the whole row segment is one contiguous span of the sorted arrays
+                int a = max(xlo, 0), b = min(xhi, cl.gw - 1);
+                if (a > b) continue;
+                int p0 = cl.start[y * cl.gw + a], p1 = cl.start[y * cl.gw + b + 1];
+                for (int p = p0; p < p1; ++p) {
+                    double2 t = cl.sorted_pos[p];
+                    double dx = qx - t.x, dy = qy - t.y;
+                    top.push(dx * dx + dy * dy, cl.sorted_idx[p]);
+                }
+            } else {
+                if (xlo >= 0) {
+                    int p0 = cl.start[y * cl.gw + xlo], p1 = cl.start[y * cl.gw + xlo + 1];
+                    for (int p = p0; p < p1; ++p) {
+                        double2 t = cl.sorted_pos[p];
+                        double dx = qx - t.x, dy = qy - t.y;
+                        top.push(dx * dx + dy * dy, cl.sorted_idx[p]);
+                    }
+                }
+                if (xhi < cl.gw && r > 0) {
+                    int p0 = cl.start[y * cl.gw + xhi], p1 = cl.start[y * cl.gw + xhi + 1];
+                    for (int p = p0; p < p1; ++p) {
+                        double2 t = cl.sorted_pos[p];
+                        double dx = qx - t.x, dy = qy - t.y;
+                        top.push(dx * dx + dy * dy, cl.sorted_idx[p]);
+                    }
+                }
+            }
+        }
+        // every unseen point lies outside the (2r+1)^2 block: lower-bound its distance
+        double bound = INFINITY;
+        if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
+        if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
+        if (xhi < cl.gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < cl.gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (bound == INFINITY) break;                         // whole grid visited
+        if (bound > 0.0 && top.d2[K - 1] < bound * bound) break;   // strict: ties at the bound stay open
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) knn_cells_kernel(CellView cl, const double2* __restrict__ q,
+                                                             int nq_host, const int* d_nq, int k,
+                                                             int32_t* out_idx, double* out_d2, int* status) {
+    int nq = d_nq ? *d_nq : nq_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        double2 p = q[i];
+        TopK<K> top;
+        knn_cells_query<K>(cl, p.x, p.y, top);
+        bool shortfall = false;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k) {
+                bool empty = top.idx[j] == 0x7fffffff;
+                shortfall |= empty;
+                out_idx[(size_t)i * k + j] = empty ? -1 : top.idx[j];
+                out_d2[(size_t)i * k + j] = top.d2[j];
+            }
+        }
+        if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+    }
+}
+
+int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,
+              const int* d_nq, int k, int32_t* d_idx, double* d_d2, int, const int*) {
+    CellView v = view_of(cl);
+    const double2* q = (const double2*)d_query;
+    if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (k == 1) knn_cells_kernel<1><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else if (k == 2) knn_cells_kernel<2><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else if (k <= 4) knn_cells_kernel<4><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else knn_cells_kernel<8><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// =======================================================================================
+// exact kNN in sklearn's order: depth-first single-tree query of KDTree(leaf_size=1)
+// (sklearn/neighbors/_binary_tree.pxi.tp:1603-1656, _kd_tree.pyx.tp:128-145,
+//  sklearn/utils/_heap.pyx:heap_push, sklearn/utils/_sorting.pyx: insertion sort for n <= 15)
+// =======================================================================================
+struct KdView {
+    int n, n_nodes;
+    const int32_t* idx_array;
+    const int32_t* node_start;
+    const int32_t* node_end;
+    const double* bounds;          // [n_nodes][4] lo_x lo_y hi_x hi_y
+    const double2* data;
+};
+
+__device__ __forceinline__ double kd_min_rdist(const KdView& t, int node, double qx, double qy) {
+    const double* b = t.bounds + (size_t)node * 4;
+    double r = 0.0;
+    {
+        double d_lo = b[0] - qx, d_hi = qx - b[2];
+        double d = (d_lo + fabs(d_lo)) + (d_hi + fabs(d_hi));
+        double h = 0.5 * d;
+        r += h * h;
+    }
+    {
+        double d_lo = b[1] - qy, d_hi = qy - b[3];
+        double d = (d_lo + fabs(d_lo)) + (d_hi + fabs(d_hi));
+        double h = 0.5 * d;
+        r += h * h;
+    }
+    return r;
+}
+
+__device__ __forceinline__ void sk_heap_push(double* vals, int* idxs, int size, double val, int val_idx) {
+    if (val >= vals[0]) return;
+    vals[0] = val; idxs[0] = val_idx;
+    int cur = 0;
+    while (true) {
+        int l = 2 * cur + 1, r = l + 1, sw;
+        if (l >= size) break;
+        else if (r >= size) {
+            if (vals[l] > val) sw = l; else break;
+        } else if (vals[l] >= vals[r]) {
+            if (val < vals[l]) sw = l; else break;
+        } else {
+            if (val < vals[r]) sw = r; else break;
+        }
+        vals[cur] = vals[sw]; idxs[cur] = idxs[sw];
+        cur = sw;
+    }
+    vals[cur] = val; idxs[cur] = val_idx;
+}
+
+__global__ void __launch_bounds__(128) knn_sklearn_kernel(KdView t, const double2* __restrict__ q, int nq, int k,
+                                                          int32_t* out_idx, double* out_d2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double qx = q[i].x, qy = q[i].y;
+    double vals[AOSLO_KMAX];
+    int idxs[AOSLO_KMAX];
+    for (int j = 0; j < k; ++j) { vals[j] = INFINITY; idxs[j] = 0; }
+    int st_node[48];
+    double st_lb[48];
+    int sp = 0;
+    st_node[0] = 0; st_lb[0] = kd_min_rdist(t, 0, qx, qy); sp = 1;
+    while (sp > 0) {
+        --sp;
+        int node = st_node[sp];
+        double lb = st_lb[sp];
+        if (lb > vals[0]) continue;                      // trim
+        if (2 * node + 1 >= t.n_nodes) {                 // leaf
+            for (int a = t.node_start[node]; a < t.node_end[node]; ++a) {
+                int id = t.idx_array[a];
+                double2 p = t.data[id];
+                double dx = qx - p.x, dy = qy - p.y;
+                double d = dx * dx + dy * dy;            // euclidean_rdist: sequential sum of squares
+                sk_heap_push(vals, idxs, k, d, id);
+            }
+        } else {
+            int i1 = 2 * node + 1, i2 = i1 + 1;
+            double lb1 = kd_min_rdist(t, i1, qx, qy), lb2 = kd_min_rdist(t, i2, qx, qy);
+            if (lb1 <= lb2) {                            // nearer child first, left on ties
+                st_node[sp] = i2; st_lb[sp] = lb2; ++sp;
+                st_node[sp] = i1; st_lb[sp] = lb1; ++sp;
+            } else {
+                st_node[sp] = i1; st_lb[sp] = lb1; ++sp;
+                st_node[sp] = i2; st_lb[sp] = lb2; ++sp;
+            }
+        }
+    }
+    // simultaneous_sort for n <= 15: insertion sort by value, stable w.r.t. the heap array
+    for (int a = 1; a < k; ++a) {
+        double tv = vals[a]; int ti = idxs[a];
+        int b = a;
+        while (b > 0 && vals[b - 1] > tv) { vals[b] = vals[b - 1]; idxs[b] = idxs[b - 1]; --b; }
+        vals[b] = tv; idxs[b] = ti;
+    }
+    for (int j = 0; j < k; ++j) {
+        out_idx[(size_t)i * k + j] = idxs[j];
+        out_d2[(size_t)i * k + j] = vals[j];
+    }
+}
+
+int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
+                int n_query, int k, int32_t* d_idx, double* d_d2) {
+    KdTreeDev& kd = ctx->kd;
+    if (n_points > kd.cap) return AOSLO_ERR_CAPACITY;
+    if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (n_points < k) return AOSLO_ERR_INVALID;   // sklearn: ValueError("Expected n_neighbors <= n_samples_fit")
+    // host round trip: sklearn's idx_array is the residue of libstdc++ std::nth_element
+    AOSLO_CUDA(cudaMemcpyAsync(kd.h_points, d_points, sizeof(double) * 2 * n_points, cudaMemcpyDeviceToHost, s));
+    AOSLO_CUDA(cudaStreamSynchronize(s));
+    int n_nodes = aoslo_kdtree_num_nodes(n_points);
+    AOSLO_TRY(aoslo_kdtree_build_host(kd.h_points, n_points, kd.h_idx_array, kd.h_node_start, kd.h_node_end,
+                                      kd.h_node_bounds, n_nodes));
+    AOSLO_CUDA(cudaMemcpyAsync(kd.idx_array, kd.h_idx_array, sizeof(int32_t) * n_points, cudaMemcpyHostToDevice, s));
+    AOSLO_CUDA(cudaMemcpyAsync(kd.node_start, kd.h_node_start, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
+    AOSLO_CUDA(cudaMemcpyAsync(kd.node_end, kd.h_node_end, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
+    AOSLO_CUDA(cudaMemcpyAsync(kd.node_bounds, kd.h_node_bounds, sizeof(double) * 4 * n_nodes,
+                               cudaMemcpyHostToDevice, s));
+    KdView v{n_points, n_nodes, kd.idx_array, kd.node_start, kd.node_end, kd.node_bounds, (const double2*)d_points};
+    int blocks = (n_query + 127) / 128;
+    if (blocks > 0) {
+        knn_sklearn_kernel<<<blocks, 128, 0, s>>>(v, (const double2*)d_query, n_query, k, d_idx, d_d2);
+        AOSLO_LAUNCH_CHECK();
+    }
+    // the pinned staging buffers are reused by the next call
+    AOSLO_CUDA(cudaStreamSynchronize(s));
+    return AOSLO_OK;
+}
+
+// =======================================================================================
+// seeding: raster-order compaction of the inner-region mask R_b > threshold
+// =======================================================================================
+template <typename T>
+struct SeedOp {
+    const T* Rb;
+    int W, bx, by, wi;
+    double thr;
+    double2* out;
+    int cap;
+    int* status;
+    __device__ int value(int m) const {
+        int y = by + m / wi, x = bx + m % wi;
+        return ((double)Rb[(size_t)y * W + x] > thr) ? 1 : 0;
+    }
+    __device__ void emit(int m, int v, int dst) const {
+        if (!v) return;
+        if (dst >= cap) { atomicOr(status, AOSLO_DEV_CAPACITY); return; }
+        int y = by + m / wi, x = bx + m % wi;
+        out[dst] = make_double2((double)x, (double)y);
+    }
+};
+
+// =======================================================================================
+// deletion (utils.py:245-278)
+// =======================================================================================
+// Row i of the kNN(k=2) table is (from, to, dist).  The reference walks the rows in order and
+// deletes the endpoint with the lower blobness unless one endpoint is already deleted; the
+// outcome of a row therefore depends only on earlier rows sharing an endpoint.  Wavefront
+// rounds: in every round each unresolved row stamps both endpoints with (round, ~row) by
+// atomicMax -- the lowest unresolved row wins an endpoint -- and a row that owns both of its
+// endpoints is resolved.  Rows resolved in one round never share an endpoint, so the result is
+// exactly the sequential one.
+struct DeleteParams {
+    const double2* pos;
+    const uint8_t* stable;
+    int n_host;
+    const int* d_n;
+    const int32_t* knn_idx;     // [n][2]
+    const double* knn_d2;       // [n][2]
+    double thr;
+    int W, H;
+    unsigned long long* touch;
+    uint8_t* del;
+    uint8_t* rowstate;          // 0 inactive / resolved, 1 pending
+    int* counters;              // [3] rotating "rows still pending"
+    int* rounds_out;
+    int* status;
+};
+
+template <typename T>
+__device__ __forceinline__ double energy_at(const T* Rb, double2 p, int W, int H, int* status) {
+    int ix = (int)p.x, iy = (int)p.y;
+    if (ix < 0 || ix >= W || iy < 0 || iy >= H || p.x != p.x || p.y != p.y) {
+        atomicOr(status, (p.x != p.x || p.y != p.y) ? AOSLO_DEV_NAN : AOSLO_DEV_ESCAPED);
+        return 0.0;
+    }
+    return (double)Rb[(size_t)iy * W + ix];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p, const T* Rb) {
+    cg::grid_group grid = cg::this_grid();
+    const int n = p.d_n ? *p.d_n : p.n_host;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthr = gridDim.x * blockDim.x;
+    __shared__ int s_pending;
+
+    for (int i = tid; i < n; i += nthr) {
+        int from = p.knn_idx[2 * i], to = p.knn_idx[2 * i + 1];
+        double dist = sqrt(p.knn_d2[2 * i + 1]);
+        bool active = (to >= 0) && (from >= 0) && !p.stable[from] && (dist < p.thr);
+        p.rowstate[i] = active ? 1 : 0;
+        p.del[i] = 0;
+        p.touch[i] = 0ull;
+    }
+    if (tid < 3) p.counters[tid] = 0;
+    grid.sync();
+
+    int round = 1;
+    for (;; ++round) {
+        const unsigned long long hi = (unsigned long long)round << 32;
+        for (int i = tid; i < n; i += nthr) {
+            if (p.rowstate[i] != 1) continue;
+            unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            atomicMax(&p.touch[p.knn_idx[2 * i]], key);
+            atomicMax(&p.touch[p.knn_idx[2 * i + 1]], key);
+        }
+        if (tid == 0) p.counters[(round + 1) % 3] = 0;
+        grid.sync();
+        if (threadIdx.x == 0) s_pending = 0;
+        __syncthreads();
+        int pending = 0;
+        for (int i = tid; i < n; i += nthr) {
+            if (p.rowstate[i] != 1) continue;
+            int from = p.knn_idx[2 * i], to = p.knn_idx[2 * i + 1];
+            unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            if (__ldcg(&p.touch[from]) == key && __ldcg(&p.touch[to]) == key) {
+                if (!__ldcg(&p.del[from]) && !__ldcg(&p.del[to])) {
+                    double e1 = energy_at<T>(Rb, p.pos[from], p.W, p.H, p.status);
+                    double e2 = energy_at<T>(Rb, p.pos[to], p.W, p.H, p.status);
+                    p.del[(e1 < e2) ? from : to] = 1;
+                }
+                p.rowstate[i] = 0;
+            } else {
+                ++pending;
+            }
+        }
+        if (pending) atomicAdd(&s_pending, pending);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_pending) atomicAdd(&p.counters[round % 3], s_pending);
+        grid.sync();
+        if (p.counters[round % 3] == 0) break;
+    }
+    if (tid == 0 && p.rounds_out) *p.rounds_out = round;
+}
+
+struct KeepOp {
+    const double2* pos;
+    const uint8_t* stable;
+    const uint8_t* del;
+    double2* pos_out;
+    uint8_t* stable_out;
+    __device__ int value(int i) const { return del[i] ? 0 : 1; }
+    __device__ void emit(int i, int v, int dst) const {
+        if (!v) return;
+        pos_out[dst] = pos[i];
+        stable_out[dst] = stable[i];
+    }
+};
+
+// =======================================================================================
+// pit energy (utils.py:82-87 with scipy.stats written out) and the LUT (utils.py:95-109)
+// =======================================================================================
+__device__ __forceinline__ double energy_pit2(double dist, double mu, double sigma, double lam) {
+    const double kSqrt2Pi = 2.5066282746310002;   // np.sqrt(2 * np.pi)
+    double z = dist - lam;
+    double e = (z >= 0.0) ? exp(-z) : 0.0;        // expon(loc=lam).pdf: 0 left of loc
+    double y = (dist - mu) / sigma;
+    double nrm = exp(-(y * y) / 2.0) / kSqrt2Pi / sigma;
+    return (dist <= mu) ? (e - nrm + 0.48) : (e + nrm - 0.48);
+}
+
+__global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, double* lut) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rfs * rfs) return;
+    int y = i / rfs, x = i - y * rfs;
+    double dx = (double)(x - rfs / 2), dy = (double)(y - rfs / 2);
+    lut[i] = energy_pit2(sqrt(dx * dx + dy * dy), mu, sigma, lam);
+}
+
+// =======================================================================================
+// gravity field (utils.py:310-333) as a per-pixel gather over the cell list
+// =======================================================================================
+constexpr int kGravTile = 32;
+constexpr int kGravList = 1024;
+
+__global__ void __launch_bounds__(kThreads) gravity_field_kernel(CellView cl, const double* __restrict__ lut,
+                                                                int rfs, int H, int W, double* field) {
+    extern __shared__ double s_lut[];                 // rfs*rfs
+    __shared__ int s_px[kGravList], s_py[kGravList];
+    __shared__ int s_row_lo[80], s_row_n[80], s_row_off[81];
+    const int h = rfs / 2;
+    const int x0 = blockIdx.x * kGravTile, y0 = blockIdx.y * kGravTile;
+    for (int i = threadIdx.x; i < rfs * rfs; i += blockDim.x) s_lut[i] = lut[i];
+
+    const int c = 1 << cl.shift;
+    int cx0 = max(x0 - h, 0) >> cl.shift, cx1 = min((min(x0 + kGravTile - 1, W - 1) + h) >> cl.shift, cl.gw - 1);
+    int cy0 = max(y0 - h, 0) >> cl.shift, cy1 = min((min(y0 + kGravTile - 1, H - 1) + h) >> cl.shift, cl.gh - 1);
+    (void)c;
+    int nrows = cy1 - cy0 + 1;                        // <= (32 + 2*32)/4 + 2 < 80 for rfs <= 64, shift >= 1
+    if (threadIdx.x < nrows) {
+        int y = cy0 + threadIdx.x;
+        int a = cl.start[y * cl.gw + cx0], b = cl.start[y * cl.gw + cx1 + 1];
+        s_row_lo[threadIdx.x] = a;
+        s_row_n[threadIdx.x] = b - a;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int r = 0; r < nrows; ++r) { s_row_off[r] = acc; acc += s_row_n[r]; }
+        s_row_off[nrows] = acc;
+    }
+    __syncthreads();
+    const int total = s_row_off[nrows];
+
+    // each thread owns 4 pixels of the 32x32 tile: rows ty, ty+8, ty+16, ty+24
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    double m[4] = {-0.48, -0.48, -0.48, -0.48};
+    const int gx = x0 + tx;
+
+    for (int base = 0; base < total; base += kGravList) {
+        int cnt = min(kGravList, total - base);
+        for (int v = threadIdx.x; v < cnt; v += blockDim.x) {
+            int g = base + v, r = 0;
+            while (g >= s_row_off[r + 1]) ++r;
+            double2 pp = cl.sorted_pos[s_row_lo[r] + (g - s_row_off[r])];
+            s_px[v] = (int)pp.x;                       // int(particle[0]) truncation
+            s_py[v] = (int)pp.y;
+        }
+        __syncthreads();
+        for (int v = 0; v < cnt; ++v) {
+            int dx = gx - s_px[v];
+            if (dx < -h || dx > h) continue;
+            int py = s_py[v];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int dy = (y0 + ty + 8 * u) - py;
+                if (dy >= -h && dy <= h) {
+                    double val = s_lut[(dy + h) * rfs + (dx + h)];
+                    m[u] = (val > m[u]) ? val : m[u];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (gx < W) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int gy = y0 + ty + 8 * u;
+            if (gy < H) field[(size_t)gy * W + gx] = m[u];
+        }
+    }
+}
+
+// =======================================================================================
+// adding particles (utils.py:336-356): first-occurrence row-major argmin per window
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads) window_argmin_kernel(const double* __restrict__ field, int H, int W,
+                                                                int bx, int by, int step, double thr, int nwx,
+                                                                int nwy, int32_t* cand) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwx * nwy) return;
+    int wy = w / nwx, wx = w - wy * nwx;
+    int px = bx + wx * step, py = by + wy * step;
+    int x1 = min(px + step, W), y1 = min(py + step, H);
+    double best = INFINITY;
+    int bxy = -1;
+    bool first = true;
+    for (int y = py; y < y1; ++y)
+        for (int x = px; x < x1; ++x) {
+            double v = field[(size_t)y * W + x];
+            if (first || v < best) { best = v; bxy = y * W + x; first = false; }
+        }
+    cand[w] = (bxy >= 0 && fabs(best) < thr) ? bxy : -1;
+}
+
+struct AppendOp {
+    const int32_t* cand;
+    int W;
+    double2* pos;
+    uint8_t* stable;
+    int cap;
+    int* status;
+    __device__ int value(int w) const { return cand[w] >= 0 ? 1 : 0; }
+    __device__ void emit(int w, int v, int dst) const {
+        if (!v) return;
+        if (dst >= cap) { atomicOr(status, AOSLO_DEV_CAPACITY); return; }
+        int c = cand[w];
+        pos[dst] = make_double2((double)(c % W), (double)(c / W));
+        stable[dst] = 0;
+    }
+};
+
+// =======================================================================================
+// distance force (utils.py:112-134 'pit', :43-58 'exp')
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads) dist_force_kernel(const double2* __restrict__ pos,
+                                                              const uint8_t* __restrict__ stable, int n_host,
+                                                              const int* d_n, const int32_t* __restrict__ knn_idx,
+                                                              int kk /*row stride = k+1*/, int energy_type,
+                                                              double p0, double p1, double p2, double2* force) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double fx = 0.0, fy = 0.0;
+        bool skip = (energy_type == AOSLO_ENERGY_PIT) && stable && stable[i];
+        if (!skip) {
+            double2 p = pos[i];
+            for (int j = 1; j < kk; ++j) {             // column 0 ("self") is dropped, utils.py:32
+                int nb = knn_idx[(size_t)i * kk + j];
+                double2 q = (nb >= 0) ? pos[nb] : make_double2(NAN, NAN);
+                double vx = p.x - q.x, vy = p.y - q.y;
+                double nrm = sqrt(vx * vx + vy * vy);
+                double dx, dy;
+                if (energy_type == AOSLO_ENERGY_PIT) {
+                    double f = energy_pit2(nrm, p0, p1, p2);
+                    dx = (vx / nrm) * f;
+                    dy = (vy / nrm) * f;
+                } else {                                // 'exp': vec / (norm / sigma^2); alpha applied after the sum
+                    double den = nrm / (p1 * p1);
+                    dx = vx / den;
+                    dy = vy / den;
+                }
+                if (j == 1) { fx = dx; fy = dy; } else { fx += dx; fy += dy; }
+            }
+            if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
+        }
+        force[i] = make_double2(fx, fy);
+    }
+}
+
+// =======================================================================================
+// move step (pipeline_with_delitions.py:215-245)
+// =======================================================================================
+__device__ __forceinline__ double np_sign(double v) {
+    if (v > 0.0) return 1.0;
+    if (v < 0.0) return -1.0;
+    return v;   // 0 -> 0, NaN -> NaN
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint8_t* __restrict__ stable,
+                                                        int n_host, const int* d_n, const T* __restrict__ grad,
+                                                        int H, int W, const double2* __restrict__ force,
+                                                        double lb, double ld, int step_mode, int* status) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (stable[i]) continue;
+        double2 p = pos[i];
+        if (p.x != p.x || p.y != p.y) { atomicOr(status, AOSLO_DEV_NAN); continue; }
+        int ix = (int)p.x, iy = (int)p.y;
+        if (ix < 0 || ix >= W || iy < 0 || iy >= H) {   // reference: IndexError / silent negative wrap
+            atomicOr(status, AOSLO_DEV_ESCAPED);
+            continue;
+        }
+        size_t o = ((size_t)iy * W + ix) * 2;
+        double g0 = (double)grad[o], g1 = (double)grad[o + 1];
+        double2 f = force[i];
+        if (step_mode == AOSLO_STEP_CONTIN) {
+            double dy = (-1.0 * lb) * g0 + (-ld) * f.x;
+            double dx = (-1.0 * lb) * g1 + ld * f.y;
+            dy = -dy;
+            p.x += dx;
+            p.y += dy;
+        } else {
+            double delta_y = (-1.0 * lb) * g0 + (-ld) * f.y;
+            double delta_x = (-1.0 * lb) * g1 + ld * f.x;
+            delta_y = -delta_y;
+            double ax = fabs(delta_x), ay = fabs(delta_y);
+            if (ax > ay) {
+                p.x += np_sign(delta_x);
+                if (ax < ay * 2.0) p.y += np_sign(delta_y);
+            } else {
+                p.y += np_sign(delta_y);
+                if (ay < ax * 2.0) p.x += np_sign(delta_x);
+            }
+        }
+        pos[i] = p;
+    }
+}
+
+// =======================================================================================
+// metrics
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads) nn_dist_kernel(CellView cl, const double2* __restrict__ q, int nq_host,
+                                                           const int* d_nq, double* dist_out, int* status) {
+    int nq = d_nq ? *d_nq : nq_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        TopK<1> top;
+        knn_cells_query<1>(cl, q[i].x, q[i].y, top);
+        if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+        dist_out[i] = sqrt(top.d2[0]);
+    }
+}
+
+// deterministic block reduction (fixed tree) of a double
+__device__ __forceinline__ double block_sum(double v, double* sm /*[kScanThreads]*/) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    double r = sm[0];
+    __syncthreads();
+    return r;
+}
+
+// one block: every reduction of one metrics evaluation, in a fixed order
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) metrics_finalize_kernel(
+    const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host, const int* d_n, int n_gt,
+    const double* __restrict__ d_p2g, const double* __restrict__ d_g2p, const T* __restrict__ Rb, int H, int W,
+    int bx, int by, int iteration, aoslo_metrics_record* rec, int* status) {
+    __shared__ double sm[kScanThreads];
+    __shared__ int si[8];
+    const int n = d_n ? *d_n : n_host;
+    const int t = threadIdx.x;
+    if (t < 8) si[t] = 0;
+    __syncthreads();
+    int tp1 = 0, tp2 = 0, fn1 = 0, fn2 = 0, fp1 = 0, fp2 = 0, nin = 0, nst = 0;
+    double s_g = 0.0, s_p = 0.0, s_e = 0.0;
+    for (int j = t; j < n_gt; j += blockDim.x) {
+        double d = d_g2p[j];
+        tp1 += (d <= 1.42); fn1 += (d > 1.42);
+        tp2 += (d <= 2.83); fn2 += (d > 2.83);
+        s_g += d;
+    }
+    for (int i = t; i < n; i += blockDim.x) {
+        double d = d_p2g[i];
+        double2 p = pos[i];
+        bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) && (p.y < (double)(H - by));
+        nin += inside;
+        fp1 += inside && (d > 1.42);
+        fp2 += inside && (d > 2.83);
+        nst += stable[i] ? 1 : 0;
+        s_p += d;
+        s_e += energy_at<T>(Rb, p, W, H, status);
+    }
+    atomicAdd(&si[0], tp1); atomicAdd(&si[1], tp2); atomicAdd(&si[2], fn1); atomicAdd(&si[3], fn2);
+    atomicAdd(&si[4], fp1); atomicAdd(&si[5], fp2); atomicAdd(&si[6], nin); atomicAdd(&si[7], nst);
+    double sum_g = block_sum(s_g, sm);
+    double sum_p = block_sum(s_p, sm);
+    double sum_e = block_sum(s_e, sm);
+    double mean_g = sum_g / (double)n_gt, mean_p = sum_p / (double)n;
+    double v_g = 0.0, v_p = 0.0;
+    for (int j = t; j < n_gt; j += blockDim.x) { double d = d_g2p[j] - mean_g; v_g += d * d; }
+    for (int i = t; i < n; i += blockDim.x) { double d = d_p2g[i] - mean_p; v_p += d * d; }
+    double var_g = block_sum(v_g, sm) / (double)n_gt;
+    double var_p = block_sum(v_p, sm) / (double)n;
+    if (t == 0) {
+        rec->iteration = iteration;
+        rec->n_particles = n;
+        rec->n_stable = si[7];
+        rec->n_gt = n_gt;
+        rec->tp[0] = si[0]; rec->tp[1] = si[1];
+        rec->fn[0] = si[2]; rec->fn[1] = si[3];
+        rec->fp[0] = si[4]; rec->fp[1] = si[5];
+        rec->n_in_image = si[6];
+        rec->pad_ = 0;
+        rec->sum_p2g = sum_p; rec->sum_g2p = sum_g;
+        rec->var_p2g = var_p; rec->var_g2p = var_g;
+        rec->blob_energy_sum = sum_e;
+    }
+}
+
+__global__ void set_all_stable_kernel(uint8_t* stable, int n_host, const int* d_n, uint8_t v) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stable[i] = v;
+}
+
+// count stable flags -> counters[0] (used by the early-stop test, pipeline_with_delitions.py:381)
+__global__ void __launch_bounds__(kScanThreads) count_stable_kernel(const uint8_t* stable, int n_host,
+                                                                    const int* d_n, int* out) {
+    __shared__ int s;
+    if (threadIdx.x == 0) s = 0;
+    __syncthreads();
+    int n = d_n ? *d_n : n_host;
+    int c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c += stable[i] ? 1 : 0;
+    atomicAdd(&s, c);
+    __syncthreads();
+    if (threadIdx.x == 0) *out = s;
+}
+
+// =======================================================================================
+// host-side stage drivers (stream ordered; used by the C ABI wrappers and by aoslo_run)
+// =======================================================================================
+int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
+              int n_query, int k, int tie_mode, int32_t* d_idx, double* d_d2, bool tree_is_particles) {
+    if (tie_mode == AOSLO_TIE_SKLEARN) return knn_sklearn(ctx, s, d_points, n_points, d_query, n_query, k, d_idx, d_d2);
+    CellList& cl = tree_is_particles ? ctx->cl_p : ctx->cl_g;
+    if (n_points > cl.cap) return AOSLO_ERR_CAPACITY;
+    AOSLO_TRY(build_cell_list(ctx, s, cl, d_points, n_points, nullptr));
+    return knn_cells(ctx, s, cl, d_query, n_query, nullptr, k, d_idx, d_d2, n_points, nullptr);
+}
+
+template <typename T>
+int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
+                   const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
+                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out) {
+    if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
+    if (n < 2) return AOSLO_ERR_INVALID;   // sklearn: n_neighbors=2 > n_samples
+    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true));
+    DeleteParams p;
+    p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = nullptr;
+    p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.W = W; p.H = H;
+    p.touch = ctx->d_touch; p.del = ctx->d_del; p.rowstate = ctx->d_rowstate;
+    p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
+    void* args[] = {&p, (void*)&d_Rb};
+    int blocks = ctx->coop_blocks;
+    int need = (n + kThreads - 1) / kThreads;
+    if (need < blocks) blocks = need < 1 ? 1 : need;
+    AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kThreads), args, 0, s));
+    if (d_deleted_out) AOSLO_CUDA(cudaMemcpyAsync(d_deleted_out, ctx->d_del, n, cudaMemcpyDeviceToDevice, s));
+    KeepOp op{(const double2*)d_pos, d_stable, ctx->d_del, (double2*)d_pos_out, d_stable_out};
+    return ordered_scan(ctx, s, op, n, n, nullptr, d_n_out, nullptr, 0, nullptr);
+}
+
+int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
+                 const void* d_Rb, int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out,
+                 uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out) {
+    if (field_dtype == AOSLO_F32)
+        return stage_delete_t<float>(ctx, s, d_pos, d_stable, n, (const float*)d_Rb, H, W, thr, tie_mode, d_pos_out,
+                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out);
+    return stage_delete_t<double>(ctx, s, d_pos, d_stable, n, (const double*)d_Rb, H, W, thr, tie_mode, d_pos_out,
+                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out);
+}
+
+int stage_seed(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
+               double thr, double* d_pos, int cap, int* d_n_out) {
+    int wi = W - 2 * bx, hi = H - 2 * by;
+    if (wi <= 0 || hi <= 0) return AOSLO_ERR_INVALID;
+    int m = wi * hi;
+    if (field_dtype == AOSLO_F32) {
+        SeedOp<float> op{(const float*)d_Rb, W, bx, by, wi, thr, (double2*)d_pos, cap, ctx->d_status};
+        return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr);
+    }
+    SeedOp<double> op{(const double*)d_Rb, W, bx, by, wi, thr, (double2*)d_pos, cap, ctx->d_status};
+    return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr);
+}
+
+int stage_lut(aoslo_ctx*, cudaStream_t s, int rfs, double mu, double sigma, double lam, double* d_lut) {
+    if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
+    dist_lut_kernel<<<(rfs * rfs + 255) / 256, 256, 0, s>>>(rfs, mu, sigma, lam, d_lut);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// requires ctx->cl_p built on the particles
+int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, int H, int W, double* d_field) {
+    if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
+    dim3 grid((W + kGravTile - 1) / kGravTile, (H + kGravTile - 1) / kGravTile);
+    size_t smem = sizeof(double) * rfs * rfs;
+    gravity_field_kernel<<<grid, kThreads, smem, s>>>(view_of(ctx->cl_p), d_lut, rfs, H, W, d_field);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_add(aoslo_ctx* ctx, cudaStream_t s, const double* d_field, int H, int W, int bx, int by, int window,
+              double thr, double* d_pos, uint8_t* d_stable, int n_host, const int* d_n, int cap, int* d_n_out) {
+    if (window < 1) return AOSLO_ERR_INVALID;
+    int nwx = (W - 2 * bx + window - 1) / window, nwy = (H - 2 * by + window - 1) / window;
+    if (nwx <= 0 || nwy <= 0) return AOSLO_ERR_INVALID;
+    int nw = nwx * nwy;
+    window_argmin_kernel<<<(nw + kThreads - 1) / kThreads, kThreads, 0, s>>>(d_field, H, W, bx, by, window, thr,
+                                                                           nwx, nwy, ctx->d_win);
+    AOSLO_LAUNCH_CHECK();
+    AppendOp op{ctx->d_win, W, (double2*)d_pos, d_stable, cap, ctx->d_status};
+    return ordered_scan(ctx, s, op, nw, nw, nullptr, d_n_out, d_n, n_host, nullptr);
+}
+
+int stage_force(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
+                int energy_type, double p0, double p1, double p2, int tie_mode, double* d_force) {
+    if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
+    if (n < k + 1) return AOSLO_ERR_INVALID;
+    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, k + 1, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true));
+    dist_force_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, ctx->d_knn_idx, k + 1,
+                                                   energy_type, p0, p1, p2, (double2*)d_force);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_move(aoslo_ctx* ctx, cudaStream_t s, double* d_pos, const uint8_t* d_stable, int n, const void* d_grad,
+               int field_dtype, int H, int W, const double* d_force, double lb, double ld, int step_mode) {
+    if (field_dtype == AOSLO_F32)
+        move_kernel<float><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, nullptr, (const float*)d_grad, H,
+                                                        W, (const double2*)d_force, lb, ld, step_mode, ctx->d_status);
+    else
+        move_kernel<double><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, nullptr, (const double*)d_grad,
+                                                         H, W, (const double2*)d_force, lb, ld, step_mode,
+                                                         ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// particles cell list must NOT be assumed: builds both lists (GT list can be cached by the caller)
+int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
+                  const double* d_gt, int n_gt, bool gt_list_ready, bool p_list_ready, const void* d_Rb,
+                  int field_dtype, int H, int W, int bx, int by, int iteration, aoslo_metrics_record* d_rec,
+                  double* d_p2g, double* d_g2p) {
+    if (n > ctx->cap || n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
+    if (n < 1 || n_gt < 1) return AOSLO_ERR_INVALID;
+    if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));
+    if (!p_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_pos, n, nullptr));
+    // particle -> nearest GT  ("gt_to_particles" of the reference, :322)
+    nn_dist_kernel<<<ctx->nb, kThreads, 0, s>>>(view_of(ctx->cl_g), (const double2*)d_pos, n, nullptr, d_p2g,
+                                                ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    // GT -> nearest particle  ("particles_to_gt", :323)
+    nn_dist_kernel<<<ctx->nb, kThreads, 0, s>>>(view_of(ctx->cl_p), (const double2*)d_gt, n_gt, nullptr, d_g2p,
+                                                ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    if (field_dtype == AOSLO_F32)
+        metrics_finalize_kernel<float><<<1, kScanThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, n_gt,
+                                                                  d_p2g, d_g2p, (const float*)d_Rb, H, W, bx, by,
+                                                                  iteration, d_rec, ctx->d_status);
+    else
+        metrics_finalize_kernel<double><<<1, kScanThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, n_gt,
+                                                                   d_p2g, d_g2p, (const double*)d_Rb, H, W, bx, by,
+                                                                   iteration, d_rec, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_set_stable(aoslo_ctx* ctx, cudaStream_t s, uint8_t* d_stable, int n, uint8_t v) {
+    set_all_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, nullptr, v);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_count_stable(aoslo_ctx*, cudaStream_t s, const uint8_t* d_stable, int n, int* d_out) {
+    count_stable_kernel<<<1, kScanThreads, 0, s>>>(d_stable, n, nullptr, d_out);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+__global__ void sqrt_inplace_kernel(double* a, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        a[i] = sqrt(a[i]);
+}
+
+int sqrt_inplace(cudaStream_t s, double* a, size_t n) {
+    if (n == 0) return AOSLO_OK;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    sqrt_inplace_kernel<<<blocks, 256, 0, s>>>(a, n);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int coop_blocks_for_delete(int num_sms) {
+    int per_sm_f = 0, per_sm_d = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, delete_resolve_kernel<float>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, delete_resolve_kernel<double>, kThreads, 0);
+    int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    return per_sm * num_sms;
+}
+
+}  // namespace aoslo

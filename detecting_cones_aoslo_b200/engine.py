@@ -1,0 +1,242 @@
+"""Device engine: owns one libaoslo_b200 context and the torch tensors (device memory,
+streams) the stage kernels work on.  PyTorch is plumbing here -- every computation is a
+hand-written sm_100a kernel reached through the C ABI (include/aoslo_b200.h)."""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def gaussian_half_kernel(sigma, truncate=4.0):
+    """scipy.ndimage._filters._gaussian_kernel1d (order 0) -> (half weights w[0..r], r).
+    Parameter set-up only (9 floats for sigma = 1); the convolution runs on the device."""
+    sd = float(sigma)
+    radius = int(truncate * sd + 0.5)
+    sigma2 = sd * sd
+    x = np.arange(-radius, radius + 1)
+    phi_x = np.exp(-0.5 / sigma2 * x ** 2)
+    phi_x = phi_x / phi_x.sum()
+    return phi_x[radius:].astype(np.float64), radius
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("detecting_cones_aoslo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class Engine:
+    """One context per (device, padded image shape, capacities)."""
+
+    def __init__(self, H, W, particle_capacity=None, gt_capacity=65536, device=None):
+        _require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.H, self.W = int(H), int(W)
+        if particle_capacity is None:
+            particle_capacity = self.H * self.W          # seeds can cover every inner pixel
+        self.cap = int(max(2, particle_capacity))
+        self.gt_cap = int(max(1, gt_capacity))
+        h = C.c_void_p()
+        check(lib.aoslo_ctx_create(C.byref(h), self.device.index, self.H, self.W, self.cap, self.gt_cap),
+              "aoslo_ctx_create")
+        self._h = h
+        self._n_out = C.c_int(0)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.aoslo_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    def status(self, clear=True):
+        w = C.c_int(0)
+        check(lib.aoslo_ctx_status(self._h, self._stream(), C.byref(w), 1 if clear else 0), "aoslo_ctx_status")
+        return w.value
+
+    def raise_on_status(self):
+        w = self.status(clear=True)
+        if w:
+            _lib.raise_device_status(w)
+
+    @staticmethod
+    def _fdt(t):
+        if t.dtype == torch.float32:
+            return _lib.F32
+        if t.dtype == torch.float64:
+            return _lib.F64
+        raise TypeError("field must be float32 or float64, got %s" % t.dtype)
+
+    # ------------------------------------------------------------------ L2 field
+    def blobness(self, img_u8, formula='custom', grad_type='np_grad', scales=(1.0,), dtype=torch.float64,
+                 want_grad=True, out=None):
+        """u8 (H,W) device tensor -> (R_b (H,W), grad (H,W,2)) of `dtype`."""
+        if formula == 'div_corrected':
+            raise IndexError("blobness_formula='div_corrected' is broken in the reference "
+                             "(pipeline_with_delitions.py:77, list-of-mask indexing)")
+        if formula not in _lib.FORMULA:
+            raise NotImplementedError
+        if grad_type not in _lib.GRAD:
+            raise AttributeError('grad_type {0} is not implemented'.format(grad_type))
+        assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.dim() == 2
+        H, W = img_u8.shape
+        ns = len(scales)
+        if ns < 1 or ns > _lib.MAX_SCALES:
+            raise ValueError("1..%d scales" % _lib.MAX_SCALES)
+        wts = np.zeros((ns, _lib.MAX_RADIUS + 1), dtype=np.float64)
+        radii = np.zeros(ns, dtype=np.int32)
+        s2 = np.zeros(ns, dtype=np.float64)
+        for i, s in enumerate(scales):
+            w, r = gaussian_half_kernel(s)
+            if r > _lib.MAX_RADIUS:
+                raise NotImplementedError("sigma %.2f needs radius %d > %d" % (s, r, _lib.MAX_RADIUS))
+            wts[i, :r + 1] = w
+            radii[i] = r
+            s2[i] = float(s) * float(s)
+        if out is None:
+            Rb = self.empty((H, W), dtype)
+            grad = self.empty((H, W, 2), dtype) if want_grad else None
+        else:
+            Rb, grad = out
+        check(lib.aoslo_blobness(self._h, self._stream(), self._p(img_u8), H, W, img_u8.stride(0),
+                                 wts.ctypes.data_as(C.POINTER(C.c_double)),
+                                 radii.ctypes.data_as(C.POINTER(C.c_int)),
+                                 s2.ctypes.data_as(C.POINTER(C.c_double)), ns,
+                                 _lib.FORMULA[formula], _lib.GRAD[grad_type], self._fdt(Rb),
+                                 self._p(Rb), self._p(grad)), "aoslo_blobness")
+        return Rb, grad
+
+    def grad_field(self, field, grad_type):
+        if grad_type not in _lib.GRAD:
+            raise AttributeError('grad_type {0} is not implemented'.format(grad_type))
+        H, W = field.shape
+        out = self.empty((H, W, 2), field.dtype)
+        check(lib.aoslo_grad_field(self._h, self._stream(), self._p(field), H, W, _lib.GRAD[grad_type],
+                                   self._fdt(field), self._p(out)), "aoslo_grad_field")
+        return out
+
+    # ------------------------------------------------------------------ L3 particle system
+    def seed(self, Rb, bx, by, threshold):
+        pos = self.empty((self.cap, 2), torch.float64)
+        check(lib.aoslo_seed(self._h, self._stream(), self._p(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by),
+                             float(threshold), self._p(pos), self.cap, C.byref(self._n_out)), "aoslo_seed")
+        return pos[: self._n_out.value]
+
+    def knn(self, points, query, k, tie_mode='canonical'):
+        n, nq = points.shape[0], query.shape[0]
+        if k > n:
+            raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d" % (k, n))
+        idx = self.empty((nq, k), torch.int32)
+        dist = self.empty((nq, k), torch.float64)
+        check(lib.aoslo_knn(self._h, self._stream(), self._p(points), n, self._p(query), nq, int(k),
+                            _lib.TIE[tie_mode], self._p(idx), self._p(dist)), "aoslo_knn")
+        return dist, idx
+
+    def delete_close(self, pos, stable, Rb, threshold, tie_mode='canonical'):
+        n = pos.shape[0]
+        if n < 2:
+            raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = 2, n_samples_fit = %d" % n)
+        pos_out = self.empty((n, 2), torch.float64)
+        st_out = self.empty((n,), torch.uint8)
+        deleted = self.empty((n,), torch.uint8)
+        check(lib.aoslo_delete_close(self._h, self._stream(), self._p(pos), self._p(stable), n, self._p(Rb),
+                                     self._fdt(Rb), self.H, self.W, float(threshold), _lib.TIE[tie_mode],
+                                     self._p(pos_out), self._p(st_out), self._p(deleted), C.byref(self._n_out)),
+              "aoslo_delete_close")
+        m = self._n_out.value
+        return pos_out[:m], st_out[:m], deleted
+
+    def dist_lut(self, rfs, mu, sigma, lambda_):
+        lut = self.empty((rfs, rfs), torch.float64)
+        check(lib.aoslo_dist_lut(self._h, self._stream(), int(rfs), float(mu), float(sigma), float(lambda_),
+                                 self._p(lut)), "aoslo_dist_lut")
+        return lut
+
+    def gravity_field(self, pos, lut):
+        field = self.empty((self.H, self.W), torch.float64)
+        check(lib.aoslo_gravity_field(self._h, self._stream(), self._p(pos), pos.shape[0], self._p(lut),
+                                      lut.shape[0], self.H, self.W, self._p(field)), "aoslo_gravity_field")
+        return field
+
+    def add_particles(self, field, pos, stable, bx, by, window, threshold):
+        if not isinstance(window, (int, np.integer)):
+            # reference: range(..., step) with a float step -> TypeError (utils.py:341)
+            raise TypeError("'%s' object cannot be interpreted as an integer" % type(window).__name__)
+        n = pos.shape[0]
+        nwin = (math.ceil((self.W - 2 * bx) / window)) * (math.ceil((self.H - 2 * by) / window))
+        cap = min(self.cap, n + nwin)
+        pos2 = self.empty((cap, 2), torch.float64)
+        st2 = self.empty((cap,), torch.uint8)
+        pos2[:n] = pos
+        st2[:n] = stable
+        check(lib.aoslo_add_particles(self._h, self._stream(), self._p(field), self.H, self.W, int(bx), int(by),
+                                      int(window), float(threshold), self._p(pos2), self._p(st2), n, cap,
+                                      C.byref(self._n_out)), "aoslo_add_particles")
+        m = self._n_out.value
+        return pos2[:m], st2[:m]
+
+    def dist_force(self, pos, stable, n_neighbours, energy_type, p0, p1, p2=0.0, tie_mode='canonical'):
+        n = pos.shape[0]
+        if n_neighbours + 1 > n:
+            raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d"
+                             % (n_neighbours + 1, n))
+        force = self.empty((n, 2), torch.float64)
+        check(lib.aoslo_dist_force(self._h, self._stream(), self._p(pos), self._p(stable), n, int(n_neighbours),
+                                   _lib.ENERGY[energy_type], float(p0), float(p1), float(p2), _lib.TIE[tie_mode],
+                                   self._p(force)), "aoslo_dist_force")
+        return force
+
+    def move(self, pos, stable, grad, force, lambda_blob, lambda_dist, step_mode):
+        check(lib.aoslo_move(self._h, self._stream(), self._p(pos), self._p(stable), pos.shape[0], self._p(grad),
+                             self._fdt(grad), self.H, self.W, self._p(force), float(lambda_blob), float(lambda_dist),
+                             _lib.STEP[step_mode]), "aoslo_move")
+        return pos
+
+    # ------------------------------------------------------------------ L4 metrics
+    def metrics(self, pos, stable, gt, Rb, bx, by, want_dists=False):
+        n, g = pos.shape[0], gt.shape[0]
+        rec = _lib.MetricsRecord()
+        p2g = self.empty((n,), torch.float64) if want_dists else None
+        g2p = self.empty((g,), torch.float64) if want_dists else None
+        check(lib.aoslo_metrics(self._h, self._stream(), self._p(pos), self._p(stable), n, self._p(gt), g,
+                                self._p(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by), C.byref(rec),
+                                self._p(p2g), self._p(g2p)), "aoslo_metrics")
+        return rec, p2g, g2p
+
+    # ------------------------------------------------------------------ L5 whole run
+    def run(self, cfg_struct, Rb, grad, gt, max_records=None):
+        if max_records is None:
+            max_records = cfg_struct.epoch_num // max(1, cfg_struct.metric_measure_freq) + 2
+        recs = (_lib.MetricsRecord * max_records)()
+        summ = _lib.RunSummary()
+        ms = (C.c_float * 5)()
+        pos = self.empty((self.cap, 2), torch.float64)
+        st = self.empty((self.cap,), torch.uint8)
+        check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._p(Rb), self._p(grad), self._fdt(Rb),
+                            self._p(gt), gt.shape[0], recs, max_records, self._p(pos), self._p(st), C.byref(summ), ms),
+              "aoslo_run")
+        n = summ.n_particles
+        return summ, [recs[i] for i in range(summ.n_records)], pos[:n], st[:n], list(ms)

@@ -1,0 +1,336 @@
+"""GPU parity tests: every stage kernel and the whole run, through the C ABI, against the CPU
+oracle (oracle/aoslo_oracle.py) and the committed traces of the executed reference.
+
+Tolerances (stated per assertion):
+  * integer / index / decision outputs (seeds, kNN indices, deletion masks, particle
+    positions in discrete mode, TP/FP/FN and the ratios derived from them): bit exact;
+  * f64 fields: 5e-14 absolute (CUDA's exp is 1 ulp, R_b ~ 5); f32 fields: 1e-4 of max|ref|
+    (BASELINE.json north_star tolerance);
+  * f64 forces: 1e-13 absolute; Chamfer sums: 1e-12 relative (different summation order).
+"""
+import numpy as np
+import pytest
+import torch
+
+from detecting_cones_aoslo_b200 import configs
+from golden_io import GoldenTrace, load_dataset
+from oracle import aoslo_oracle as orc
+from trace_compare import compare_traces
+
+pytestmark = pytest.mark.gpu
+
+gpu_utils = pytest.importorskip("detecting_cones_aoslo_b200.utils")
+
+
+def _padded(cfg):
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs
+    img, gt = load_dataset()
+    return prepare_inputs(cfg, gt.copy(), img)
+
+
+@pytest.fixture(scope="module")
+def zoo_field():
+    cfg = configs.zoo_config()
+    img, gt = _padded(cfg)
+    Rb = orc.calc_blobness(img, 'custom')
+    grad = orc.calc_grad_field(Rb, 'np_grad')
+    return cfg, img, gt, Rb, grad
+
+
+# ----------------------------------------------------------------------------------- K1 field
+def test_blobness_f64_matches_oracle(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    rb, g = gpu_utils.calc_blobness(img, cfg, return_grad=True)
+    assert rb.dtype == np.float64 and rb.shape == Rb.shape and g.shape == grad.shape
+    assert np.abs(rb - Rb).max() <= 5e-14
+    assert np.abs(g - grad).max() <= 5e-14
+    # decisions derived from the field are identical
+    assert np.array_equal(rb > 5.0, Rb > 5.0)
+
+
+def test_blobness_f32_within_north_star_tolerance(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    rb, g = gpu_utils.calc_blobness(img, cfg, dtype=np.float32, return_grad=True)
+    assert rb.dtype == np.float32
+    assert np.abs(rb - Rb).max() <= 1e-4 * np.abs(Rb).max()
+    assert np.abs(g - grad).max() <= 1e-4 * np.abs(grad).max()
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (64, 64), (2, 2), (33, 2), (130, 97)])
+def test_blobness_ragged_shapes(shape):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                    return_grad=True)
+    assert np.abs(rb - ref).max() <= 5e-14
+    assert np.abs(g - orc.calc_grad_field(ref, 'np_grad')).max() <= 5e-14
+
+
+def test_blobness_sobel_and_simple_div(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'sobel'},
+                                    return_grad=True)
+    assert np.abs(g - orc.calc_grad_field(Rb, 'sobel')).max() <= 2e-13
+    eigs = orc.hessian_eigs(img, 1.0)
+    ref = orc.blobness_from_eigs(eigs, 'simple_div')
+    rb2 = gpu_utils.calc_blobness(img, {'blobness_formula': 'simple_div', 'gradient_type': 'np_grad'})
+    assert np.abs(rb2 - ref).max() <= 1e-12
+    # stand-alone calc_grad_field on an arbitrary field
+    for gt_ in ('np_grad', 'sobel'):
+        assert np.abs(gpu_utils.calc_grad_field(Rb, gt_) - orc.calc_grad_field(Rb, gt_)).max() <= 2e-13
+
+
+def test_blobness_multiscale_extension(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    scales = (1.0, 1.5, 2.0, 2.5, 3.0)
+    ref = orc.calc_blobness(img, 'custom', scales)
+    rb = gpu_utils.calc_blobness(img, cfg, scales=scales)
+    assert np.abs(rb - ref).max() <= 1e-12
+    rb32 = gpu_utils.calc_blobness(img, cfg, scales=scales, dtype=np.float32)
+    assert np.abs(rb32 - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_errors_match_reference():
+    img = np.zeros((32, 32), np.uint8)          # flat patch: e0 == e1 -> the reference's assert fires
+    with pytest.raises(AssertionError):
+        gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'})
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(32, 32), dtype=np.uint8)
+    with pytest.raises(AttributeError):
+        gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'nope'})
+    with pytest.raises(NotImplementedError):
+        gpu_utils.calc_blobness(img, {'blobness_formula': 'nope', 'gradient_type': 'np_grad'})
+    with pytest.raises(IndexError):
+        gpu_utils.calc_blobness(img, {'blobness_formula': 'div_corrected', 'gradient_type': 'np_grad'})
+    with pytest.raises(AttributeError):
+        gpu_utils.calc_grad_field(np.zeros((8, 8)), 'nope')
+
+
+# ----------------------------------------------------------------------------------- seeds
+@pytest.mark.parametrize("thr", [4.95, 5.0, 5.01])
+def test_seeds_exact(zoo_field, thr):
+    cfg, img, gt, Rb, grad = zoo_field
+    ref = orc.initialize_high_prop_location(Rb, thr, img.shape, cfg)
+    got = gpu_utils.initialize_high_prop_location(Rb, thr, img.shape, cfg)
+    assert got.dtype == np.int64
+    np.testing.assert_array_equal(got, ref)
+
+
+# ----------------------------------------------------------------------------------- kNN
+def _lattice(rng, n, span):
+    p = np.unique(rng.integers(0, span, size=(n * 2, 2)), axis=0)
+    rng.shuffle(p)
+    return p[:n].astype(np.float64)
+
+
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+@pytest.mark.parametrize("n,k", [(5, 2), (64, 1), (283, 2), (1000, 4), (5000, 7), (20000, 4)])
+def test_knn_lattice_ties_exact(tie_mode, n, k):
+    rng = np.random.default_rng(n + k)
+    pts = _lattice(rng, n, max(4, int(np.sqrt(n) * 2.2)))
+    n = pts.shape[0]
+    qry = np.vstack([pts, _lattice(rng, max(3, n // 3), max(4, int(np.sqrt(n) * 2.2)))])
+    d_ref, i_ref = orc.knn(pts, qry, k, tie_mode)
+    d, i = gpu_utils.calc_dist_to_neares(pts, qry, n_neighbours=k, return_indexes=True, tie_mode=tie_mode)
+    np.testing.assert_array_equal(i, i_ref)
+    np.testing.assert_array_equal(d, d_ref)         # sqrt of exact integer d^2: bit exact
+
+
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+def test_knn_continuous_and_duplicates(tie_mode):
+    rng = np.random.default_rng(3)
+    pts = rng.random((3000, 2)) * 200
+    pts[50:60] = pts[0:10]                          # coincident points (zero distances)
+    d_ref, i_ref = orc.knn(pts, pts, 4, tie_mode)
+    d, i = gpu_utils.calc_dist_to_neares(pts, pts, n_neighbours=4, return_indexes=True, tie_mode=tie_mode)
+    np.testing.assert_array_equal(i, i_ref)
+    np.testing.assert_allclose(d, d_ref, rtol=0, atol=1e-13)
+
+
+def test_knn_too_few_points():
+    pts = np.array([[1., 1.], [3., 4.]])
+    with pytest.raises(ValueError):
+        gpu_utils.calc_dist_to_neares(pts, pts, n_neighbours=3, return_indexes=True)
+
+
+# ----------------------------------------------------------------------------------- deletion
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+def test_delete_close_matches_oracle_until_fixpoint(zoo_field, tie_mode):
+    cfg, img, gt, Rb, grad = zoo_field
+    p = orc.initialize_high_prop_location(Rb, 5.0, img.shape, cfg).astype(np.float64)
+    st = [0] * p.shape[0]
+    rounds = 0
+    while True:
+        ref_p, ref_del, ref_st = orc.del_close_particles(p, st, Rb, cfg, threshold_dist=3, tie_mode=tie_mode)
+        got_p, got_del, got_st = gpu_utils.del_close_particles(p, st, Rb, cfg, threshold_dist=3, tie_mode=tie_mode)
+        np.testing.assert_array_equal(np.array([got_del[i] for i in range(len(got_del))]), ref_del)
+        np.testing.assert_array_equal(got_p, ref_p)
+        assert got_st == ref_st
+        rounds += 1
+        if ref_del.sum() == 0:
+            break
+        p, st = ref_p, ref_st
+    assert rounds >= 3
+    if tie_mode == 'sklearn':
+        assert p.shape[0] == 5521                   # golden of the executed reference
+
+
+def test_delete_close_stable_particles(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    rng = np.random.default_rng(5)
+    p = _lattice(rng, 6000, 500) + 20.0
+    st = list((rng.random(p.shape[0]) < 0.5).astype(int))
+    for tie_mode in ("canonical", "sklearn"):
+        ref_p, ref_del, ref_st = orc.del_close_particles(p, st, Rb, cfg, threshold_dist=3.5, tie_mode=tie_mode)
+        got_p, got_del, got_st = gpu_utils.del_close_particles(p, st, Rb, cfg, threshold_dist=3.5, tie_mode=tie_mode)
+        np.testing.assert_array_equal(got_p, ref_p)
+        assert got_st == ref_st
+        assert ref_del.sum() > 100
+
+
+# ----------------------------------------------------------------------------------- resampling
+def test_lut_gravity_adding_match_oracle(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    lut_ref = orc.get_precomputed_dist_func(cfg)
+    lut = gpu_utils.get_precomputed_dist_func(cfg)
+    assert np.abs(lut - lut_ref).max() <= 5e-16
+    gold = GoldenTrace("zoo")
+    g0 = gold.of("gravity")[0]
+    particles = np.asarray(g0["particles"], dtype=np.float64)
+    field_ref = orc.calc_gravity_field_optim(lut_ref, img.shape, particles, cfg)
+    field = gpu_utils.calc_gravity_field_optim(lut_ref, img.shape, particles, cfg)
+    np.testing.assert_array_equal(field, field_ref)          # a max of LUT entries: exact
+    # particles stamped partly outside the image (window clipping, utils.py:316-324)
+    edge = np.array([[0., 0.], [img.shape[1] - 1., img.shape[0] - 1.], [3., img.shape[0] - 2.], [200.5, 100.9]])
+    np.testing.assert_array_equal(gpu_utils.calc_gravity_field_optim(lut_ref, img.shape, edge, cfg),
+                                  orc.calc_gravity_field_optim(lut_ref, img.shape, edge, cfg))
+    st = [1] * particles.shape[0]
+    for window, thr in ((5, 0.3), (9, 0.1), (7, 0.15)):
+        c2 = configs.variant(cfg, particle_call_window=window, particle_call_threshold=thr)
+        ref_p, ref_s = orc.adding_particles(particles, st, field_ref, img.shape, c2)
+        got_p, got_s = gpu_utils.adding_particles(particles, st, field_ref, img.shape, c2)
+        np.testing.assert_array_equal(got_p, ref_p)
+        assert got_s == ref_s
+    with pytest.raises(TypeError):                           # float window crashes the reference too
+        gpu_utils.adding_particles(particles, st, field_ref, img.shape,
+                                   configs.variant(cfg, particle_call_window=5.5))
+
+
+# ----------------------------------------------------------------------------------- force / move
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+@pytest.mark.parametrize("k", [1, 3, 6])
+def test_force_and_move_match_oracle(zoo_field, tie_mode, k):
+    cfg, img, gt, Rb, grad = zoo_field
+    gold = GoldenTrace("zoo")
+    a0 = gold.of("adding")[0]
+    p = np.asarray(a0["particles_out"], dtype=np.float64)
+    st = list(np.asarray(a0["stable_out"]).astype(int))
+    f_ref, m_ref = orc.calc_dist_energy_pit_optim(p, st, k, 5.84, 0.83, -0.1, tie_mode=tie_mode)
+    f, m = gpu_utils.calc_dist_energy_pit_optim(p, st, k, 5.84, 0.83, -0.1, tie_mode=tie_mode)
+    assert np.abs(f - f_ref).max() <= 1e-13
+    fe_ref, _ = orc.calc_dist_energy(p, k, 0.3, 0.3, tie_mode=tie_mode)
+    fe, _ = gpu_utils.calc_dist_energy(p, k, 0.3, 0.3, tie_mode=tie_mode)
+    assert np.abs(fe - fe_ref).max() <= 1e-13
+    for step_mode in ("discrete", "contin"):
+        c2 = configs.variant(cfg, step_mode=step_mode)
+        ref = orc.move_particles(p.copy(), st, grad, f_ref, c2)
+        got = gpu_utils.move_particles(p.copy(), st, grad, f_ref, c2)
+        if step_mode == "discrete":
+            np.testing.assert_array_equal(got, ref)
+        else:
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13)
+
+
+# ----------------------------------------------------------------------------------- metrics
+def test_metrics_bit_exact_counts(zoo_field):
+    cfg, img, gt, Rb, grad = zoo_field
+    gold = GoldenTrace("zoo")
+    for a in gold.of("acc"):
+        p = np.asarray(a["particles"], dtype=np.float64)
+        pm, lsa_sum, lsa_mean, lsa_var, blob_mean = gpu_utils.detection_metrics(p, gt, Rb, cfg)
+        for t in ("1", "2"):
+            for key in ("TP", "FP", "FN"):
+                assert int(pm[t][key]) == a["metrics"][t][key]
+            for key in ("dice", "precision", "recall"):
+                assert float(pm[t][key]) == a["metrics"][t][key]      # bit exact: same integers, same formula
+        g2p = orc.calc_dist_to_neares(gt, p)
+        p2g = orc.calc_dist_to_neares(p, gt)
+        _, s, m, v = orc.calc_metrics(p, gt, g2p, p2g, mode='Chamfer')
+        np.testing.assert_allclose([lsa_sum, lsa_mean, lsa_var], [s, m, v], rtol=1e-12)
+        np.testing.assert_allclose(blob_mean, np.mean(orc.calc_blob_energy(Rb, p)), rtol=1e-13)
+
+
+# ----------------------------------------------------------------------------------- whole run
+STAGED = {
+    "main": configs.main_config,
+    "main_sobel": lambda: configs.variant(configs.main_config(), gradient_type="sobel", lambda_blob=1.),
+    "main_contin": lambda: configs.variant(configs.main_config(), step_mode="contin", lambda_blob=1.),
+    "main_exp": lambda: configs.variant(configs.main_config(), dist_energy_type="exp"),
+    "main_k3": lambda: configs.variant(configs.main_config(), dist_n_neighbours=3, lambda_blob=1., lambda_dist=0.1),
+    "zoo": configs.zoo_config,
+    "full_b10": configs.full_b10_config,
+    "sweep_like": configs.sweep_like_config,
+}
+
+
+@pytest.mark.parametrize("name", list(STAGED))
+def test_find_blobs_replays_reference_trace(name):
+    """The GPU run, stage by stage, against the trace of the EXECUTED REFERENCE (sklearn tie order):
+    identical seeds, deletion decisions, particle positions, counts and TP/FP/FN at every step."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs, Trace
+    img, gt = load_dataset()
+    gold = GoldenTrace(name)
+    tr = Trace()
+    cfg = STAGED[name]()
+    result, ts = find_blobs(cfg, gt.copy(), img, None, False, False, trace=tr)
+    compare_traces(gold.events, tr.events, stride=gold.stride, field_tol=5e-14, force_tol=1e-13, label=name)
+    for key in ("dice_coeff_1", "dice_coeff_2"):
+        assert result[key] == gold.result[key]
+    np.testing.assert_allclose(result["best_lsa_mean"], gold.result["best_lsa_mean"], rtol=1e-12)
+    np.testing.assert_allclose(result["best_blobEn_mean"], gold.result["best_blobEn_mean"], rtol=1e-13)
+    assert set(ts) == {'dist_energy_calc', 'moving_particles', 'deleting_particles', 'fix_resample',
+                       'metrics_logging'}
+
+
+@pytest.mark.parametrize("tie_mode", ["sklearn", "canonical"])
+@pytest.mark.parametrize("name", ["main", "zoo", "sweep_like"])
+def test_find_blobs_fused_matches_oracle(name, tie_mode):
+    """aoslo_run (one C-ABI call for the whole loop) against the oracle in the same tie mode."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    cfg = STAGED[name]()
+    cfg['tie_mode'] = tie_mode
+    ref, _ = orc.find_blobs(dict(cfg), gt.copy(), img, None, False, False, tie_mode=tie_mode)
+    res, ts = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    got = res["_final_particles"].cpu().numpy()
+    np.testing.assert_array_equal(got, ref["final_particles"])
+    np.testing.assert_array_equal(res["_final_stable"].cpu().numpy(), ref["final_stable"])
+    assert res["_summary"]["n_iterations"] == ref["n_iterations"]
+    for key in ("dice_coeff_1", "dice_coeff_2"):
+        assert res[key] == ref[key]
+    np.testing.assert_allclose(res["best_lsa_mean"], ref["best_lsa_mean"], rtol=1e-12)
+    np.testing.assert_allclose(res["best_blobEn_mean"], ref["best_blobEn_mean"], rtol=1e-13)
+
+
+def test_find_blobs_published_f1_on_shipped_image():
+    """Reference-equivalent F1 on the shipped annotated image (BASELINE.md goldens)."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    res, _ = find_blobs(configs.zoo_config(), gt.copy(), img, None, False, False)
+    assert res["dice_coeff_2"] == 0.9343206696716033
+    assert res["dice_coeff_1"] == 0.833386591678916
+    assert res["_summary"]["n_seeds"] == 31876
+    assert res["_summary"]["n_after_thinning"] == 5521
+
+
+def test_find_blobs_mutates_gt_like_reference_and_f32_mode():
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    g = gt.copy()
+    cfg = configs.main_config()
+    find_blobs(cfg, g, img, None, False, False)
+    np.testing.assert_array_equal(g, gt - 1.0)             # GT shifted by -1 in place (utils.py:16)
+    cfg32 = configs.variant(configs.zoo_config(), field_dtype='f32', tie_mode='canonical')
+    res, _ = find_blobs(cfg32, gt.copy(), img, None, False, False)
+    assert abs(res["dice_coeff_2"] - 0.9343) < 0.01         # f32 fields: statistically equivalent F1
