@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""bench.py -- detection runs/s of the full `find_blobs` pipeline on a synthetic 2048^2 AOSLO frame.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = `--batch` whole detection runs (blobness field + gradient, seeding, thinning, resampling,
+M move/delete iterations, metrics), each on its own synthetic frame, run concurrently on one GPU
+(one CUDA stream + scratch context per frame -- frames / sweep trials are independent).
+Per-GPU work is fixed as N grows (weak scaling); the only collective is one NCCL all-gather of the
+per-run metric records at the end of the timed region.  The single-run latency is reported too.
+
+value     runs/s with the frame and GT already resident in HBM (timed: aoslo_blobness + aoslo_run)
+e2e       runs/s through the reference-facing entry point find_blobs(cur_config, GT_data, img, ...)
+          with HOST NumPy buffers: crop/pad on the host, host->device copies and the device->host
+          read of the metric records are inside the timed region
+roofline  the fused blobness kernel (K1), the HBM-bound kernel of the path, timed inside the timed
+          region with CUDA events on its launch stream, against MEASURED_PEAKS.json
+cpu_baseline / --impl reference
+          the CPU oracle (port of the reference's NumPy/SciPy/scikit-learn pipeline; the reference
+          is Python and cannot travel to the GPU box) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SIZE = 2048
+PITCH = 5.8
+EPOCHS = 30
+BOUNDARY = 15
+SAMPLE = 1024           # edge of the CPU baseline's bounded sample (a crop of the same frame)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def workload_name():
+    return ("synthetic %dx%d AOSLO-like cone lattice (pitch %.1f px, seed 2022+rank), config_zoo, boundary %d, "
+            "k=3, M=%d iterations (early stop off), f64 fields, canonical tie order"
+            % (SIZE, SIZE, PITCH, BOUNDARY, EPOCHS))
+
+
+def make_workload(rank, size=SIZE):
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = synth_aoslo(size, size, PITCH, seed=2022 + rank)
+    cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS, early_stop=False,
+                       tie_mode='canonical', field_dtype='f64')
+    return img, gt, cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_sample_run(size=SAMPLE, epochs=EPOCHS):
+    """One oracle run on the bounded sample: the top-left size x size crop of rank 0's frame."""
+    from oracle import aoslo_oracle as orc
+    from detecting_cones_aoslo_b200.synth import synth_config
+    img, gt, _ = make_workload(0)
+    img = np.ascontiguousarray(img[:size, :size])
+    gt = gt[(gt[:, 0] < size) & (gt[:, 1] < size)].copy()
+    cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=epochs)
+    t = time.perf_counter()
+    res, _ = orc.find_blobs(cfg, gt, img, None, False, False, tie_mode='sklearn', early_stop=False)
+    return time.perf_counter() - t, res
+
+
+def _cpu_worker(_):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    return cpu_sample_run()[0]
+
+
+def cpu_baseline(processes=1):
+    """runs/s of the CPU oracle, scaled from the sample by pixel count ((SIZE/SAMPLE)^2 samples per run)."""
+    scale = (SIZE / SAMPLE) ** 2
+    if processes <= 1:
+        dt = cpu_sample_run()[0]
+        runs_per_s = 1.0 / (dt * scale)
+    else:
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        t = time.perf_counter()
+        with ctx.Pool(processes) as pool:
+            pool.map(_cpu_worker, range(processes))
+        wall = time.perf_counter() - t
+        dt = wall
+        runs_per_s = processes / (wall * scale)
+    return {"value": runs_per_s, "unit": "runs/s", "cores": processes, "kind": "port",
+            "sample": "CPU oracle (NumPy/SciPy/scikit-learn port of the reference, sklearn KD-tree kNN) on the "
+                      "%dx%d top-left crop of the %dx%d frame, same config, M=%d; %.1f s per sample%s, runs/s = "
+                      "1 / (t * %d) by pixel count" % (SAMPLE, SAMPLE, SIZE, SIZE, EPOCHS, dt,
+                                                      " wall for %d concurrent processes" % processes
+                                                      if processes > 1 else "", int(scale)),
+            "seconds_per_sample": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = max(1, min(os.cpu_count() or 1, 16))
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(1, args.warmup) if args.warmup < 1 else 0):
+        pass
+    steps = max(1, min(args.steps, 2))          # each step is a bounded CPU sample; keep the arm to minutes
+    base = None
+    for _ in range(steps):
+        base = cpu_baseline(processes=procs)
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "detection runs/s (full pipeline, 2048^2 image)", "value": v,
+        "unit": "runs/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": 1e3 / v * procs, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(), "l2": "n/a (CPU arm)"},
+        "cpu_baseline": dict(base, value=v),
+        "e2e": {"value": v, "unit": "runs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class Lane:
+    """One concurrent detection lane: its own synthetic frame, context (scratch) and CUDA stream."""
+
+    def __init__(self, frame_seed_index, dev):
+        import torch
+        from detecting_cones_aoslo_b200.engine import Engine
+        from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs, make_config_struct
+        self.torch = torch
+        self.img, self.gt, self.cfg = make_workload(frame_seed_index)
+        pimg, pgt = prepare_inputs(self.cfg, self.gt.copy(), self.img)
+        self.H, self.W = pimg.shape
+        self.h2d = pimg.nbytes + pgt.nbytes
+        self.eng = Engine(self.H, self.W, particle_capacity=self.H * self.W, gt_capacity=max(65536, pgt.shape[0]),
+                          device=dev.index)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.d_img = self.eng.upload_image(pimg)
+        self.d_gt = self.eng.dev(pgt, torch.float64)
+        self.cs = make_config_struct(self.cfg, self.H, self.W)
+        self.Rb = self.eng.empty((self.H, self.W), torch.float64)
+        self.grad = self.eng.empty((self.H, self.W, 2), torch.float64)
+        self.n_gt = int(pgt.shape[0])
+        self.k1_events = []
+        self.last = None
+
+    def run_resident(self, time_k1=False):
+        """frame + GT resident in HBM: aoslo_blobness + aoslo_run (the whole loop)."""
+        from detecting_cones_aoslo_b200 import _lib
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            if time_k1:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self.eng.blobness(self.d_img, self.cfg['blobness_formula'], self.cfg['gradient_type'], (1.0,),
+                              torch.float64, out=(self.Rb, self.grad))
+            if time_k1:
+                e1.record()
+                self.k1_events.append((e0, e1))
+            summ, recs, pos, st, ms = self.eng.run(self.cs, self.Rb, self.grad, self.d_gt)
+        if summ.status:
+            _lib.raise_device_status(summ.status)
+        self.last = (summ, recs, ms)
+        return summ
+
+    def run_e2e(self):
+        """the reference-facing call with HOST buffers (crop/pad, H2D, run, D2H of the records)."""
+        from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+        with self.torch.cuda.stream(self.stream):
+            res, _ = find_blobs(dict(self.cfg), self.gt.copy(), self.img, None, False, False, engine=self.eng)
+        return res
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from concurrent.futures import ThreadPoolExecutor
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from detecting_cones_aoslo_b200 import _lib
+    from detecting_cones_aoslo_b200.utils import metrics_from_record
+
+    B = max(1, args.batch)
+    lanes = [Lane(rank * B + j, dev) for j in range(B)]
+    H, W = lanes[0].H, lanes[0].W
+    pool = ThreadPoolExecutor(max_workers=B)
+    main = torch.cuda.current_stream()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def evict_l2():
+        """Evict L2 (256 MiB write) and park the GPU ~150 us so the host runs ahead of the device:
+        the events then bracket device work, not Python launch latency.  Untimed."""
+        flush.fill_(1)
+        torch.cuda._sleep(300000)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_step(fn, active):
+        """one step = every active lane once, concurrently; returns device ms (CUDA events on `main`,
+        lane streams forked from / joined to it)."""
+        evict_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for ln in active:
+            ln.stream.wait_event(e0)
+        if len(active) == 1:
+            fn(active[0])
+        else:
+            for f in [pool.submit(fn, ln) for ln in active]:
+                f.result()
+        for ln in active:
+            d = torch.cuda.Event()
+            d.record(ln.stream)
+            main.wait_event(d)
+        e1.record(main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- warm-up (all lanes), then the throughput pass: K steps of B concurrent runs
+    for _ in range(args.warmup):
+        timed_step(lambda ln: ln.run_resident(), lanes)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.lib.aoslo_launch_count()
+    step_ms = [timed_step(lambda ln: ln.run_resident(), lanes) for _ in range(args.steps)]
+    # the sweep's only exchange: all-gather of the per-run metric records (tiny, latency only)
+    rows = []
+    for ln in lanes:
+        summ, recs, _ms = ln.last
+        pm, lsa_sum, lsa_mean, lsa_var, blob_mean = metrics_from_record(recs[-1])
+        rows.append([rank, summ.n_particles, summ.n_iterations, float(pm['1']['dice']), float(pm['2']['dice']),
+                     lsa_mean, blob_mean, summ.n_seeds])
+    rec_t = torch.tensor(rows, dtype=torch.float64, device=dev)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    if world > 1:
+        gathered = [torch.zeros_like(rec_t) for _ in range(world)]
+        dist.all_gather(gathered, rec_t)
+    else:
+        gathered = [rec_t]
+    g1.record()
+    barrier()
+    launches = _lib.lib.aoslo_launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = float(sum(step_ms)) + g0.elapsed_time(g1)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    value = world * args.steps * B / (total_ms / 1e3)
+
+    # ---- latency pass: one lane alone (single stream), K1 timed inside the step
+    lane0 = lanes[0]
+    for _ in range(2):
+        timed_step(lambda ln: ln.run_resident(), [lane0])
+    lane0.k1_events.clear()
+    lat_ms = [timed_step(lambda ln: ln.run_resident(time_k1=True), [lane0]) for _ in range(args.steps)]
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in lane0.k1_events]))
+    latency_ms = float(np.mean(lat_ms))
+    summ, recs, stage_ms = lane0.last
+
+    # ---- end to end through the reference-facing entry point, HOST buffers in, records out
+    for _ in range(min(2, args.warmup)):
+        timed_step(lambda ln: ln.run_e2e(), lanes)
+    barrier()
+    e2e_ms = [timed_step(lambda ln: ln.run_e2e(), lanes) for _ in range(args.steps)]
+    te = torch.tensor([float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * B / (float(te.item()) / 1e3)
+    e2e_lat = [timed_step(lambda ln: ln.run_e2e(), [lane0]) for _ in range(args.steps)]
+    d2h = summ.n_records * 88 + 32 + 4
+
+    # ---- blobness MPix/s (second half of BASELINE.json's metric): K1 alone, f32 fields, L2 flushed
+    eng = lane0.eng
+    Rb32 = eng.empty((H, W), torch.float32)
+    g32 = eng.empty((H, W, 2), torch.float32)
+    f32_ms = []
+    for i in range(3 + 10):
+        evict_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng.blobness(lane0.d_img, 'custom', 'np_grad', (1.0,), torch.float32, out=(Rb32, g32))
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            f32_ms.append(a.elapsed_time(b))
+    k1_f32_ms = float(np.mean(f32_ms))
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        bytes_f64 = 25.0 * H * W                       # 1 B u8 in + 8 B R_b + 16 B grad out per pixel
+        ach = bytes_f64 / (k1_ms / 1e3) / 1e9
+        line = {
+            "metric": "detection runs/s (full pipeline, 2048^2 image)", "value": value, "unit": "runs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(), "batch": B,
+                       "step": "one step = %d frames run concurrently (one CUDA stream + context each)" % B,
+                       "padded_shape": [H, W], "n_gt": lane0.n_gt,
+                       "n_particles_final": int(summ.n_particles), "n_seeds": int(summ.n_seeds),
+                       "iterations": int(summ.n_iterations), "thinning_rounds": int(summ.n_thinning_rounds),
+                       "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "parallelism": "one frame per lane, %d lanes per rank, NCCL all-gather of metric records" % B},
+            "clocks": clocks,
+            "latency_ms_single_run": latency_ms,
+            "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": int(lane0.h2d * B),
+                    "d2h_bytes_per_step": int(d2h * B), "latency_ms_single_run": float(np.mean(e2e_lat))},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "blobness_kernel<double> (K1, fused Hessian/eig/blobness/gradient)",
+                         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_f64, "ms_per_launch": k1_ms,
+                         "share_of_step": k1_ms / latency_ms,
+                         "timed": "CUDA events on the launch stream inside the single-lane latency pass"},
+            "blobness_mpix_s": {"f32": H * W / (k1_f32_ms / 1e3) / 1e6, "f64": H * W / (k1_ms / 1e3) / 1e6,
+                                "f32_ms": k1_f32_ms, "f32_gbs": 13.0 * H * W / (k1_f32_ms / 1e3) / 1e9,
+                                "f32_frac_of_hbm_peak": 13.0 * H * W / (k1_f32_ms / 1e3) / 1e9 / peak},
+            "stage_ms_single_run": dict(zip(['dist_energy_calc', 'moving_particles', 'deleting_particles',
+                                             'fix_resample', 'metrics_logging'], [float(x) for x in stage_ms])),
+            "last_run": {"dice_1": float(gathered[0][0][3]), "dice_2": float(gathered[0][0][4])},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(processes=1)
+        print(json.dumps(line))
+    pool.shutdown()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="frames run concurrently per step (lanes per GPU)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -66,6 +66,7 @@ SYMBOLS = {
     "aoslo_version": (C.c_char_p, []),
     "aoslo_last_cuda_error": (C.c_char_p, []),
     "aoslo_device_count": (_i, []),
+    "aoslo_launch_count": (C.c_longlong, []),
     "aoslo_ctx_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "aoslo_ctx_destroy": (_i, [_vp]),
     "aoslo_ctx_status": (_i, [_vp, _vp, _ip, _i]),

@@ -1,15 +1,20 @@
 // api.cu -- context management, the C ABI wrappers of the stage kernels and the whole-run
 // driver `aoslo_run` (reference pipeline_with_delitions.py:12-403 after crop / pad).
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
 namespace aoslo {
 
 static thread_local char g_last_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -17,23 +22,24 @@ int set_cuda_error(cudaError_t e, const char* where) {
     return AOSLO_ERR_CUDA;
 }
 
-// stage drivers defined in particles.cu
-int stage_knn(aoslo_ctx*, cudaStream_t, const double*, int, const double*, int, int, int, int32_t*, double*, bool);
+// stage drivers defined in particles.cu (trailing d_n: optional device-resident particle count)
+int stage_knn(aoslo_ctx*, cudaStream_t, const double*, int, const double*, int, int, int, int32_t*, double*, bool,
+              const int* d_n);
 int stage_delete(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, const void*, int, int, int, double, int,
-                 double*, uint8_t*, uint8_t*, int*, int*);
+                 double*, uint8_t*, uint8_t*, int*, int*, const int* d_n);
 int stage_seed(aoslo_ctx*, cudaStream_t, const void*, int, int, int, int, int, double, double*, int, int*);
 int stage_lut(aoslo_ctx*, cudaStream_t, int, double, double, double, double*);
-int stage_gravity(aoslo_ctx*, cudaStream_t, const double*, int, int, int, double*);
+int stage_gravity(aoslo_ctx*, cudaStream_t, const double*, int, int, int, double*, bool packed_ready);
 int stage_add(aoslo_ctx*, cudaStream_t, const double*, int, int, int, int, int, double, double*, uint8_t*, int,
               const int*, int, int*);
 int stage_force(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, int, int, double, double, double, int,
-                double*);
+                double*, const int* d_n);
 int stage_move(aoslo_ctx*, cudaStream_t, double*, const uint8_t*, int, const void*, int, int, int, const double*,
-               double, double, int);
+               double, double, int, const int* d_n);
 int stage_metrics(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, const double*, int, bool, bool,
-                  const void*, int, int, int, int, int, int, aoslo_metrics_record*, double*, double*);
-int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t*, int, uint8_t);
-int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int*);
+                  const void*, int, int, int, int, int, int, aoslo_metrics_record*, double*, double*, const int* d_n);
+int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t*, int, uint8_t, const int* d_n);
+int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int*, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
 int sqrt_inplace(cudaStream_t, double*, size_t);
 
@@ -56,8 +62,30 @@ static int alloc_cell_list(CellList& cl, int H, int W, int cap, int shift) {
     AOSLO_TRY(dmalloc(&cl.sorted_idx, cap));
     AOSLO_TRY(dmalloc(&cl.sorted_pos, cap));
     AOSLO_CUDA(cudaMemset(cl.start, 0, sizeof(int) * (cl.ncell + 1)));
+    AOSLO_CUDA(cudaMemset(cl.count, 0, sizeof(int) * cl.ncell));
     return AOSLO_OK;
 }
+
+}  // namespace aoslo
+// device + pinned-host mirrors of the sklearn-order KD tree; only the sklearn tie mode needs them
+int aoslo::kd_reserve(aoslo_ctx* c) {
+    KdTreeDev& kd = c->kd;
+    if (kd.cap >= c->cap) return AOSLO_OK;
+    int cap = c->cap;
+    size_t nn = (size_t)2 * cap + 2;
+    AOSLO_TRY(dmalloc(&kd.idx_array, cap));
+    AOSLO_TRY(dmalloc(&kd.node_start, nn));
+    AOSLO_TRY(dmalloc(&kd.node_end, nn));
+    AOSLO_TRY(dmalloc(&kd.node_bounds, nn * 4));
+    AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_points, sizeof(double) * 2 * cap, cudaHostAllocDefault));
+    AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_idx_array, sizeof(int32_t) * cap, cudaHostAllocDefault));
+    AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_node_start, sizeof(int32_t) * nn, cudaHostAllocDefault));
+    AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_node_end, sizeof(int32_t) * nn, cudaHostAllocDefault));
+    AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_node_bounds, sizeof(double) * 4 * nn, cudaHostAllocDefault));
+    kd.cap = cap;
+    return AOSLO_OK;
+}
+namespace aoslo {
 
 static void free_cell_list(CellList& cl) {
     cudaFree(cl.count); cudaFree(cl.start); cudaFree(cl.slot); cudaFree(cl.cell_of);
@@ -78,6 +106,7 @@ using namespace aoslo;
 
 extern "C" const char* aoslo_version(void) { return "aoslo_b200 0.1 (sm_100a)"; }
 extern "C" const char* aoslo_last_cuda_error(void) { return g_last_err; }
+extern "C" long long aoslo_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int aoslo_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -123,29 +152,19 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_stable[1], cap));
     A(dmalloc(&c->d_dist_p2g, cap));
     A(dmalloc(&c->d_dist_g2p, gcap));
-    A(dmalloc(&c->d_partials, 4096));
+    A(dmalloc(&c->d_partials, (size_t)c->nb * 16));
     A(dmalloc(&c->d_record, 1));
+    c->max_records = 1024;
+    A(dmalloc(&c->d_records, c->max_records));
+    if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_records, sizeof(aoslo_metrics_record) * c->max_records, cudaHostAllocDefault) != cudaSuccess)
+        st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_record, sizeof(aoslo_metrics_record), cudaHostAllocDefault) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_lut, 64 * 64));
+    A(dmalloc(&c->d_lut_packed, 64 * 64));
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
-    // sklearn-order KD tree mirrors
-    KdTreeDev& kd = c->kd;
-    kd.cap = cap;
-    size_t nn = (size_t)2 * cap + 2;
-    A(dmalloc(&kd.idx_array, cap));
-    A(dmalloc(&kd.node_start, nn));
-    A(dmalloc(&kd.node_end, nn));
-    A(dmalloc(&kd.node_bounds, nn * 4));
-    if (st == AOSLO_OK) {
-        bool ok = cudaHostAlloc((void**)&kd.h_points, sizeof(double) * 2 * cap, cudaHostAllocDefault) == cudaSuccess &&
-                  cudaHostAlloc((void**)&kd.h_idx_array, sizeof(int32_t) * cap, cudaHostAllocDefault) == cudaSuccess &&
-                  cudaHostAlloc((void**)&kd.h_node_start, sizeof(int32_t) * nn, cudaHostAllocDefault) == cudaSuccess &&
-                  cudaHostAlloc((void**)&kd.h_node_end, sizeof(int32_t) * nn, cudaHostAllocDefault) == cudaSuccess &&
-                  cudaHostAlloc((void**)&kd.h_node_bounds, sizeof(double) * 4 * nn, cudaHostAllocDefault) == cudaSuccess;
-        if (!ok) st = set_cuda_error(cudaGetLastError(), "cudaHostAlloc(kd)");
-    }
+    c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)
     for (int i = 0; i < 12 && st == AOSLO_OK; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) st = AOSLO_ERR_CUDA;
 #undef A
@@ -165,12 +184,13 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
-    cudaFreeHost(c->h_record); cudaFree(c->d_lut); cudaFree(c->d_field); cudaFree(c->d_win);
+    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_packed); cudaFree(c->d_field); cudaFree(c->d_win);
     KdTreeDev& kd = c->kd;
     cudaFree(kd.idx_array); cudaFree(kd.node_start); cudaFree(kd.node_end); cudaFree(kd.node_bounds);
     cudaFreeHost(kd.h_points); cudaFreeHost(kd.h_idx_array); cudaFreeHost(kd.h_node_start);
     cudaFreeHost(kd.h_node_end); cudaFreeHost(kd.h_node_bounds);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaGetLastError();
     delete c;
     return AOSLO_OK;
@@ -202,7 +222,7 @@ extern "C" int aoslo_knn(aoslo_ctx* ctx, void* stream, const double* d_points, i
     if (n_points < k) return AOSLO_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     // distances come back squared from the kernels; take the root in place (rdist_to_dist)
-    AOSLO_TRY(stage_knn(ctx, s, d_points, n_points, d_query, n_query, k, tie_mode, d_idx_out, d_dist_out, true));
+    AOSLO_TRY(stage_knn(ctx, s, d_points, n_points, d_query, n_query, k, tie_mode, d_idx_out, d_dist_out, true, nullptr));
     return sqrt_inplace(s, d_dist_out, (size_t)n_query * k);
 }
 
@@ -214,7 +234,7 @@ extern "C" int aoslo_delete_close(aoslo_ctx* ctx, void* stream, const double* d_
     if (H != ctx->H || W != ctx->W) return AOSLO_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     AOSLO_TRY(stage_delete(ctx, s, d_particles, d_stable, n, d_Rb, field_dtype, H, W, threshold, tie_mode,
-                           d_particles_out, d_stable_out, d_deleted_out, ctx->d_counters, ctx->d_counters + 1));
+                           d_particles_out, d_stable_out, d_deleted_out, ctx->d_counters, ctx->d_counters + 1, nullptr));
     return read_int(ctx, s, ctx->d_counters, h_n_out);
 }
 
@@ -230,7 +250,7 @@ extern "C" int aoslo_gravity_field(aoslo_ctx* ctx, void* stream, const double* d
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     cudaStream_t s = (cudaStream_t)stream;
     AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_particles, n, nullptr));
-    return stage_gravity(ctx, s, d_lut, rfs, H, W, d_field);
+    return stage_gravity(ctx, s, d_lut, rfs, H, W, d_field, false);
 }
 
 extern "C" int aoslo_add_particles(aoslo_ctx* ctx, void* stream, const double* d_field, int H, int W, int bx, int by,
@@ -250,7 +270,7 @@ extern "C" int aoslo_dist_force(aoslo_ctx* ctx, void* stream, const double* d_pa
     if (!ctx || !d_particles || !d_force) return AOSLO_ERR_INVALID;
     if (energy_type != AOSLO_ENERGY_PIT && energy_type != AOSLO_ENERGY_EXP) return AOSLO_ERR_UNSUPPORTED;
     return stage_force(ctx, (cudaStream_t)stream, d_particles, d_stable, n, n_neighbours, energy_type, p0, p1, p2,
-                       tie_mode, d_force);
+                       tie_mode, d_force, nullptr);
 }
 
 extern "C" int aoslo_move(aoslo_ctx* ctx, void* stream, double* d_particles, const uint8_t* d_stable, int n,
@@ -259,7 +279,7 @@ extern "C" int aoslo_move(aoslo_ctx* ctx, void* stream, double* d_particles, con
     if (!ctx || !d_particles || !d_stable || !d_grad || !d_force || n < 0) return AOSLO_ERR_INVALID;
     if (step_mode != AOSLO_STEP_DISCRETE && step_mode != AOSLO_STEP_CONTIN) return AOSLO_ERR_UNSUPPORTED;
     return stage_move(ctx, (cudaStream_t)stream, d_particles, d_stable, n, d_grad, field_dtype, H, W, d_force,
-                      lambda_blob, lambda_dist, step_mode);
+                      lambda_blob, lambda_dist, step_mode, nullptr);
 }
 
 extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_particles, const uint8_t* d_stable, int n,
@@ -271,7 +291,7 @@ extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_parti
     double* p2g = d_dist_p2g ? d_dist_p2g : ctx->d_dist_p2g;
     double* g2p = d_dist_g2p ? d_dist_g2p : ctx->d_dist_g2p;
     AOSLO_TRY(stage_metrics(ctx, s, d_particles, d_stable, n, d_gt, n_gt, false, false, d_Rb, field_dtype, H, W, bx,
-                            by, 0, ctx->d_record, p2g, g2p));
+                            by, 0, ctx->d_record, p2g, g2p, nullptr));
     AOSLO_CUDA(cudaMemcpyAsync(ctx->h_record, ctx->d_record, sizeof(aoslo_metrics_record), cudaMemcpyDeviceToHost, s));
     AOSLO_CUDA(cudaStreamSynchronize(s));
     *h_record_out = *ctx->h_record;
@@ -281,20 +301,12 @@ extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_parti
 // ---------------------------------------------------------------------------------------
 // whole run
 // ---------------------------------------------------------------------------------------
-namespace {
-struct StageTimer {
-    aoslo_ctx* ctx;
-    cudaStream_t s;
-    float acc[5] = {0, 0, 0, 0, 0};
-    std::chrono::steady_clock::time_point t0;
-    void begin() { t0 = std::chrono::steady_clock::now(); }
-    // v1 run loop synchronises at the end of every stage (count read-back), so host time == device time
-    void end(int bucket) {
-        acc[bucket] += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    }
-};
-}  // namespace
-
+// Control flow = reference pipeline_with_delitions.py:101-382.  The particle count lives in a
+// device scalar (double-buffered with the particle arrays); in the canonical tie mode the
+// host only synchronises where it needs a decision: the thinning fixpoint test, after every
+// resample (to refresh its upper bound of the count), for the early-stop test when that is
+// enabled, and once at the end for the records.  The sklearn-order tie mode needs the count
+// on the host for every kNN (host tree build) and synchronises per stage.
 extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
                          int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records,
                          int max_records, double* d_particles_out, uint8_t* d_stable_out,
@@ -305,36 +317,53 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     if (cfg->particle_call_window < 1 || cfg->reception_field_size < 1 || cfg->reception_field_size > 64)
         return AOSLO_ERR_UNSUPPORTED;
     if (cfg->fix_particles_frequency < 1 || cfg->metric_measure_freq < 1) return AOSLO_ERR_INVALID;
+    if (max_records > ctx->max_records) max_records = ctx->max_records;
     cudaStream_t s = (cudaStream_t)stream;
     const int H = cfg->H, W = cfg->W, cap = ctx->cap;
+    const bool on_device = (cfg->tie_mode == AOSLO_TIE_CANONICAL);   // count stays on the device
     memset(h_summary, 0, sizeof(*h_summary));
     AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), s));
-    StageTimer tm{ctx, s};
+    float acc_ms[5] = {0, 0, 0, 0, 0};
+    // stage timing: CUDA events on the launch stream, resolved once at the end (no extra syncs)
+    std::vector<cudaEvent_t>& pool = ctx->ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_bucket;
+    auto mark = [&](int bucket) -> int {            // records an event; bucket = stage that just ended (-1: start)
+        if (!h_stage_ms) return AOSLO_OK;
+        if (ev_used == pool.size()) {
+            cudaEvent_t e;
+            AOSLO_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        AOSLO_CUDA(cudaEventRecord(pool[ev_used], s));
+        ev_bucket.push_back(bucket);
+        ++ev_used;
+        return AOSLO_OK;
+    };
 
     int cur = 0, n = 0;
-    int* d_n = ctx->d_counters;          // scratch scalar
+    int* d_cnt[2] = {ctx->d_counters + 4, ctx->d_counters + 5};   // count of buffer 0 / 1
     // ---- seeds (:101) and flags (:113)
     AOSLO_TRY(stage_seed(ctx, s, d_Rb, field_dtype, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold, ctx->d_pos[cur],
-                         cap, d_n));
-    AOSLO_TRY(read_int(ctx, s, d_n, &n));
+                         cap, d_cnt[cur]));
+    AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
     if (n > cap) return AOSLO_ERR_CAPACITY;
     h_summary->n_seeds = n;
     if (n < 2) { h_summary->status = AOSLO_DEV_KNN_SHORT; return AOSLO_OK; }
-    AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 0));
+    AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 0, nullptr));
     // ---- thinning to a fixpoint (:115-120)
     int rounds = 0;
     while (true) {
         int n_new = 0;
         AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
                                cfg->thinning_threshold, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
-                               nullptr, d_n, nullptr));
-        AOSLO_TRY(read_int(ctx, s, d_n, &n_new));
+                               nullptr, d_cnt[cur ^ 1], nullptr, nullptr));
+        AOSLO_TRY(read_int(ctx, s, d_cnt[cur ^ 1], &n_new));
         cur ^= 1;
         ++rounds;
         bool none = (n_new == n);
         n = n_new;
-        if (none) break;
-        if (n < 2) break;
+        if (none || n < 2) break;
     }
     h_summary->n_after_thinning = n;
     h_summary->n_thinning_rounds = rounds;
@@ -342,76 +371,96 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     // ---- all stable, gravity field, adding (:130-152)
     AOSLO_TRY(stage_lut(ctx, s, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, ctx->d_lut));
-    auto resample = [&]() -> int {
-        AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 1));
-        AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, ctx->d_pos[cur], n, nullptr));
-        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field));
+    // resample: needs the exact count on the host afterwards (it bounds every later launch)
+    bool packed_ready = false;                       // rank-packed LUT: derived once per run
+    auto resample = [&](const int* d_n_in) -> int {
+        AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 1, d_n_in));
+        AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, ctx->d_pos[cur], n, d_n_in));
+        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
+        packed_ready = true;
         AOSLO_TRY(stage_add(ctx, s, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
-                            cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, nullptr, cap, d_n));
-        AOSLO_TRY(read_int(ctx, s, d_n, &n));
+                            cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, d_n_in, cap,
+                            ctx->d_counters + 6));
+        // the appended count lands in a scratch scalar, then becomes this buffer's count
+        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[cur], ctx->d_counters + 6, sizeof(int), cudaMemcpyDeviceToDevice, s));
+        AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
         if (n > cap) return AOSLO_ERR_CAPACITY;
         return AOSLO_OK;
     };
-    AOSLO_TRY(resample());
-    // GT cell list once
-    AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));
+    AOSLO_TRY(resample(nullptr));
+    AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));      // GT cell list once
 
     const int k = cfg->dist_n_neighbours;
     const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
     int n_rec = 0, it_done = 0;
+    AOSLO_TRY(mark(-1));
     for (int it = 0; it < cfg->epoch_num; ++it) {
         ++it_done;
         if (n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
-        tm.begin();
+        // `n` is exact in the synchronising mode and an upper bound of the device count otherwise
+        const int* dn = on_device ? d_cnt[cur] : nullptr;
         AOSLO_TRY(stage_force(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type,
                               pit ? cfg->mu_dist_func : cfg->dist_alpha, pit ? cfg->sigma_dist_func : cfg->dist_sigma,
-                              pit ? cfg->lambda_dist_func : 0.0, cfg->tie_mode, ctx->d_force));
-        AOSLO_CUDA(cudaStreamSynchronize(s));
-        tm.end(0);
-        tm.begin();
+                              pit ? cfg->lambda_dist_func : 0.0, cfg->tie_mode, ctx->d_force, dn));
+        AOSLO_TRY(mark(0));
         AOSLO_TRY(stage_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W, ctx->d_force,
-                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode));
-        AOSLO_CUDA(cudaStreamSynchronize(s));
-        tm.end(1);
-        tm.begin();
+                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
+        AOSLO_TRY(mark(1));
         AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
                                cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
-                               nullptr, d_n, nullptr));
-        AOSLO_TRY(read_int(ctx, s, d_n, &n));
+                               nullptr, d_cnt[cur ^ 1], nullptr, dn));
         cur ^= 1;
-        tm.end(2);
-        tm.begin();
-        if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample());
-        AOSLO_CUDA(cudaStreamSynchronize(s));
-        tm.end(3);
-        tm.begin();
+        if (!on_device) AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+        dn = on_device ? d_cnt[cur] : nullptr;
+        AOSLO_TRY(mark(2));
+        if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample(dn));
+        AOSLO_TRY(mark(3));
         if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) {
             AOSLO_TRY(stage_metrics(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
-                                    field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_record, ctx->d_dist_p2g,
-                                    ctx->d_dist_g2p));
-            AOSLO_CUDA(cudaMemcpyAsync(ctx->h_record, ctx->d_record, sizeof(aoslo_metrics_record),
-                                       cudaMemcpyDeviceToHost, s));
-            AOSLO_CUDA(cudaStreamSynchronize(s));
-            h_records[n_rec++] = *ctx->h_record;
+                                    field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec, ctx->d_dist_p2g,
+                                    ctx->d_dist_g2p, dn));
+            ++n_rec;
         }
-        int n_stable = 0;
-        AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2));
-        AOSLO_TRY(read_int(ctx, s, ctx->d_counters + 2, &n_stable));
-        h_summary->n_stable = n_stable;
-        // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
-        if (cfg->early_stop && ((double)n_stable / (double)n > 0.997)) break;
-        tm.end(4);
+        if (cfg->early_stop) {
+            int n_stable = 0;
+            AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, dn));
+            AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+            AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+            n_stable = ctx->h_pinned[1];
+            h_summary->n_stable = n_stable;
+            // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
+            if ((double)n_stable / (double)n > 0.997) break;
+        }
+        AOSLO_TRY(mark(4));
     }
+    // ---- results: records, final particles, status -- one synchronisation
+    if (n_rec)
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->h_records, ctx->d_records, sizeof(aoslo_metrics_record) * n_rec,
+                                   cudaMemcpyDeviceToHost, s));
+    if (!cfg->early_stop) {
+        AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, on_device ? d_cnt[cur] : nullptr));
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+    AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
+    AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+    if (!cfg->early_stop) h_summary->n_stable = ctx->h_pinned[1];
+    h_summary->status |= ctx->h_pinned[2];
+    for (int i = 0; i < n_rec; ++i) h_records[i] = ctx->h_records[i];
     if (d_particles_out)
         AOSLO_CUDA(cudaMemcpyAsync(d_particles_out, ctx->d_pos[cur], sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
     if (d_stable_out)
         AOSLO_CUDA(cudaMemcpyAsync(d_stable_out, ctx->d_stable[cur], n, cudaMemcpyDeviceToDevice, s));
-    int status = 0;
-    AOSLO_TRY(read_int(ctx, s, ctx->d_status, &status));
-    h_summary->status |= status;
     h_summary->n_iterations = it_done;
     h_summary->n_particles = n;
     h_summary->n_records = n_rec;
-    if (h_stage_ms) for (int i = 0; i < 5; ++i) h_stage_ms[i] = tm.acc[i];
+    if (h_stage_ms) {
+        for (size_t i = 1; i < ev_used; ++i) {
+            if (ev_bucket[i] < 0) continue;
+            float ms = 0.f;
+            AOSLO_CUDA(cudaEventElapsedTime(&ms, pool[i - 1], pool[i]));
+            acc_ms[ev_bucket[i]] += ms;
+        }
+        for (int i = 0; i < 5; ++i) h_stage_ms[i] = acc_ms[i];
+    }
     return AOSLO_OK;
 }

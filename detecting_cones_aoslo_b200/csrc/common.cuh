@@ -11,11 +11,14 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <vector>
+
 #include "aoslo_b200.h"
 
 namespace aoslo {
 
 int set_cuda_error(cudaError_t e, const char* where);
+void count_launch();
 
 #define AOSLO_CUDA(call)                                                         \
     do {                                                                         \
@@ -27,7 +30,12 @@ int set_cuda_error(cudaError_t e, const char* where);
         int s__ = (call);                                                        \
         if (s__ != AOSLO_OK) return s__;                                         \
     } while (0)
-#define AOSLO_LAUNCH_CHECK() AOSLO_CUDA(cudaGetLastError())
+// every kernel launch is followed by this: counts the launch (aoslo_launch_count) and checks it
+#define AOSLO_LAUNCH_CHECK()                                                     \
+    do {                                                                         \
+        ::aoslo::count_launch();                                                 \
+        AOSLO_CUDA(cudaGetLastError());                                          \
+    } while (0)
 
 constexpr int kThreads = 256;          // block size of the grid-stride kernels
 constexpr int kScanThreads = 1024;     // block size of the ordered-compaction kernels
@@ -98,14 +106,19 @@ struct aoslo_ctx {
     uint8_t* d_stable[2] = {nullptr, nullptr};
     double* d_dist_p2g = nullptr;     // [cap]
     double* d_dist_g2p = nullptr;     // [gt_cap]
-    double* d_partials = nullptr;     // [4096] fp64 reduction partials
+    double* d_partials = nullptr;     // per-block metrics partials (nb * 9 doubles)
     aoslo_metrics_record* d_record = nullptr;
     aoslo_metrics_record* h_record = nullptr;   // pinned
+    aoslo_metrics_record* d_records = nullptr;  // [max_records] one per metrics evaluation of a run
+    aoslo_metrics_record* h_records = nullptr;  // pinned
+    int max_records = 0;
     double* d_lut = nullptr;          // [64*64]
+    uint32_t* d_lut_packed = nullptr; // [64*64] (rank + 1) << 16 | index
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd;
     cudaEvent_t ev[12] = {};
+    std::vector<cudaEvent_t> ev_pool;   // stage-timing events of aoslo_run
 };
 
 namespace aoslo {
@@ -219,7 +232,9 @@ __device__ __forceinline__ double fld(const T* p, long long i) {
 
 // ---------------------------------------------------------------------------------------
 // stage entry points implemented in particles.cu / blobness.cu (host side, stream-ordered)
+// (kd_reserve: api.cu)
 // ---------------------------------------------------------------------------------------
+int kd_reserve(aoslo_ctx* ctx);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,
               const int* d_nq, int k, int32_t* d_idx, double* d_d2, int n_points_host, const int* d_np);

@@ -81,10 +81,11 @@ __global__ void __launch_bounds__(kThreads) cell_count_kernel(const double2* __r
 }
 
 struct CellScanOp {
-    const int* count;
+    int* count;
     int* start;
     __device__ int value(int i) const { return count[i]; }
-    __device__ void emit(int i, int, int excl) const { start[i] = excl; }
+    // the count is consumed here, so it is re-zeroed for the next build (no memset per build)
+    __device__ void emit(int i, int, int excl) const { start[i] = excl; count[i] = 0; }
 };
 
 __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double2* __restrict__ pos, int n_host,
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(kThreads) cell_scatter_kernel(const double2* _
 }
 
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n) {
-    AOSLO_CUDA(cudaMemsetAsync(cl.count, 0, sizeof(int) * cl.ncell, s));
+    // cl.count is all zero here: zeroed at allocation and re-zeroed by every scan (CellScanOp::emit)
     cell_count_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, cl.shift, cl.gw, cl.gh,
                                                    ctx->W, ctx->H, cl.count, cl.cell_of, cl.slot, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
@@ -333,8 +334,9 @@ __global__ void __launch_bounds__(128) knn_sklearn_kernel(KdView t, const double
 
 int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
                 int n_query, int k, int32_t* d_idx, double* d_d2) {
+    if (n_points > ctx->cap) return AOSLO_ERR_CAPACITY;
+    AOSLO_TRY(kd_reserve(ctx));
     KdTreeDev& kd = ctx->kd;
-    if (n_points > kd.cap) return AOSLO_ERR_CAPACITY;
     if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (n_points < k) return AOSLO_ERR_INVALID;   // sklearn: ValueError("Expected n_neighbors <= n_samples_fit")
     // host round trip: sklearn's idx_array is the residue of libstdc++ std::nth_element
@@ -513,74 +515,68 @@ __global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, do
 // =======================================================================================
 // gravity field (utils.py:310-333) as a per-pixel gather over the cell list
 // =======================================================================================
-constexpr int kGravTile = 32;
-constexpr int kGravList = 1024;
+// field[y][x] = max(-0.48, max over particles p with |x-px|<=h, |y-py|<=h of T[y-py+h][x-px+h]).
+// The max of LUT ENTRIES is taken on their ranks: `packed[i] = (rank(T[i]) + 1) << 16 | i` where
+// rank = number of strictly smaller entries, so an integer max selects exactly the entry a float
+// max would (ties have equal rank and equal value).  A thread owns kGravRows consecutive rows of
+// one column; the packed LUT is staged in shared memory with kGravRows-1 zero rows above and
+// below, so every candidate particle updates all rows with one LDS + IMNMX each and no
+// per-row range test.
+constexpr int kGravRows = 16;
+constexpr int kGravCols = 128;
 
-__global__ void __launch_bounds__(kThreads) gravity_field_kernel(CellView cl, const double* __restrict__ lut,
-                                                                int rfs, int H, int W, double* field) {
-    extern __shared__ double s_lut[];                 // rfs*rfs
-    __shared__ int s_px[kGravList], s_py[kGravList];
-    __shared__ int s_row_lo[80], s_row_n[80], s_row_off[81];
+__global__ void lut_rank_kernel(const double* __restrict__ lut, int n, uint32_t* packed) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double v = lut[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += (lut[j] < v) ? 1 : 0;
+        packed[i] = ((uint32_t)(rank + 1) << 16) | (uint32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(kGravCols) gravity_field_kernel(CellView cl, const double* __restrict__ lut,
+                                                                 const uint32_t* __restrict__ packed, int rfs,
+                                                                 int H, int W, double* field) {
+    extern __shared__ uint32_t s_pk[];                // (rfs + 2*(kGravRows-1)) * rfs
     const int h = rfs / 2;
-    const int x0 = blockIdx.x * kGravTile, y0 = blockIdx.y * kGravTile;
-    for (int i = threadIdx.x; i < rfs * rfs; i += blockDim.x) s_lut[i] = lut[i];
-
-    const int c = 1 << cl.shift;
-    int cx0 = max(x0 - h, 0) >> cl.shift, cx1 = min((min(x0 + kGravTile - 1, W - 1) + h) >> cl.shift, cl.gw - 1);
-    int cy0 = max(y0 - h, 0) >> cl.shift, cy1 = min((min(y0 + kGravTile - 1, H - 1) + h) >> cl.shift, cl.gh - 1);
-    (void)c;
-    int nrows = cy1 - cy0 + 1;                        // <= (32 + 2*32)/4 + 2 < 80 for rfs <= 64, shift >= 1
-    if (threadIdx.x < nrows) {
-        int y = cy0 + threadIdx.x;
-        int a = cl.start[y * cl.gw + cx0], b = cl.start[y * cl.gw + cx1 + 1];
-        s_row_lo[threadIdx.x] = a;
-        s_row_n[threadIdx.x] = b - a;
+    const int pad = kGravRows - 1;
+    const int rows = rfs + 2 * pad;
+    for (int i = threadIdx.x; i < rows * rfs; i += blockDim.x) {
+        int r = i / rfs - pad;
+        s_pk[i] = (r >= 0 && r < rfs) ? packed[r * rfs + (i % rfs)] : 0u;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int r = 0; r < nrows; ++r) { s_row_off[r] = acc; acc += s_row_n[r]; }
-        s_row_off[nrows] = acc;
-    }
-    __syncthreads();
-    const int total = s_row_off[nrows];
-
-    // each thread owns 4 pixels of the 32x32 tile: rows ty, ty+8, ty+16, ty+24
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    double m[4] = {-0.48, -0.48, -0.48, -0.48};
-    const int gx = x0 + tx;
-
-    for (int base = 0; base < total; base += kGravList) {
-        int cnt = min(kGravList, total - base);
-        for (int v = threadIdx.x; v < cnt; v += blockDim.x) {
-            int g = base + v, r = 0;
-            while (g >= s_row_off[r + 1]) ++r;
-            double2 pp = cl.sorted_pos[s_row_lo[r] + (g - s_row_off[r])];
-            s_px[v] = (int)pp.x;                       // int(particle[0]) truncation
-            s_py[v] = (int)pp.y;
-        }
-        __syncthreads();
-        for (int v = 0; v < cnt; ++v) {
-            int dx = gx - s_px[v];
-            if (dx < -h || dx > h) continue;
-            int py = s_py[v];
+    const int x = blockIdx.x * kGravCols + threadIdx.x;
+    const int y0 = blockIdx.y * kGravRows;
+    if (x >= W) return;
+    uint32_t best[kGravRows];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int dy = (y0 + ty + 8 * u) - py;
-                if (dy >= -h && dy <= h) {
-                    double val = s_lut[(dy + h) * rfs + (dx + h)];
-                    m[u] = (val > m[u]) ? val : m[u];
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (gx < W) {
+    for (int r = 0; r < kGravRows; ++r) best[r] = 0u;
+    const int cxa = max(x - h, 0) >> cl.shift, cxb = min(min(x + h, W - 1) >> cl.shift, cl.gw - 1);
+    const int cya = max(y0 - h, 0) >> cl.shift;
+    const int cyb = min(min(y0 + kGravRows - 1 + h, H - 1) >> cl.shift, cl.gh - 1);
+    for (int cy = cya; cy <= cyb; ++cy) {
+        int p0 = cl.start[cy * cl.gw + cxa], p1 = cl.start[cy * cl.gw + cxb + 1];
+        for (int p = p0; p < p1; ++p) {
+            double2 pp = cl.sorted_pos[p];
+            int dx = x - (int)pp.x;                    // int(particle[0]) truncation
+            int dyb = y0 - (int)pp.y + h + pad;        // padded LUT row of this thread's row 0
+            if (dx < -h || dx > h || dyb < 0 || dyb > 2 * h + pad) continue;
+            const uint32_t* col = s_pk + dyb * rfs + (dx + h);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int gy = y0 + ty + 8 * u;
-            if (gy < H) field[(size_t)gy * W + gx] = m[u];
+            for (int r = 0; r < kGravRows; ++r) best[r] = max(best[r], col[r * rfs]);
         }
+    }
+#pragma unroll
+    for (int r = 0; r < kGravRows; ++r) {
+        int y = y0 + r;
+        if (y >= H) break;
+        double v = -0.48;
+        if (best[r]) {
+            double t = lut[best[r] & 0xffffu];
+            v = (t > v) ? t : v;
+        }
+        field[(size_t)y * W + x] = v;
     }
 }
 
@@ -713,86 +709,161 @@ __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint
 // =======================================================================================
 // metrics
 // =======================================================================================
-__global__ void __launch_bounds__(kThreads) nn_dist_kernel(CellView cl, const double2* __restrict__ q, int nq_host,
-                                                           const int* d_nq, double* dist_out, int* status) {
-    int nq = d_nq ? *d_nq : nq_host;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
-        TopK<1> top;
-        knn_cells_query<1>(cl, q[i].x, q[i].y, top);
-        if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-        dist_out[i] = sqrt(top.d2[0]);
+// Chan / Welford running moments (count, mean, M2): numerically stable and mergeable in a fixed order
+struct Moments {
+    double n, mean, m2, sum;
+    __device__ __forceinline__ void init() { n = 0.0; mean = 0.0; m2 = 0.0; sum = 0.0; }
+    __device__ __forceinline__ void add(double x) {
+        n += 1.0;
+        double d = x - mean;
+        mean += d / n;
+        m2 += d * (x - mean);
+        sum += x;
     }
-}
+    __device__ __forceinline__ void merge(const Moments& o) {
+        if (o.n == 0.0) return;
+        if (n == 0.0) { *this = o; return; }
+        double nn = n + o.n, d = o.mean - mean;
+        mean += d * (o.n / nn);
+        m2 += o.m2 + d * d * (n * o.n / nn);
+        n = nn;
+        sum += o.sum;
+    }
+};
 
-// deterministic block reduction (fixed tree) of a double
-__device__ __forceinline__ double block_sum(double v, double* sm /*[kScanThreads]*/) {
-    sm[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
-        __syncthreads();
-    }
-    double r = sm[0];
-    __syncthreads();
+__device__ __forceinline__ Moments shfl_down_moments(const Moments& m, int o) {
+    Moments r;
+    r.n = __shfl_down_sync(0xffffffffu, m.n, o);
+    r.mean = __shfl_down_sync(0xffffffffu, m.mean, o);
+    r.m2 = __shfl_down_sync(0xffffffffu, m.m2, o);
+    r.sum = __shfl_down_sync(0xffffffffu, m.sum, o);
     return r;
 }
 
-// one block: every reduction of one metrics evaluation, in a fixed order
+struct MetricsPartial {          // one per block
+    Moments p2g, g2p;
+    double energy;
+};
+
+// One grid pass over [0, n) particles (nearest GT, in-image test, FP counts, blob energy) and
+// [n, n + n_gt) ground-truth points (nearest particle, TP / FN counts).  Integer counts go to
+// global atomics (order independent); FP64 moments are merged in a fixed tree per block and
+// written as per-block partials for the finalize kernel.
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) metrics_finalize_kernel(
-    const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host, const int* d_n, int n_gt,
-    const double* __restrict__ d_p2g, const double* __restrict__ d_g2p, const T* __restrict__ Rb, int H, int W,
-    int bx, int by, int iteration, aoslo_metrics_record* rec, int* status) {
-    __shared__ double sm[kScanThreads];
-    __shared__ int si[8];
+__global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
+    CellView cl_g, CellView cl_p, const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host,
+    const int* d_n, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W, int bx, int by,
+    double* d_p2g, double* d_g2p, int* icount /*[8]*/, MetricsPartial* partials, int* status) {
     const int n = d_n ? *d_n : n_host;
-    const int t = threadIdx.x;
-    if (t < 8) si[t] = 0;
+    const int total = n + n_gt;
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tp1 tp2 fn1 fn2 fp1 fp2 nin nst
+    Moments mp, mg;
+    mp.init(); mg.init();
+    double energy = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        TopK<1> top;
+        if (i < n) {
+            double2 p = pos[i];
+            knn_cells_query<1>(cl_g, p.x, p.y, top);
+            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            double d = sqrt(top.d2[0]);
+            if (d_p2g) d_p2g[i] = d;
+            bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) &&
+                          (p.y < (double)(H - by));
+            c[6] += inside;
+            c[4] += inside && (d > 1.42);
+            c[5] += inside && (d > 2.83);
+            c[7] += stable[i] ? 1 : 0;
+            mp.add(d);
+            energy += energy_at<T>(Rb, p, W, H, status);
+        } else {
+            double2 g = gt[i - n];
+            knn_cells_query<1>(cl_p, g.x, g.y, top);
+            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            double d = sqrt(top.d2[0]);
+            if (d_g2p) d_g2p[i - n] = d;
+            c[0] += (d <= 1.42); c[2] += (d > 1.42);
+            c[1] += (d <= 2.83); c[3] += (d > 2.83);
+            mg.add(d);
+        }
+    }
+    // ---- block reduction
+    __shared__ MetricsPartial s_part[kThreads / 32];
+    __shared__ int s_c[8];
+    if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
     __syncthreads();
-    int tp1 = 0, tp2 = 0, fn1 = 0, fn2 = 0, fp1 = 0, fp2 = 0, nin = 0, nst = 0;
-    double s_g = 0.0, s_p = 0.0, s_e = 0.0;
-    for (int j = t; j < n_gt; j += blockDim.x) {
-        double d = d_g2p[j];
-        tp1 += (d <= 1.42); fn1 += (d > 1.42);
-        tp2 += (d <= 2.83); fn2 += (d > 2.83);
-        s_g += d;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int v = c[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[j], v);
     }
-    for (int i = t; i < n; i += blockDim.x) {
-        double d = d_p2g[i];
-        double2 p = pos[i];
-        bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) && (p.y < (double)(H - by));
-        nin += inside;
-        fp1 += inside && (d > 1.42);
-        fp2 += inside && (d > 2.83);
-        nst += stable[i] ? 1 : 0;
-        s_p += d;
-        s_e += energy_at<T>(Rb, p, W, H, status);
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments a = shfl_down_moments(mp, o), b = shfl_down_moments(mg, o);
+        double e = __shfl_down_sync(0xffffffffu, energy, o);
+        mp.merge(a); mg.merge(b); energy += e;
     }
-    atomicAdd(&si[0], tp1); atomicAdd(&si[1], tp2); atomicAdd(&si[2], fn1); atomicAdd(&si[3], fn2);
-    atomicAdd(&si[4], fp1); atomicAdd(&si[5], fp2); atomicAdd(&si[6], nin); atomicAdd(&si[7], nst);
-    double sum_g = block_sum(s_g, sm);
-    double sum_p = block_sum(s_p, sm);
-    double sum_e = block_sum(s_e, sm);
-    double mean_g = sum_g / (double)n_gt, mean_p = sum_p / (double)n;
-    double v_g = 0.0, v_p = 0.0;
-    for (int j = t; j < n_gt; j += blockDim.x) { double d = d_g2p[j] - mean_g; v_g += d * d; }
-    for (int i = t; i < n; i += blockDim.x) { double d = d_p2g[i] - mean_p; v_p += d * d; }
-    double var_g = block_sum(v_g, sm) / (double)n_gt;
-    double var_p = block_sum(v_p, sm) / (double)n;
-    if (t == 0) {
-        rec->iteration = iteration;
-        rec->n_particles = n;
-        rec->n_stable = si[7];
-        rec->n_gt = n_gt;
-        rec->tp[0] = si[0]; rec->tp[1] = si[1];
-        rec->fn[0] = si[2]; rec->fn[1] = si[3];
-        rec->fp[0] = si[4]; rec->fp[1] = si[5];
-        rec->n_in_image = si[6];
-        rec->pad_ = 0;
-        rec->sum_p2g = sum_p; rec->sum_g2p = sum_g;
-        rec->var_p2g = var_p; rec->var_g2p = var_g;
-        rec->blob_energy_sum = sum_e;
+    if ((threadIdx.x & 31) == 0) {
+        s_part[threadIdx.x >> 5].p2g = mp;
+        s_part[threadIdx.x >> 5].g2p = mg;
+        s_part[threadIdx.x >> 5].energy = energy;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MetricsPartial acc = s_part[0];
+        for (int w = 1; w < kThreads / 32; ++w) {
+            acc.p2g.merge(s_part[w].p2g);
+            acc.g2p.merge(s_part[w].g2p);
+            acc.energy += s_part[w].energy;
+        }
+        partials[blockIdx.x] = acc;
+    }
+    if (threadIdx.x < 8 && s_c[threadIdx.x]) atomicAdd(&icount[threadIdx.x], s_c[threadIdx.x]);
+}
+
+// one block: merges the per-block partials in a fixed shuffle tree (deterministic) -> record
+__global__ void __launch_bounds__(kScanThreads) metrics_finalize_kernel(
+    const MetricsPartial* __restrict__ partials, int nblocks, const int* __restrict__ icount, int n_host,
+    const int* d_n, int n_gt, int iteration, aoslo_metrics_record* rec) {
+    __shared__ MetricsPartial s_part[kScanThreads / 32];
+    MetricsPartial acc;
+    acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {      // nblocks <= blockDim in practice
+        acc.p2g.merge(partials[b].p2g);
+        acc.g2p.merge(partials[b].g2p);
+        acc.energy += partials[b].energy;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
+        double e = __shfl_down_sync(0xffffffffu, acc.energy, o);
+        acc.p2g.merge(a); acc.g2p.merge(g); acc.energy += e;
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int nw = blockDim.x >> 5;
+        if (threadIdx.x < nw) acc = s_part[threadIdx.x];
+        else { acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0; }
+        for (int o = 16; o > 0; o >>= 1) {
+            Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
+            double e = __shfl_down_sync(0xffffffffu, acc.energy, o);
+            acc.p2g.merge(a); acc.g2p.merge(g); acc.energy += e;
+        }
+    }
+    if (threadIdx.x != 0) return;
+    const int n = d_n ? *d_n : n_host;
+    rec->iteration = iteration;
+    rec->n_particles = n;
+    rec->n_stable = icount[7];
+    rec->n_gt = n_gt;
+    rec->tp[0] = icount[0]; rec->tp[1] = icount[1];
+    rec->fn[0] = icount[2]; rec->fn[1] = icount[3];
+    rec->fp[0] = icount[4]; rec->fp[1] = icount[5];
+    rec->n_in_image = icount[6];
+    rec->pad_ = 0;
+    rec->sum_p2g = acc.p2g.sum; rec->sum_g2p = acc.g2p.sum;
+    rec->var_p2g = acc.p2g.m2 / acc.p2g.n; rec->var_g2p = acc.g2p.m2 / acc.g2p.n;
+    rec->blob_energy_sum = acc.energy;
 }
 
 __global__ void set_all_stable_kernel(uint8_t* stable, int n_host, const int* d_n, uint8_t v) {
@@ -800,62 +871,66 @@ __global__ void set_all_stable_kernel(uint8_t* stable, int n_host, const int* d_
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) stable[i] = v;
 }
 
-// count stable flags -> counters[0] (used by the early-stop test, pipeline_with_delitions.py:381)
-__global__ void __launch_bounds__(kScanThreads) count_stable_kernel(const uint8_t* stable, int n_host,
-                                                                    const int* d_n, int* out) {
-    __shared__ int s;
-    if (threadIdx.x == 0) s = 0;
-    __syncthreads();
+// count stable flags into *out (zeroed by the caller); used by the early-stop test (:381)
+__global__ void __launch_bounds__(kThreads) count_stable_kernel(const uint8_t* __restrict__ stable, int n_host,
+                                                                const int* d_n, int* out) {
     int n = d_n ? *d_n : n_host;
     int c = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) c += stable[i] ? 1 : 0;
-    atomicAdd(&s, c);
-    __syncthreads();
-    if (threadIdx.x == 0) *out = s;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += stable[i] ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // =======================================================================================
 // host-side stage drivers (stream ordered; used by the C ABI wrappers and by aoslo_run)
 // =======================================================================================
+// d_n (optional): device-resident point/query count of a self-query (canonical mode only; the
+// sklearn-order path needs the count on the host to build the tree)
 int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
-              int n_query, int k, int tie_mode, int32_t* d_idx, double* d_d2, bool tree_is_particles) {
-    if (tie_mode == AOSLO_TIE_SKLEARN) return knn_sklearn(ctx, s, d_points, n_points, d_query, n_query, k, d_idx, d_d2);
+              int n_query, int k, int tie_mode, int32_t* d_idx, double* d_d2, bool tree_is_particles,
+              const int* d_n = nullptr) {
+    if (tie_mode == AOSLO_TIE_SKLEARN) {
+        if (d_n) return AOSLO_ERR_INVALID;
+        return knn_sklearn(ctx, s, d_points, n_points, d_query, n_query, k, d_idx, d_d2);
+    }
     CellList& cl = tree_is_particles ? ctx->cl_p : ctx->cl_g;
     if (n_points > cl.cap) return AOSLO_ERR_CAPACITY;
-    AOSLO_TRY(build_cell_list(ctx, s, cl, d_points, n_points, nullptr));
-    return knn_cells(ctx, s, cl, d_query, n_query, nullptr, k, d_idx, d_d2, n_points, nullptr);
+    AOSLO_TRY(build_cell_list(ctx, s, cl, d_points, n_points, d_n));
+    return knn_cells(ctx, s, cl, d_query, n_query, d_n, k, d_idx, d_d2, n_points, d_n);
 }
 
 template <typename T>
 int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                    const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
-                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out) {
+                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n) {
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     if (n < 2) return AOSLO_ERR_INVALID;   // sklearn: n_neighbors=2 > n_samples
-    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true));
+    if (d_n && d_n == d_n_out) return AOSLO_ERR_INVALID;   // the count is double-buffered
+    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
     DeleteParams p;
-    p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = nullptr;
+    p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
     p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.W = W; p.H = H;
     p.touch = ctx->d_touch; p.del = ctx->d_del; p.rowstate = ctx->d_rowstate;
     p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
     void* args[] = {&p, (void*)&d_Rb};
     int blocks = ctx->coop_blocks;
-    int need = (n + kThreads - 1) / kThreads;
+    int need = (n + kThreads - 1) / kThreads;   // n is an upper bound when the count lives on the device
     if (need < blocks) blocks = need < 1 ? 1 : need;
     AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kThreads), args, 0, s));
+    count_launch();
     if (d_deleted_out) AOSLO_CUDA(cudaMemcpyAsync(d_deleted_out, ctx->d_del, n, cudaMemcpyDeviceToDevice, s));
     KeepOp op{(const double2*)d_pos, d_stable, ctx->d_del, (double2*)d_pos_out, d_stable_out};
-    return ordered_scan(ctx, s, op, n, n, nullptr, d_n_out, nullptr, 0, nullptr);
+    return ordered_scan(ctx, s, op, n, n, d_n, d_n_out, nullptr, 0, nullptr);
 }
 
 int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                  const void* d_Rb, int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out,
-                 uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out) {
+                 uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n) {
     if (field_dtype == AOSLO_F32)
         return stage_delete_t<float>(ctx, s, d_pos, d_stable, n, (const float*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out);
+                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n);
     return stage_delete_t<double>(ctx, s, d_pos, d_stable, n, (const double*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out);
+                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n);
 }
 
 int stage_seed(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
@@ -878,12 +953,20 @@ int stage_lut(aoslo_ctx*, cudaStream_t s, int rfs, double mu, double sigma, doub
     return AOSLO_OK;
 }
 
-// requires ctx->cl_p built on the particles
-int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, int H, int W, double* d_field) {
+// requires ctx->cl_p built on the particles; d_packed = rank-packed LUT (nullptr: derive it here)
+int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, int H, int W, double* d_field,
+                  bool packed_ready) {
     if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
-    dim3 grid((W + kGravTile - 1) / kGravTile, (H + kGravTile - 1) / kGravTile);
-    size_t smem = sizeof(double) * rfs * rfs;
-    gravity_field_kernel<<<grid, kThreads, smem, s>>>(view_of(ctx->cl_p), d_lut, rfs, H, W, d_field);
+    if ((rfs & 1) == 0) return AOSLO_ERR_INVALID;     // even rfs: shape mismatch in the reference (utils.py:329)
+    if (ctx->cl_p.shift < 1) return AOSLO_ERR_UNSUPPORTED;
+    if (!packed_ready) {
+        lut_rank_kernel<<<(rfs * rfs + 127) / 128, 128, 0, s>>>(d_lut, rfs * rfs, ctx->d_lut_packed);
+        AOSLO_LAUNCH_CHECK();
+    }
+    dim3 grid((W + kGravCols - 1) / kGravCols, (H + kGravRows - 1) / kGravRows);
+    size_t smem = sizeof(uint32_t) * (rfs + 2 * (kGravRows - 1)) * rfs;
+    gravity_field_kernel<<<grid, kGravCols, smem, s>>>(view_of(ctx->cl_p), d_lut, ctx->d_lut_packed, rfs, H, W,
+                                                       d_field);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
@@ -902,24 +985,25 @@ int stage_add(aoslo_ctx* ctx, cudaStream_t s, const double* d_field, int H, int 
 }
 
 int stage_force(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
-                int energy_type, double p0, double p1, double p2, int tie_mode, double* d_force) {
+                int energy_type, double p0, double p1, double p2, int tie_mode, double* d_force, const int* d_n) {
     if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     if (n < k + 1) return AOSLO_ERR_INVALID;
-    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, k + 1, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true));
-    dist_force_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, ctx->d_knn_idx, k + 1,
+    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, k + 1, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
+    dist_force_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, ctx->d_knn_idx, k + 1,
                                                    energy_type, p0, p1, p2, (double2*)d_force);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
 
 int stage_move(aoslo_ctx* ctx, cudaStream_t s, double* d_pos, const uint8_t* d_stable, int n, const void* d_grad,
-               int field_dtype, int H, int W, const double* d_force, double lb, double ld, int step_mode) {
+               int field_dtype, int H, int W, const double* d_force, double lb, double ld, int step_mode,
+               const int* d_n) {
     if (field_dtype == AOSLO_F32)
-        move_kernel<float><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, nullptr, (const float*)d_grad, H,
+        move_kernel<float><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, d_n, (const float*)d_grad, H,
                                                         W, (const double2*)d_force, lb, ld, step_mode, ctx->d_status);
     else
-        move_kernel<double><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, nullptr, (const double*)d_grad,
+        move_kernel<double><<<ctx->nb, kThreads, 0, s>>>((double2*)d_pos, d_stable, n, d_n, (const double*)d_grad,
                                                          H, W, (const double2*)d_force, lb, ld, step_mode,
                                                          ctx->d_status);
     AOSLO_LAUNCH_CHECK();
@@ -930,39 +1014,39 @@ int stage_move(aoslo_ctx* ctx, cudaStream_t s, double* d_pos, const uint8_t* d_s
 int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                   const double* d_gt, int n_gt, bool gt_list_ready, bool p_list_ready, const void* d_Rb,
                   int field_dtype, int H, int W, int bx, int by, int iteration, aoslo_metrics_record* d_rec,
-                  double* d_p2g, double* d_g2p) {
+                  double* d_p2g, double* d_g2p, const int* d_n) {
     if (n > ctx->cap || n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
     if (n < 1 || n_gt < 1) return AOSLO_ERR_INVALID;
     if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));
-    if (!p_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_pos, n, nullptr));
-    // particle -> nearest GT  ("gt_to_particles" of the reference, :322)
-    nn_dist_kernel<<<ctx->nb, kThreads, 0, s>>>(view_of(ctx->cl_g), (const double2*)d_pos, n, nullptr, d_p2g,
-                                                ctx->d_status);
-    AOSLO_LAUNCH_CHECK();
-    // GT -> nearest particle  ("particles_to_gt", :323)
-    nn_dist_kernel<<<ctx->nb, kThreads, 0, s>>>(view_of(ctx->cl_p), (const double2*)d_gt, n_gt, nullptr, d_g2p,
-                                                ctx->d_status);
-    AOSLO_LAUNCH_CHECK();
+    if (!p_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_pos, n, d_n));
+    // one pass: particle -> nearest GT ("gt_to_particles", :322) and GT -> nearest particle
+    // ("particles_to_gt", :323), counts, moments and blob energy
+    int* icount = ctx->d_counters + 16;
+    AOSLO_CUDA(cudaMemsetAsync(icount, 0, sizeof(int) * 8, s));
+    MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
     if (field_dtype == AOSLO_F32)
-        metrics_finalize_kernel<float><<<1, kScanThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, n_gt,
-                                                                  d_p2g, d_g2p, (const float*)d_Rb, H, W, bx, by,
-                                                                  iteration, d_rec, ctx->d_status);
+        metrics_pass_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
+            view_of(ctx->cl_g), view_of(ctx->cl_p), (const double2*)d_pos, d_stable, n, d_n, (const double2*)d_gt,
+            n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, ctx->d_status);
     else
-        metrics_finalize_kernel<double><<<1, kScanThreads, 0, s>>>((const double2*)d_pos, d_stable, n, nullptr, n_gt,
-                                                                   d_p2g, d_g2p, (const double*)d_Rb, H, W, bx, by,
-                                                                   iteration, d_rec, ctx->d_status);
+        metrics_pass_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
+            view_of(ctx->cl_g), view_of(ctx->cl_p), (const double2*)d_pos, d_stable, n, d_n, (const double2*)d_gt,
+            n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    metrics_finalize_kernel<<<1, kScanThreads, 0, s>>>(partials, ctx->nb, icount, n, d_n, n_gt, iteration, d_rec);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
 
-int stage_set_stable(aoslo_ctx* ctx, cudaStream_t s, uint8_t* d_stable, int n, uint8_t v) {
-    set_all_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, nullptr, v);
+int stage_set_stable(aoslo_ctx* ctx, cudaStream_t s, uint8_t* d_stable, int n, uint8_t v, const int* d_n) {
+    set_all_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, d_n, v);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
 
-int stage_count_stable(aoslo_ctx*, cudaStream_t s, const uint8_t* d_stable, int n, int* d_out) {
-    count_stable_kernel<<<1, kScanThreads, 0, s>>>(d_stable, n, nullptr, d_out);
+int stage_count_stable(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_stable, int n, int* d_out, const int* d_n) {
+    AOSLO_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int), s));
+    count_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, d_n, d_out);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }

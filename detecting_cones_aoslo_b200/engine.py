@@ -65,6 +65,17 @@ class Engine:
             return a.to(device=self.device, dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
 
+    def upload_image(self, img):
+        """uint8 (H,W) host image -> device tensor VIEW (H,W) whose row pitch is a multiple of 16 bytes,
+        so that the blobness kernel can fetch 4 pixels per 32-bit load."""
+        img = np.ascontiguousarray(img)
+        H, W = img.shape
+        pitch = (W + 15) // 16 * 16
+        buf = torch.zeros((H, pitch), dtype=torch.uint8, device=self.device)
+        view = buf[:, :W]
+        view.copy_(torch.as_tensor(img), non_blocking=False)
+        return view
+
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
@@ -91,18 +102,14 @@ class Engine:
         raise TypeError("field must be float32 or float64, got %s" % t.dtype)
 
     # ------------------------------------------------------------------ L2 field
-    def blobness(self, img_u8, formula='custom', grad_type='np_grad', scales=(1.0,), dtype=torch.float64,
-                 want_grad=True, out=None):
-        """u8 (H,W) device tensor -> (R_b (H,W), grad (H,W,2)) of `dtype`."""
-        if formula == 'div_corrected':
-            raise IndexError("blobness_formula='div_corrected' is broken in the reference "
-                             "(pipeline_with_delitions.py:77, list-of-mask indexing)")
-        if formula not in _lib.FORMULA:
-            raise NotImplementedError
-        if grad_type not in _lib.GRAD:
-            raise AttributeError('grad_type {0} is not implemented'.format(grad_type))
-        assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.dim() == 2
-        H, W = img_u8.shape
+    _SCALE_CACHE = {}
+
+    @classmethod
+    def _scale_tables(cls, scales):
+        """Per-scale Gaussian half kernels / radii / sigma^2 (host parameter tables, cached)."""
+        hit = cls._SCALE_CACHE.get(scales)
+        if hit is not None:
+            return hit
         ns = len(scales)
         if ns < 1 or ns > _lib.MAX_SCALES:
             raise ValueError("1..%d scales" % _lib.MAX_SCALES)
@@ -116,6 +123,23 @@ class Engine:
             wts[i, :r + 1] = w
             radii[i] = r
             s2[i] = float(s) * float(s)
+        cls._SCALE_CACHE[scales] = (wts, radii, s2)
+        return wts, radii, s2
+
+    def blobness(self, img_u8, formula='custom', grad_type='np_grad', scales=(1.0,), dtype=torch.float64,
+                 want_grad=True, out=None):
+        """u8 (H,W) device tensor -> (R_b (H,W), grad (H,W,2)) of `dtype`."""
+        if formula == 'div_corrected':
+            raise IndexError("blobness_formula='div_corrected' is broken in the reference "
+                             "(pipeline_with_delitions.py:77, list-of-mask indexing)")
+        if formula not in _lib.FORMULA:
+            raise NotImplementedError
+        if grad_type not in _lib.GRAD:
+            raise AttributeError('grad_type {0} is not implemented'.format(grad_type))
+        assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.dim() == 2
+        H, W = img_u8.shape
+        ns = len(scales)
+        wts, radii, s2 = self._scale_tables(tuple(float(s) for s in scales))
         if out is None:
             Rb = self.empty((H, W), dtype)
             grad = self.empty((H, W, 2), dtype) if want_grad else None

@@ -116,7 +116,9 @@ def _track(result, pm, lsa_mean, lsa_var, blob_mean, n_gt, n_particles, use_wand
 
 
 def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, experiment_idx=0, trace=None,
-               log_fn=None):
+               log_fn=None, engine=None):
+    """`trace`, `log_fn`, `engine` are extensions: a stage recorder, a sink for the per-iteration log
+    records the reference sends to wandb, and a caller-owned Engine (one per concurrent stream)."""
     result = {
         'best_lsa_mean': +np.inf,
         'best_blobEn_mean': -np.inf,
@@ -141,9 +143,11 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     if trace is not None:
         mode = 'staged'
 
-    eng = get_engine(H, W, n_gt=GT_data.shape[0])
+    eng = engine if engine is not None else get_engine(H, W, n_gt=GT_data.shape[0])
+    if eng.H != H or eng.W != W or eng.gt_cap < GT_data.shape[0]:
+        raise ValueError('engine was created for a different padded shape / GT capacity')
     eng.status(clear=True)
-    d_img = eng.dev(img, torch.uint8)
+    d_img = eng.upload_image(img)
     d_gt = eng.dev(GT_data, torch.float64)
     Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype)
     eng.raise_on_status()                               # assert (eigs[0] > eigs[1]).all()  (:43)

@@ -101,7 +101,7 @@ def calc_blobness(img, cur_config=None, scales=None, dtype=np.float64, return_gr
         scales = cfg.get('blobness_scales', (1.0,)) if hasattr(cfg, 'get') else (1.0,)
     eng = get_engine(*img.shape)
     tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
-    Rb, grad = eng.blobness(eng.dev(img, torch.uint8), formula, grad_type, tuple(scales), tdt,
+    Rb, grad = eng.blobness(eng.upload_image(img), formula, grad_type, tuple(scales), tdt,
                             want_grad=return_grad)
     eng.raise_on_status()
     if return_grad:

@@ -114,6 +114,8 @@ typedef struct {
 const char* aoslo_version(void);
 const char* aoslo_last_cuda_error(void);
 int aoslo_device_count(void);
+/* number of kernels this library has launched in this process (monotonic counter) */
+long long aoslo_launch_count(void);
 
 /* ---- context: owns all scratch (cell lists, kNN tables, scan spines, status word) ------ */
 int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int particle_capacity, int gt_capacity);

@@ -67,6 +67,19 @@ def test_blobness_ragged_shapes(shape):
     assert np.abs(g - orc.calc_grad_field(ref, 'np_grad')).max() <= 5e-14
 
 
+@pytest.mark.parametrize("shape", [(37, 53), (64, 64), (2, 2), (33, 2), (130, 97), (300, 113), (17, 260), (70, 225)])
+def test_blobness_f32_fast_path_ragged_shapes(shape):
+    """The f32 column-marching kernel (strip / chunk seams, one-sided edges) against the f64 oracle."""
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
+    gref = orc.calc_grad_field(ref, 'np_grad')
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                    dtype=np.float32, return_grad=True)
+    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+
+
 def test_blobness_sobel_and_simple_div(zoo_field):
     cfg, img, gt, Rb, grad = zoo_field
     rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'sobel'},
