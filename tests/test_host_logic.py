@@ -1,0 +1,138 @@
+"""CPU tests: C-ABI surface, config packing, host geometry, sharding + gloo all-gather (world_size 2)."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from detecting_cones_aoslo_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "aoslo_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(aoslo_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
+    for name in declared:
+        assert getattr(_lib.lib, name) is not None           # bound by ctypes at import
+    assert _lib.lib.aoslo_version().decode().startswith("aoslo_b200")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "detecting_cones_aoslo_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from detecting_cones_aoslo_b200 import utils
+    with pytest.raises(RuntimeError):
+        utils.calc_blobness(np.zeros((16, 16), np.uint8) + 7, {'blobness_formula': 'custom',
+                                                               'gradient_type': 'np_grad'})
+
+
+def test_crop_and_pad_match_oracle():
+    from detecting_cones_aoslo_b200 import image_transformation as it
+    from oracle import aoslo_oracle as orc
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=(60, 70), dtype=np.uint8)
+    gt = rng.random((200, 2)) * [70, 60]
+    region = {'x_min': 5, 'x_max': 61, 'y_min': 3, 'y_max': 50}
+    a_img, _, a_gt = it.crop_image(img, None, gt.copy(), region)
+    b_img, _, b_gt = orc.crop_image(img, None, gt.copy(), region)
+    np.testing.assert_array_equal(a_img, b_img)
+    np.testing.assert_array_equal(a_gt, b_gt)
+    pa, ga = it.mirror_padding_image(a_img, {'x': 7, 'y': 4}, a_gt.copy())
+    pb, gb = orc.mirror_padding_image(b_img, {'x': 7, 'y': 4}, b_gt.copy())
+    np.testing.assert_array_equal(pa, pb)
+    np.testing.assert_array_equal(ga, gb)
+    with pytest.raises(AssertionError):
+        it.crop_image(img, None, gt.copy(), {'x_min': 0, 'x_max': 70, 'y_min': 0, 'y_max': 10})
+
+
+def test_config_struct_packing_and_errors():
+    from detecting_cones_aoslo_b200 import configs
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import make_config_struct
+    c = make_config_struct(configs.zoo_config(), 549, 552)
+    assert (c.H, c.W, c.bx, c.by) == (549, 552, 17, 17)
+    assert c.dist_n_neighbours == 3 and c.reception_field_size == 21 and c.tie_mode == 1 and c.early_stop == 1
+    assert c.threshhold_dist_del == 3.5 and c.thinning_threshold == 3.0
+    with pytest.raises(TypeError):                      # float window: range() TypeError in the reference
+        make_config_struct(configs.variant(configs.zoo_config(), particle_call_window=5.5), 549, 552)
+    with pytest.raises(AttributeError):
+        make_config_struct(configs.variant(configs.zoo_config(), dist_energy_type='nope'), 549, 552)
+
+
+def test_sweep_sampler_is_deterministic_and_in_range():
+    from detecting_cones_aoslo_b200 import configs, sweep
+    a = sweep.sample_trial(configs.zoo_config(), 17)
+    b = sweep.sample_trial(configs.zoo_config(), 17)
+    assert a == b
+    for i in range(50):
+        c = sweep.sample_trial(configs.zoo_config(), i)
+        assert 0.05 <= c['lambda_dist'] <= 2.0 and 1 <= c['dist_n_neighbours'] <= 6
+        assert isinstance(c['particle_call_window'], int) and 5 <= c['particle_call_window'] <= 9
+        assert 4 <= c['fix_particles_frequency'] <= 8 and c['reception_field_size'] == 19
+
+
+def test_shards_partition_the_units():
+    from detecting_cones_aoslo_b200 import sweep
+    for n, w in ((1024, 8), (256, 8), (10, 4), (3, 8), (7, 2)):
+        seen = [u for r in range(w) for u in sweep.shard_units(n, r, w)]
+        assert seen == list(range(n))
+
+
+def _worker(rank, world, port, n_units, out_dir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from detecting_cones_aoslo_b200 import sweep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def run_unit(u):
+        if u == 5:
+            raise RuntimeError("a failing trial must not kill the rank")
+        rng = np.random.default_rng(u)
+        rec = np.zeros(sweep.RECORD_LEN)
+        rec[0] = u
+        rec[1:] = rng.integers(0, 10000, sweep.RECORD_LEN - 1)
+        return rec
+
+    table = sweep.run_sharded(sweep.shard_units(n_units, rank, world), run_unit, n_units)
+    np.save(os.path.join(out_dir, "table_%d.npy" % rank), table)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_single_rank(tmp_path):
+    """N>1 path on CPU: gloo, world_size 2; the gathered table equals the 1-rank table bit for bit."""
+    import torch.multiprocessing as mp
+    from detecting_cones_aoslo_b200 import sweep
+    n_units = 11
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, n_units, str(tmp_path)), nprocs=2, join=True)
+    t0 = np.load(tmp_path / "table_0.npy")
+    t1 = np.load(tmp_path / "table_1.npy")
+
+    def run_unit(u):
+        if u == 5:
+            raise RuntimeError
+        rng = np.random.default_rng(u)
+        rec = np.zeros(sweep.RECORD_LEN)
+        rec[0] = u
+        rec[1:] = rng.integers(0, 10000, sweep.RECORD_LEN - 1)
+        return rec
+
+    single = sweep.run_sharded(range(n_units), run_unit, n_units)
+    assert t0.shape == (n_units, sweep.RECORD_LEN)
+    np.testing.assert_array_equal(t0, t1)
+    np.testing.assert_array_equal(t0, single)
+    assert t0[5, 1] == -1 and np.isnan(t0[5, 2])           # the failed unit is recorded, not fatal
