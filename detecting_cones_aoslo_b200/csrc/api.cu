@@ -26,7 +26,9 @@ int set_cuda_error(cudaError_t e, const char* where) {
 int stage_knn(aoslo_ctx*, cudaStream_t, const double*, int, const double*, int, int, int, int32_t*, double*, bool,
               const int* d_n);
 int stage_delete(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, const void*, int, int, int, double, int,
-                 double*, uint8_t*, uint8_t*, int*, int*, const int* d_n);
+                 double*, uint8_t*, uint8_t*, int*, int*, const int* d_n, int mode);
+int stage_force_move(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, int, int, double, double, double,
+                     const void*, int, int, int, double, double, int, double*, const int* d_n, bool links_ready);
 int stage_seed(aoslo_ctx*, cudaStream_t, const void*, int, int, int, int, int, double, double*, int, int*);
 int stage_lut(aoslo_ctx*, cudaStream_t, int, double, double, double, double*);
 int stage_gravity(aoslo_ctx*, cudaStream_t, const double*, int, int, int, double*, bool packed_ready);
@@ -87,6 +89,17 @@ int aoslo::kd_reserve(aoslo_ctx* c) {
 }
 namespace aoslo {
 
+static int alloc_links(CellLinks& lk, int H, int W, int cap, int shift) {
+    lk.shift = shift;
+    lk.gw = (W + (1 << shift) - 1) >> shift;
+    lk.gh = (H + (1 << shift) - 1) >> shift;
+    lk.ncell = lk.gw * lk.gh;
+    lk.cap = cap;
+    AOSLO_TRY(dmalloc(&lk.head, lk.ncell));
+    AOSLO_TRY(dmalloc(&lk.next, cap));
+    return AOSLO_OK;
+}
+
 static void free_cell_list(CellList& cl) {
     cudaFree(cl.count); cudaFree(cl.start); cudaFree(cl.slot); cudaFree(cl.cell_of);
     cudaFree(cl.sorted_idx); cudaFree(cl.sorted_pos);
@@ -139,6 +152,15 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         st = AOSLO_ERR_CUDA;
     A(alloc_cell_list(c->cl_p, H, W, cap, shift));
     A(alloc_cell_list(c->cl_g, H, W, gcap, shift));
+    {
+        int lshift = 3;
+        if (const char* e = getenv("AOSLO_LINK_SHIFT")) { int v = atoi(e); if (v >= 1 && v <= 6) lshift = v; }
+        A(alloc_links(c->lk_p, H, W, cap, lshift));
+    }
+    A(dmalloc(&c->d_pos_tmp, (size_t)cap * 2));
+    A(dmalloc(&c->d_active, cap));
+    A(dmalloc(&c->d_active_b, cap));
+    A(dmalloc(&c->d_ns_list, cap));
     A(dmalloc(&c->d_knn_idx, kn));
     A(dmalloc(&c->d_knn_d2, kn));
     A(dmalloc(&c->d_block_sums, kMaxScanBlocks + 1));
@@ -169,6 +191,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) st = AOSLO_ERR_CUDA;
 #undef A
     if (st == AOSLO_OK && cudaMemset(c->d_status, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_counters, 0, sizeof(int) * 32) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st != AOSLO_OK) { aoslo_ctx_destroy(c); return st; }
     *out = c;
@@ -180,6 +203,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_status); cudaFree(c->d_counters); cudaFreeHost(c->h_pinned);
     free_cell_list(c->cl_p); free_cell_list(c->cl_g);
+    cudaFree(c->lk_p.head); cudaFree(c->lk_p.next); cudaFree(c->d_pos_tmp); cudaFree(c->d_active); cudaFree(c->d_active_b); cudaFree(c->d_ns_list);
     cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_block_sums);
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
@@ -234,7 +258,7 @@ extern "C" int aoslo_delete_close(aoslo_ctx* ctx, void* stream, const double* d_
     if (H != ctx->H || W != ctx->W) return AOSLO_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     AOSLO_TRY(stage_delete(ctx, s, d_particles, d_stable, n, d_Rb, field_dtype, H, W, threshold, tie_mode,
-                           d_particles_out, d_stable_out, d_deleted_out, ctx->d_counters, ctx->d_counters + 1, nullptr));
+                           d_particles_out, d_stable_out, d_deleted_out, ctx->d_counters, ctx->d_counters + 1, nullptr, 0));
     return read_int(ctx, s, ctx->d_counters, h_n_out);
 }
 
@@ -357,7 +381,7 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
         int n_new = 0;
         AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
                                cfg->thinning_threshold, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
-                               nullptr, d_cnt[cur ^ 1], nullptr, nullptr));
+                               nullptr, d_cnt[cur ^ 1], nullptr, nullptr, 0));
         AOSLO_TRY(read_int(ctx, s, d_cnt[cur ^ 1], &n_new));
         cur ^= 1;
         ++rounds;
@@ -393,22 +417,38 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     const int k = cfg->dist_n_neighbours;
     const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
     int n_rec = 0, it_done = 0;
+    bool links_valid = false;                        // ctx->lk_p describes d_pos[cur]
     AOSLO_TRY(mark(-1));
     for (int it = 0; it < cfg->epoch_num; ++it) {
         ++it_done;
         if (n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
         // `n` is exact in the synchronising mode and an upper bound of the device count otherwise
         const int* dn = on_device ? d_cnt[cur] : nullptr;
-        AOSLO_TRY(stage_force(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type,
-                              pit ? cfg->mu_dist_func : cfg->dist_alpha, pit ? cfg->sigma_dist_func : cfg->dist_sigma,
-                              pit ? cfg->lambda_dist_func : 0.0, cfg->tie_mode, ctx->d_force, dn));
-        AOSLO_TRY(mark(0));
-        AOSLO_TRY(stage_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W, ctx->d_force,
-                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
-        AOSLO_TRY(mark(1));
-        AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
+        const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+        const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+        const double e2 = pit ? cfg->lambda_dist_func : 0.0;
+        const double* moved;
+        if (on_device) {
+            // one launch: kNN on the linked cells + force + Jacobi move into d_pos_tmp
+            AOSLO_TRY(stage_force_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0,
+                                       e1, e2, d_grad, field_dtype, H, W, cfg->lambda_blob, cfg->lambda_dist,
+                                       cfg->step_mode, ctx->d_pos_tmp, dn, links_valid));
+            links_valid = false;
+            moved = ctx->d_pos_tmp;
+            AOSLO_TRY(mark(0));
+            AOSLO_TRY(mark(1));
+        } else {
+            AOSLO_TRY(stage_force(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0, e1,
+                                  e2, cfg->tie_mode, ctx->d_force, dn));
+            AOSLO_TRY(mark(0));
+            AOSLO_TRY(stage_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W,
+                                 ctx->d_force, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
+            AOSLO_TRY(mark(1));
+            moved = ctx->d_pos[cur];
+        }
+        AOSLO_TRY(stage_delete(ctx, s, moved, ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
                                cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
-                               nullptr, d_cnt[cur ^ 1], nullptr, dn));
+                               nullptr, d_cnt[cur ^ 1], nullptr, dn, on_device ? 2 : 1));
         cur ^= 1;
         if (!on_device) AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
         dn = on_device ? d_cnt[cur] : nullptr;
@@ -419,6 +459,7 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
             AOSLO_TRY(stage_metrics(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
                                     field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec, ctx->d_dist_p2g,
                                     ctx->d_dist_g2p, dn));
+            links_valid = on_device;                 // the metrics pass left links of d_pos[cur] behind
             ++n_rec;
         }
         if (cfg->early_stop) {

@@ -65,6 +65,24 @@ inline CellView view_of(const CellList& c) {
     return CellView{c.shift, c.gw, c.gh, c.start, c.sorted_idx, c.sorted_pos};
 }
 
+// Scan-free cell structure for kNN: per-cell singly linked lists (head[cell], next[particle]).
+// Built by one memset + one kernel (atomicExch); chain order is arbitrary, which is fine because
+// neighbour selection uses the strict total order (d^2, index).
+struct CellLinks {
+    int shift = 3;
+    int gw = 0, gh = 0, ncell = 0;
+    int* head = nullptr;         // [ncell]  -1 = empty
+    int* next = nullptr;         // [cap]
+    int cap = 0;
+};
+
+struct LinkView {
+    int shift, gw, gh;
+    const int* head;
+    const int* next;
+    const double2* pos;
+};
+
 // sklearn-order KD tree mirrored on the device (built on the host, kdtree_host.cpp)
 struct KdTreeDev {
     int n = 0, n_nodes = 0;
@@ -95,6 +113,12 @@ struct aoslo_ctx {
     int* h_pinned = nullptr;          // [32] pinned readback
     aoslo::CellList cl_p;             // particles
     aoslo::CellList cl_g;             // ground truth
+    aoslo::CellLinks lk_p;            // particles (kNN)
+    double* d_pos_tmp = nullptr;      // [cap*2] moved positions (Jacobi move writes here)
+    int* d_active = nullptr;          // [cap] compact list of active deletion rows (non-stable path)
+    int* d_active_b = nullptr;        // [cap] same, all-rows fallback
+    int* d_ns_list = nullptr;         // [cap] compact list of non-stable particles
+    unsigned int epoch = 0;           // deletion call counter (stamps `touch`, no per-call reset)
     int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
     double* d_knn_d2 = nullptr;
     int* d_block_sums = nullptr;      // [kMaxScanBlocks + 1]
@@ -235,6 +259,7 @@ __device__ __forceinline__ double fld(const T* p, long long i) {
 // (kd_reserve: api.cu)
 // ---------------------------------------------------------------------------------------
 int kd_reserve(aoslo_ctx* ctx);
+int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,
               const int* d_nq, int k, int32_t* d_idx, double* d_d2, int n_points_host, const int* d_np);

@@ -231,6 +231,177 @@ int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* 
 }
 
 // =======================================================================================
+// scan-free linked cells: build (memset + 1 kernel) and the same exact ring search
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restrict__ pos, int n_host,
+                                                        const int* d_n, int shift, int gw, int gh, int W, int H,
+                                                        int* head, int* next, int* status) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double2 p = pos[i];
+        bool bad = false;
+        int cx = cell_coord(p.x, shift, gw, bad);
+        int cy = cell_coord(p.y, shift, gh, bad);
+        if (p.x != p.x || p.y != p.y) atomicOr(status, AOSLO_DEV_NAN);
+        else if (bad || p.x >= (double)W || p.y >= (double)H) atomicOr(status, AOSLO_DEV_ESCAPED);
+        next[i] = atomicExch(&head[cy * gw + cx], i);
+    }
+}
+
+int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n) {
+    AOSLO_CUDA(cudaMemsetAsync(lk.head, 0xff, sizeof(int) * lk.ncell, s));
+    link_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh, ctx->W,
+                                             ctx->H, lk.head, lk.next, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+inline LinkView link_view(const CellLinks& lk, const double* d_pos) {
+    return LinkView{lk.shift, lk.gw, lk.gh, lk.head, lk.next, (const double2*)d_pos};
+}
+
+template <int K>
+__device__ __forceinline__ void knn_links_cell(const LinkView& lv, int cell, double qx, double qy, TopK<K>& top) {
+    for (int p = lv.head[cell]; p >= 0; p = lv.next[p]) {
+        double2 t = lv.pos[p];
+        double dx = qx - t.x, dy = qy - t.y;
+        top.push(dx * dx + dy * dy, p);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void knn_links_query(const LinkView& lv, double qx, double qy, TopK<K>& top) {
+    top.init();
+    const int c = 1 << lv.shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> lv.shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> lv.shift) : 0;
+    cx = min(cx, lv.gw - 1);
+    cy = min(cy, lv.gh - 1);
+    const int rmax = max(lv.gw, lv.gh);
+    for (int r = 0; r <= rmax; ++r) {
+        const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+        for (int y = max(ylo, 0); y <= min(yhi, lv.gh - 1); ++y) {
+            if (y == ylo || y == yhi) {
+                for (int x = max(xlo, 0); x <= min(xhi, lv.gw - 1); ++x)
+                    knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, top);
+            } else {
+                if (xlo >= 0) knn_links_cell<K>(lv, y * lv.gw + xlo, qx, qy, top);
+                if (xhi < lv.gw) knn_links_cell<K>(lv, y * lv.gw + xhi, qx, qy, top);
+            }
+        }
+        double bound = INFINITY;
+        if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
+        if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
+        if (xhi < lv.gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < lv.gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (bound == INFINITY) break;
+        if (bound > 0.0 && top.d2[K - 1] < bound * bound) break;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) knn_links_kernel(LinkView lv, const double2* __restrict__ q,
+                                                             int nq_host, const int* d_nq, int k,
+                                                             int32_t* out_idx, double* out_d2, int* status) {
+    int nq = d_nq ? *d_nq : nq_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
+        double2 p = q[i];
+        TopK<K> top;
+        knn_links_query<K>(lv, p.x, p.y, top);
+        bool shortfall = false;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < k) {
+                bool empty = top.idx[j] == 0x7fffffff;
+                shortfall |= empty;
+                out_idx[(size_t)i * k + j] = empty ? -1 : top.idx[j];
+                out_d2[(size_t)i * k + j] = top.d2[j];
+            }
+        }
+        if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+    }
+}
+
+int knn_links(aoslo_ctx* ctx, cudaStream_t s, const LinkView& v, const double* d_query, int nq_host,
+              const int* d_nq, int k, int32_t* d_idx, double* d_d2) {
+    const double2* q = (const double2*)d_query;
+    if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (k == 1) knn_links_kernel<1><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else if (k == 2) knn_links_kernel<2><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else if (k <= 4) knn_links_kernel<4><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    else knn_links_kernel<8><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// =======================================================================================
+// warp-cooperative exact kNN: the 32 lanes split the cells of a ring, keep private top-K lists
+// and merge them with shuffles; the dependent-load chain of a query shrinks from ~25 cells to
+// 1-2, which is what bounds the in-loop kernels (only the few non-stable particles are queried).
+// =======================================================================================
+template <int K>
+__device__ __forceinline__ void warp_merge_topk(const TopK<K>& mine, TopK<K>& out) {
+    // K rounds of warp arg-min over the lanes' list heads by the strict order (d2, idx)
+    TopK<K> t = mine;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        double bd = t.d2[0];
+        int bi = t.idx[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        out.d2[j] = bd;
+        out.idx[j] = bi;
+        if (t.idx[0] == bi && bi != 0x7fffffff) {          // this lane owned the winner: pop it
+#pragma unroll
+            for (int m = 0; m < K - 1; ++m) { t.d2[m] = t.d2[m + 1]; t.idx[m] = t.idx[m + 1]; }
+            t.d2[K - 1] = INFINITY;
+            t.idx[K - 1] = 0x7fffffff;
+        }
+    }
+}
+
+// every lane passes the same query; on return `out` (replicated in all lanes) holds the K nearest
+template <int K>
+__device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double qx, double qy, TopK<K>& out) {
+    const int lane = threadIdx.x & 31;
+    TopK<K> mine;
+    mine.init();
+    out.init();
+    const int c = 1 << lv.shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> lv.shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> lv.shift) : 0;
+    cx = min(cx, lv.gw - 1);
+    cy = min(cy, lv.gh - 1);
+    const int rmax = max(lv.gw, lv.gh);
+    for (int r = 0; r <= rmax; ++r) {
+        const int ncells = (r == 0) ? 1 : 8 * r;
+        for (int j = lane; j < ncells; j += 32) {
+            int dx, dy;
+            if (r == 0) { dx = 0; dy = 0; }
+            else if (j <= 2 * r) { dx = -r + j; dy = -r; }
+            else if (j <= 4 * r + 1) { dx = -r + (j - 2 * r - 1); dy = r; }
+            else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
+            else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
+            const int x = cx + dx, y = cy + dy;
+            if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+        }
+        warp_merge_topk<K>(mine, out);
+        const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+        double bound = INFINITY;
+        if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
+        if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
+        if (xhi < lv.gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < lv.gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (bound == INFINITY) break;
+        if (bound > 0.0 && out.d2[K - 1] < bound * bound) break;
+    }
+}
+
+// =======================================================================================
 // exact kNN in sklearn's order: depth-first single-tree query of KDTree(leaf_size=1)
 // (sklearn/neighbors/_binary_tree.pxi.tp:1603-1656, _kd_tree.pyx.tp:128-145,
 //  sklearn/utils/_heap.pyx:heap_push, sklearn/utils/_sorting.pyx: insertion sort for n <= 15)
@@ -478,6 +649,109 @@ __global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p
     if (tid == 0 && p.rounds_out) *p.rounds_out = round;
 }
 
+// kNN(k=2) rows of the deletion step on the linked cells + compact list of the active rows
+// (rows whose `from` is not stable and whose neighbour is closer than the threshold)
+__global__ void __launch_bounds__(kThreads) knn2_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
+                                                             int n_host, const int* d_n, double thr,
+                                                             int32_t* knn_idx, double* knn_d2, uint8_t* del,
+                                                             int* active, int* n_active, int* status,
+                                                             const int* gate) {
+    if (gate && *gate == 0) return;            // fallback of the non-stable-list path: nothing coincided
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double2 p = lv.pos[i];
+        TopK<2> top;
+        knn_links_query<2>(lv, p.x, p.y, top);
+        bool ok = top.idx[1] != 0x7fffffff;
+        if (!ok) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+        int from = top.idx[0], to = ok ? top.idx[1] : -1;
+        knn_idx[2 * (size_t)i] = from;
+        knn_idx[2 * (size_t)i + 1] = to;
+        knn_d2[2 * (size_t)i] = top.d2[0];
+        knn_d2[2 * (size_t)i + 1] = top.d2[1];
+        del[i] = 0;
+        if (ok && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
+    }
+}
+
+// same collection from an existing kNN table (sklearn-order path)
+__global__ void __launch_bounds__(kThreads) collect_active_kernel(const int32_t* __restrict__ knn_idx,
+                                                                  const double* __restrict__ knn_d2,
+                                                                  const uint8_t* __restrict__ stable, int n_host,
+                                                                  const int* d_n, double thr, uint8_t* del,
+                                                                  int* active, int* n_active) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int from = knn_idx[2 * (size_t)i], to = knn_idx[2 * (size_t)i + 1];
+        del[i] = 0;
+        if (to >= 0 && from >= 0 && !stable[from] && sqrt(knn_d2[2 * (size_t)i + 1]) < thr)
+            active[atomicAdd(n_active, 1)] = i;
+    }
+}
+
+// The same wavefront resolution as delete_resolve_kernel, for the in-loop case where only the
+// rows of the few non-stable particles are active: ONE block walks the compact active list, so it
+// needs no cooperative launch / grid sync and does not monopolise the GPU (other frames keep
+// running next to it).  `touch` is never reset: keys carry a per-call epoch.
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
+    const double2* __restrict__ pos, const int32_t* __restrict__ knn_idx, const int* __restrict__ active_a,
+    int* n_active_a, const int* __restrict__ active_b, int* n_active_b, int* fallback, int* n_ns,
+    unsigned int epoch, int W, int H, const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del,
+    uint8_t* astate, int* status) {
+    __shared__ int s_pending;
+    // list B (all-rows fallback) supersedes list A (non-stable rows) when the fallback ran
+    const bool use_b = active_b != nullptr && fallback != nullptr && *fallback != 0;
+    const int* __restrict__ active = use_b ? active_b : active_a;
+    const int na = use_b ? *n_active_b : *n_active_a;
+    for (int a = threadIdx.x; a < na; a += blockDim.x) astate[a] = 1;
+    __syncthreads();
+    for (unsigned int round = 1;; ++round) {
+        const unsigned long long hi = ((unsigned long long)epoch << 44) | ((unsigned long long)round << 32);
+        for (int a = threadIdx.x; a < na; a += blockDim.x) {
+            if (!astate[a]) continue;
+            int i = active[a];
+            unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            atomicMax(&touch[knn_idx[2 * (size_t)i]], key);
+            atomicMax(&touch[knn_idx[2 * (size_t)i + 1]], key);
+        }
+        if (threadIdx.x == 0) s_pending = 0;
+        __threadfence();
+        __syncthreads();
+        int pending = 0;
+        for (int a = threadIdx.x; a < na; a += blockDim.x) {
+            if (!astate[a]) continue;
+            int i = active[a];
+            int from = knn_idx[2 * (size_t)i], to = knn_idx[2 * (size_t)i + 1];
+            unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            if (__ldcg(&touch[from]) == key && __ldcg(&touch[to]) == key) {
+                if (!__ldcg(&del[from]) && !__ldcg(&del[to])) {
+                    double e1 = energy_at<T>(Rb, pos[from], W, H, status);
+                    double e2 = energy_at<T>(Rb, pos[to], W, H, status);
+                    __stcg(&del[(e1 < e2) ? from : to], (uint8_t)1);
+                }
+                astate[a] = 0;
+            } else {
+                ++pending;
+            }
+        }
+        if (pending) atomicAdd(&s_pending, pending);
+        __threadfence();
+        __syncthreads();
+        int left = s_pending;
+        __syncthreads();
+        if (left == 0) break;
+        if (round >= 4000u) { if (threadIdx.x == 0) atomicOr(status, AOSLO_DEV_CAPACITY); break; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                   // ready for the next call
+        *n_active_a = 0;
+        if (n_active_b) *n_active_b = 0;
+        if (fallback) *fallback = 0;
+        if (n_ns) *n_ns = 0;
+    }
+}
+
 struct KeepOp {
     const double2* pos;
     const uint8_t* stable;
@@ -622,6 +896,35 @@ struct AppendOp {
 // =======================================================================================
 // distance force (utils.py:112-134 'pit', :43-58 'exp')
 // =======================================================================================
+// force of one particle from its neighbour list (column 0 = "self" is dropped, utils.py:32)
+template <int KMAX>
+__device__ __forceinline__ double2 force_from_neighbours(double2 p, const int* nb_idx, int kk,
+                                                         const double2* __restrict__ pos, int energy_type,
+                                                         double p0, double p1, double p2) {
+    double fx = 0.0, fy = 0.0;
+#pragma unroll
+    for (int j = 1; j < KMAX; ++j) {
+        if (j >= kk) break;
+        int nb = nb_idx[j];
+        double2 q = (nb >= 0 && nb != 0x7fffffff) ? pos[nb] : make_double2(NAN, NAN);
+        double vx = p.x - q.x, vy = p.y - q.y;
+        double nrm = sqrt(vx * vx + vy * vy);
+        double dx, dy;
+        if (energy_type == AOSLO_ENERGY_PIT) {
+            double f = energy_pit2(nrm, p0, p1, p2);
+            dx = (vx / nrm) * f;
+            dy = (vy / nrm) * f;
+        } else {                                // 'exp': vec / (norm / sigma^2); alpha applied after the sum
+            double den = nrm / (p1 * p1);
+            dx = vx / den;
+            dy = vy / den;
+        }
+        if (j == 1) { fx = dx; fy = dy; } else { fx += dx; fy += dy; }
+    }
+    if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
+    return make_double2(fx, fy);
+}
+
 __global__ void __launch_bounds__(kThreads) dist_force_kernel(const double2* __restrict__ pos,
                                                               const uint8_t* __restrict__ stable, int n_host,
                                                               const int* d_n, const int32_t* __restrict__ knn_idx,
@@ -629,30 +932,10 @@ __global__ void __launch_bounds__(kThreads) dist_force_kernel(const double2* __r
                                                               double p0, double p1, double p2, double2* force) {
     int n = d_n ? *d_n : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double fx = 0.0, fy = 0.0;
         bool skip = (energy_type == AOSLO_ENERGY_PIT) && stable && stable[i];
-        if (!skip) {
-            double2 p = pos[i];
-            for (int j = 1; j < kk; ++j) {             // column 0 ("self") is dropped, utils.py:32
-                int nb = knn_idx[(size_t)i * kk + j];
-                double2 q = (nb >= 0) ? pos[nb] : make_double2(NAN, NAN);
-                double vx = p.x - q.x, vy = p.y - q.y;
-                double nrm = sqrt(vx * vx + vy * vy);
-                double dx, dy;
-                if (energy_type == AOSLO_ENERGY_PIT) {
-                    double f = energy_pit2(nrm, p0, p1, p2);
-                    dx = (vx / nrm) * f;
-                    dy = (vy / nrm) * f;
-                } else {                                // 'exp': vec / (norm / sigma^2); alpha applied after the sum
-                    double den = nrm / (p1 * p1);
-                    dx = vx / den;
-                    dy = vy / den;
-                }
-                if (j == 1) { fx = dx; fy = dy; } else { fx += dx; fy += dy; }
-            }
-            if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
-        }
-        force[i] = make_double2(fx, fy);
+        double2 f = make_double2(0.0, 0.0);
+        if (!skip) f = force_from_neighbours<AOSLO_KMAX>(pos[i], knn_idx + (size_t)i * kk, kk, pos, energy_type, p0, p1, p2);
+        force[i] = f;
     }
 }
 
@@ -665,6 +948,40 @@ __device__ __forceinline__ double np_sign(double v) {
     return v;   // 0 -> 0, NaN -> NaN
 }
 
+// returns false (and flags the status word) when the particle cannot be moved
+template <typename T>
+__device__ __forceinline__ bool move_one(double2& p, double2 f, const T* __restrict__ grad, int H, int W, double lb,
+                                         double ld, int step_mode, int* status) {
+    if (p.x != p.x || p.y != p.y) { atomicOr(status, AOSLO_DEV_NAN); return false; }
+    int ix = (int)p.x, iy = (int)p.y;
+    if (ix < 0 || ix >= W || iy < 0 || iy >= H) {   // reference: IndexError / silent negative wrap
+        atomicOr(status, AOSLO_DEV_ESCAPED);
+        return false;
+    }
+    size_t o = ((size_t)iy * W + ix) * 2;
+    double g0 = (double)grad[o], g1 = (double)grad[o + 1];
+    if (step_mode == AOSLO_STEP_CONTIN) {
+        double dy = (-1.0 * lb) * g0 + (-ld) * f.x;
+        double dx = (-1.0 * lb) * g1 + ld * f.y;
+        dy = -dy;
+        p.x += dx;
+        p.y += dy;
+    } else {
+        double delta_y = (-1.0 * lb) * g0 + (-ld) * f.y;
+        double delta_x = (-1.0 * lb) * g1 + ld * f.x;
+        delta_y = -delta_y;
+        double ax = fabs(delta_x), ay = fabs(delta_y);
+        if (ax > ay) {
+            p.x += np_sign(delta_x);
+            if (ax < ay * 2.0) p.y += np_sign(delta_y);
+        } else {
+            p.y += np_sign(delta_y);
+            if (ay < ax * 2.0) p.x += np_sign(delta_x);
+        }
+    }
+    return true;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint8_t* __restrict__ stable,
                                                         int n_host, const int* d_n, const T* __restrict__ grad,
@@ -674,35 +991,127 @@ __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (stable[i]) continue;
         double2 p = pos[i];
-        if (p.x != p.x || p.y != p.y) { atomicOr(status, AOSLO_DEV_NAN); continue; }
-        int ix = (int)p.x, iy = (int)p.y;
-        if (ix < 0 || ix >= W || iy < 0 || iy >= H) {   // reference: IndexError / silent negative wrap
-            atomicOr(status, AOSLO_DEV_ESCAPED);
-            continue;
+        if (move_one<T>(p, force[i], grad, H, W, lb, ld, step_mode, status)) pos[i] = p;
+    }
+}
+
+// fused force + move of the run loop: kNN on the linked cells, force, Jacobi move into pos_out.
+// Stable particles neither need a force (their move is skipped, :216) nor a neighbour search.
+template <int K, typename T>
+__global__ void __launch_bounds__(kThreads) knn_force_move_kernel(
+    LinkView lv, const uint8_t* __restrict__ stable, int n_host, const int* d_n, int kk, int energy_type, double p0,
+    double p1, double p2, const T* __restrict__ grad, int H, int W, double lb, double ld, int step_mode,
+    double2* __restrict__ pos_out, int* status) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double2 p = lv.pos[i];
+        if (!stable[i]) {
+            TopK<K> top;
+            knn_links_query<K>(lv, p.x, p.y, top);
+            bool shortfall = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j == kk - 1 && top.idx[j] == 0x7fffffff) shortfall = true;
+            if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            double2 f = force_from_neighbours<K>(p, top.idx, kk, lv.pos, energy_type, p0, p1, p2);
+            if (step_mode >= 0) move_one<T>(p, f, grad, H, W, lb, ld, step_mode, status);
         }
-        size_t o = ((size_t)iy * W + ix) * 2;
-        double g0 = (double)grad[o], g1 = (double)grad[o + 1];
-        double2 f = force[i];
-        if (step_mode == AOSLO_STEP_CONTIN) {
-            double dy = (-1.0 * lb) * g0 + (-ld) * f.x;
-            double dx = (-1.0 * lb) * g1 + ld * f.y;
-            dy = -dy;
-            p.x += dx;
-            p.y += dy;
-        } else {
-            double delta_y = (-1.0 * lb) * g0 + (-ld) * f.y;
-            double delta_x = (-1.0 * lb) * g1 + ld * f.x;
-            delta_y = -delta_y;
-            double ax = fabs(delta_x), ay = fabs(delta_y);
-            if (ax > ay) {
-                p.x += np_sign(delta_x);
-                if (ax < ay * 2.0) p.y += np_sign(delta_y);
+        pos_out[i] = p;
+    }
+}
+
+// ---- non-stable list path of the run loop (canonical tie order) --------------------------------
+// Only non-stable particles move (:216) and only rows whose `from` is non-stable can delete
+// (utils.py:253); `from` is the row's own particle unless two particles coincide.  So the loop works
+// on the compact list of non-stable particles with one WARP per query; a coincidence (distance 0 to
+// another particle) raises `fallback`, which re-runs the step on all rows (knn2_rows_kernel).
+__global__ void __launch_bounds__(kThreads) ns_prepare_kernel(const double2* __restrict__ pos,
+                                                              const uint8_t* __restrict__ stable, int n_host,
+                                                              const int* d_n, double2* __restrict__ pos_out,
+                                                              uint8_t* __restrict__ del, int* ns_list, int* n_ns) {
+    int n = d_n ? *d_n : n_host;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        pos_out[i] = pos[i];
+        del[i] = 0;
+        if (!stable[i]) ns_list[atomicAdd(n_ns, 1)] = i;
+    }
+}
+
+template <int K, typename T>
+__global__ void __launch_bounds__(kThreads) ns_force_move_kernel(
+    LinkView lv, const int* __restrict__ ns_list, const int* __restrict__ n_ns, int kk, int energy_type, double p0,
+    double p1, double p2, const T* __restrict__ grad, int H, int W, double lb, double ld, int step_mode,
+    double2* __restrict__ pos_out, int* status) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_ns;
+    for (int q = warp; q < total; q += nwarps) {
+        const int i = ns_list[q];
+        double2 p = lv.pos[i];
+        TopK<K> top;
+        knn_links_query_warp<K>(lv, p.x, p.y, top);
+        // lane j computes the term of neighbour j (column 0 is dropped); lane 0 sums them in order
+        int nb = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (lane == j) nb = top.idx[j];
+        double tx = 0.0, ty = 0.0;
+        if (lane >= 1 && lane < kk) {
+            double2 qn = (nb != 0x7fffffff) ? lv.pos[nb] : make_double2(NAN, NAN);
+            double vx = p.x - qn.x, vy = p.y - qn.y;
+            double nrm = sqrt(vx * vx + vy * vy);
+            if (energy_type == AOSLO_ENERGY_PIT) {
+                double f = energy_pit2(nrm, p0, p1, p2);
+                tx = (vx / nrm) * f;
+                ty = (vy / nrm) * f;
             } else {
-                p.y += np_sign(delta_y);
-                if (ay < ax * 2.0) p.x += np_sign(delta_x);
+                double den = nrm / (p1 * p1);
+                tx = vx / den;
+                ty = vy / den;
             }
         }
-        pos[i] = p;
+        double fx = __shfl_sync(0xffffffffu, tx, 1), fy = __shfl_sync(0xffffffffu, ty, 1);
+        for (int j = 2; j < kk; ++j) {
+            fx += __shfl_sync(0xffffffffu, tx, j);
+            fy += __shfl_sync(0xffffffffu, ty, j);
+        }
+        if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
+        if (lane == 0) {
+            bool shortfall = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j == kk - 1 && top.idx[j] == 0x7fffffff) shortfall = true;
+            if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            if (step_mode >= 0) move_one<T>(p, make_double2(fx, fy), grad, H, W, lb, ld, step_mode, status);
+            pos_out[i] = p;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) ns_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
+                                                           const int* __restrict__ ns_list,
+                                                           const int* __restrict__ n_ns, double thr,
+                                                           int32_t* knn_idx, double* knn_d2, int* active,
+                                                           int* n_active, int* fallback) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_ns;
+    for (int q = warp; q < total; q += nwarps) {
+        const int i = ns_list[q];
+        double2 p = lv.pos[i];
+        TopK<2> top;
+        knn_links_query_warp<2>(lv, p.x, p.y, top);
+        if (lane == 0) {
+            const bool ok = top.idx[1] != 0x7fffffff;
+            const int from = top.idx[0], to = ok ? top.idx[1] : -1;
+            // another particle at distance 0, or nothing found at all: the all-rows path decides
+            if (from != i || !ok || top.d2[1] == 0.0) atomicExch(fallback, 1);
+            knn_idx[2 * (size_t)i] = from;
+            knn_idx[2 * (size_t)i + 1] = to;
+            knn_d2[2 * (size_t)i] = top.d2[0];
+            knn_d2[2 * (size_t)i + 1] = top.d2[1];
+            if (ok && from == i && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
+        }
     }
 }
 
@@ -751,7 +1160,7 @@ struct MetricsPartial {          // one per block
 // written as per-block partials for the finalize kernel.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
-    CellView cl_g, CellView cl_p, const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host,
+    CellView cl_g, LinkView lk_p, const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host,
     const int* d_n, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W, int bx, int by,
     double* d_p2g, double* d_g2p, int* icount /*[8]*/, MetricsPartial* partials, int* status) {
     const int n = d_n ? *d_n : n_host;
@@ -778,7 +1187,7 @@ __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
             energy += energy_at<T>(Rb, p, W, H, status);
         } else {
             double2 g = gt[i - n];
-            knn_cells_query<1>(cl_p, g.x, g.y, top);
+            knn_links_query<1>(lk_p, g.x, g.y, top);
             if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
             double d = sqrt(top.d2[0]);
             if (d_g2p) d_g2p[i - n] = d;
@@ -893,31 +1302,83 @@ int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_poin
         if (d_n) return AOSLO_ERR_INVALID;
         return knn_sklearn(ctx, s, d_points, n_points, d_query, n_query, k, d_idx, d_d2);
     }
-    CellList& cl = tree_is_particles ? ctx->cl_p : ctx->cl_g;
-    if (n_points > cl.cap) return AOSLO_ERR_CAPACITY;
-    AOSLO_TRY(build_cell_list(ctx, s, cl, d_points, n_points, d_n));
-    return knn_cells(ctx, s, cl, d_query, n_query, d_n, k, d_idx, d_d2, n_points, d_n);
+    (void)tree_is_particles;
+    if (n_points > ctx->lk_p.cap) return AOSLO_ERR_CAPACITY;
+    AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_points, n_points, d_n));
+    return knn_links(ctx, s, link_view(ctx->lk_p, d_points), d_query, n_query, d_n, k, d_idx, d_d2);
 }
 
+static unsigned int next_epoch(aoslo_ctx* ctx, cudaStream_t s, int* err) {
+    *err = AOSLO_OK;
+    if (++ctx->epoch >= (1u << 20)) {              // 20-bit epoch in the touch keys: restart from a clean slate
+        if (cudaMemsetAsync(ctx->d_touch, 0, sizeof(unsigned long long) * ctx->cap, s) != cudaSuccess)
+            *err = AOSLO_ERR_CUDA;
+        ctx->epoch = 1;
+    }
+    return ctx->epoch;
+}
+
+// small = true: in-loop variant (compact active list + one resolving block, no cooperative launch)
 template <typename T>
 int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                    const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
-                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n) {
+                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode) {
+    // mode 0: cooperative all-rows resolve; 1: compact active list + one block; 2: as 1, rows taken from
+    // the non-stable list left by stage_force_move (canonical run loop)
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     if (n < 2) return AOSLO_ERR_INVALID;   // sklearn: n_neighbors=2 > n_samples
     if (d_n && d_n == d_n_out) return AOSLO_ERR_INVALID;   // the count is double-buffered
-    AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
-    DeleteParams p;
-    p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
-    p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.W = W; p.H = H;
-    p.touch = ctx->d_touch; p.del = ctx->d_del; p.rowstate = ctx->d_rowstate;
-    p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
-    void* args[] = {&p, (void*)&d_Rb};
-    int blocks = ctx->coop_blocks;
-    int need = (n + kThreads - 1) / kThreads;   // n is an upper bound when the count lives on the device
-    if (need < blocks) blocks = need < 1 ? 1 : need;
-    AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kThreads), args, 0, s));
-    count_launch();
+    int* n_active = ctx->d_counters + 12;
+    int* n_ns = ctx->d_counters + 13;
+    int* n_active_b = ctx->d_counters + 14;
+    int* fallback = ctx->d_counters + 15;
+    const bool small = mode != 0;
+    const bool use_ns = (mode == 2) && tie_mode == AOSLO_TIE_CANONICAL;
+    if (small) {
+        if (use_ns) {
+            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+            LinkView lv = link_view(ctx->lk_p, d_pos);
+            ns_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, ctx->d_ns_list, n_ns, thr, ctx->d_knn_idx,
+                                                        ctx->d_knn_d2, ctx->d_active, n_active, fallback);
+            AOSLO_LAUNCH_CHECK();
+            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, n, d_n, thr, ctx->d_knn_idx, ctx->d_knn_d2,
+                                                          ctx->d_del, ctx->d_active_b, n_active_b, ctx->d_status,
+                                                          fallback);
+            AOSLO_LAUNCH_CHECK();
+        } else if (tie_mode == AOSLO_TIE_CANONICAL) {
+            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx->lk_p, d_pos), d_stable, n, d_n, thr,
+                                                          ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_del, ctx->d_active,
+                                                          n_active, ctx->d_status, nullptr);
+            AOSLO_LAUNCH_CHECK();
+        } else {
+            AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
+            collect_active_kernel<<<ctx->nb, kThreads, 0, s>>>(ctx->d_knn_idx, ctx->d_knn_d2, d_stable, n, d_n, thr,
+                                                               ctx->d_del, ctx->d_active, n_active);
+            AOSLO_LAUNCH_CHECK();
+        }
+        int err;
+        unsigned int epoch = next_epoch(ctx, s, &err);
+        if (err != AOSLO_OK) return err;
+        delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
+            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_active, n_active, use_ns ? ctx->d_active_b : nullptr,
+            use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr, use_ns ? n_ns : nullptr, epoch, W, H, d_Rb,
+            ctx->d_touch, ctx->d_del, ctx->d_rowstate, ctx->d_status);
+        AOSLO_LAUNCH_CHECK();
+    } else {
+        AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
+        DeleteParams p;
+        p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
+        p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.W = W; p.H = H;
+        p.touch = ctx->d_touch; p.del = ctx->d_del; p.rowstate = ctx->d_rowstate;
+        p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
+        void* args[] = {&p, (void*)&d_Rb};
+        int blocks = ctx->coop_blocks;
+        int need = (n + kThreads - 1) / kThreads;   // n is an upper bound when the count lives on the device
+        if (need < blocks) blocks = need < 1 ? 1 : need;
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kThreads), args, 0, s));
+        count_launch();
+    }
     if (d_deleted_out) AOSLO_CUDA(cudaMemcpyAsync(d_deleted_out, ctx->d_del, n, cudaMemcpyDeviceToDevice, s));
     KeepOp op{(const double2*)d_pos, d_stable, ctx->d_del, (double2*)d_pos_out, d_stable_out};
     return ordered_scan(ctx, s, op, n, n, d_n, d_n_out, nullptr, 0, nullptr);
@@ -925,12 +1386,43 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
 
 int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                  const void* d_Rb, int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out,
-                 uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n) {
+                 uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n,
+                 int mode) {
     if (field_dtype == AOSLO_F32)
         return stage_delete_t<float>(ctx, s, d_pos, d_stable, n, (const float*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n);
+                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode);
     return stage_delete_t<double>(ctx, s, d_pos, d_stable, n, (const double*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n);
+                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode);
+}
+
+// force + move of the run loop (canonical tie order): copy positions + collect the non-stable list,
+// then one warp per non-stable particle (kNN on the linked cells, force, Jacobi move into d_pos_out).
+// Leaves ctx->d_ns_list / counters[13] for stage_delete(mode 2) and zeroes ctx->d_del.
+int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
+                     int energy_type, double p0, double p1, double p2, const void* d_grad, int field_dtype, int H,
+                     int W, double lb, double ld, int step_mode, double* d_pos_out, const int* d_n,
+                     bool links_ready) {
+    if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
+    if (!links_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+    LinkView lv = link_view(ctx->lk_p, d_pos);
+    int* n_ns = ctx->d_counters + 13;
+    ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
+                                                   ctx->d_del, ctx->d_ns_list, n_ns);
+    AOSLO_LAUNCH_CHECK();
+    const int kk = k + 1;
+#define AOSLO_FM(KT, TT)                                                                                          \
+    ns_force_move_kernel<KT, TT><<<ctx->nb, kThreads, 0, s>>>(lv, ctx->d_ns_list, n_ns, kk, energy_type, p0, p1, p2, \
+                                                              (const TT*)d_grad, H, W, lb, ld, step_mode,          \
+                                                              (double2*)d_pos_out, ctx->d_status)
+    if (field_dtype == AOSLO_F32) {
+        if (kk <= 2) AOSLO_FM(2, float); else if (kk <= 4) AOSLO_FM(4, float); else AOSLO_FM(8, float);
+    } else {
+        if (kk <= 2) AOSLO_FM(2, double); else if (kk <= 4) AOSLO_FM(4, double); else AOSLO_FM(8, double);
+    }
+#undef AOSLO_FM
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
 }
 
 int stage_seed(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
@@ -1018,7 +1510,7 @@ int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uin
     if (n > ctx->cap || n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
     if (n < 1 || n_gt < 1) return AOSLO_ERR_INVALID;
     if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));
-    if (!p_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_pos, n, d_n));
+    if (!p_list_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
     // one pass: particle -> nearest GT ("gt_to_particles", :322) and GT -> nearest particle
     // ("particles_to_gt", :323), counts, moments and blob energy
     int* icount = ctx->d_counters + 16;
@@ -1026,12 +1518,14 @@ int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uin
     MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
     if (field_dtype == AOSLO_F32)
         metrics_pass_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
-            view_of(ctx->cl_g), view_of(ctx->cl_p), (const double2*)d_pos, d_stable, n, d_n, (const double2*)d_gt,
-            n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, ctx->d_status);
+            view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
+            (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials,
+            ctx->d_status);
     else
         metrics_pass_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
-            view_of(ctx->cl_g), view_of(ctx->cl_p), (const double2*)d_pos, d_stable, n, d_n, (const double2*)d_gt,
-            n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, ctx->d_status);
+            view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
+            (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials,
+            ctx->d_status);
     AOSLO_LAUNCH_CHECK();
     metrics_finalize_kernel<<<1, kScanThreads, 0, s>>>(partials, ctx->nb, icount, n, d_n, n_gt, iteration, d_rec);
     AOSLO_LAUNCH_CHECK();
