@@ -43,6 +43,8 @@ int stage_metrics(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, 
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t*, int, uint8_t, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int*, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
+int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int, int, int, int, int, int, int, int, uint8_t*, int,
+                  const double*, int, double*, int*);
 int sqrt_inplace(cudaStream_t, double*, size_t);
 
 template <typename T>
@@ -228,6 +230,19 @@ extern "C" int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out,
     AOSLO_TRY(read_int(ctx, s, ctx->d_status, h_status_out));
     if (clear) AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), s));
     return AOSLO_OK;
+}
+
+extern "C" int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0,
+                                    int pitch0_bytes, int x_min, int x_max, int y_min, int y_max, int bx, int by,
+                                    uint8_t* d_img_out, int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw,
+                                    double* d_gt_out, int* h_n_gt_out) {
+    if (!ctx || !d_raw_img || !d_img_out || !h_n_gt_out) return AOSLO_ERR_INVALID;
+    if (n_gt_raw > 0 && (!d_gt_minus1 || !d_gt_out)) return AOSLO_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    AOSLO_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), s));
+    AOSLO_TRY(stage_prepare(ctx, s, d_raw_img, H0, W0, pitch0_bytes, x_min, x_max, y_min, y_max, bx, by, d_img_out,
+                            out_pitch_bytes, d_gt_minus1, n_gt_raw, d_gt_out, ctx->d_counters));
+    return read_int(ctx, s, ctx->d_counters, h_n_gt_out);
 }
 
 extern "C" int aoslo_seed(aoslo_ctx* ctx, void* stream, const void* d_Rb, int field_dtype, int H, int W, int bx,

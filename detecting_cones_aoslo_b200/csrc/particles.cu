@@ -1559,6 +1559,56 @@ int sqrt_inplace(cudaStream_t s, double* a, size_t n) {
     return AOSLO_OK;
 }
 
+// =======================================================================================
+// input preparation on the device (reference pipeline_with_delitions.py:27-33):
+// np.round + crop_image (image_transformation.py:6-21) + mirror_padding_image (:23-35)
+// =======================================================================================
+__global__ void __launch_bounds__(kThreads) crop_pad_kernel(const uint8_t* __restrict__ raw, int pitch0, int x_min,
+                                                            int y_min, int wc, int hc, int bx, int by,
+                                                            uint8_t* __restrict__ out, int out_pitch, int W, int H) {
+    int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    int cx = x - bx, cy = y - by;                       // symmetric (edge-including) mirror
+    cx = cx < 0 ? -1 - cx : (cx >= wc ? 2 * wc - 1 - cx : cx);
+    cy = cy < 0 ? -1 - cy : (cy >= hc ? 2 * hc - 1 - cy : cy);
+    out[(size_t)y * out_pitch + x] = raw[(size_t)(y_min + cy) * pitch0 + (x_min + cx)];
+}
+
+struct GtPrepOp {
+    const double2* gt;          // already shifted by -1 on the host (the reference mutates the caller's array)
+    double x_min, x_max, y_min, y_max, bx, by;
+    double2* out;
+    __device__ int value(int i) const {
+        double gx = rint(gt[i].x), gy = rint(gt[i].y);   // np.round: half to even
+        return (gy > y_min && gy < y_max && gx > x_min && gx < x_max) ? 1 : 0;
+    }
+    __device__ void emit(int i, int v, int dst) const {
+        if (!v) return;
+        double gx = rint(gt[i].x), gy = rint(gt[i].y);
+        out[dst] = make_double2(gx - x_min + bx, gy - y_min + by);
+    }
+};
+
+int stage_prepare(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_raw, int H0, int W0, int pitch0, int x_min,
+                  int x_max, int y_min, int y_max, int bx, int by, uint8_t* d_img_out, int out_pitch,
+                  const double* d_gt_raw, int n_gt_raw, double* d_gt_out, int* d_n_gt_out) {
+    if (x_min < 0 || y_min < 0 || x_max >= W0 || y_max >= H0) return AOSLO_ERR_INVALID;   // the reference's asserts
+    const int wc = x_max - x_min, hc = y_max - y_min;
+    if (wc < 1 || hc < 1 || bx < 0 || by < 0 || bx > wc || by > hc) return AOSLO_ERR_INVALID;
+    const int W = wc + 2 * bx, H = hc + 2 * by;
+    if (W != ctx->W || H != ctx->H || out_pitch < W) return AOSLO_ERR_INVALID;
+    dim3 grid((W + 63) / 64, (H + 3) / 4);
+    crop_pad_kernel<<<grid, kThreads, 0, s>>>(d_raw, pitch0, x_min, y_min, wc, hc, bx, by, d_img_out, out_pitch, W, H);
+    AOSLO_LAUNCH_CHECK();
+    if (d_gt_raw && n_gt_raw > 0) {
+        GtPrepOp op{(const double2*)d_gt_raw, (double)x_min, (double)x_max, (double)y_min, (double)y_max,
+                    (double)bx, (double)by, (double2*)d_gt_out};
+        AOSLO_TRY(ordered_scan(ctx, s, op, n_gt_raw, n_gt_raw, nullptr, d_n_gt_out, nullptr, 0, nullptr));
+    }
+    return AOSLO_OK;
+}
+
 int coop_blocks_for_delete(int num_sms) {
     int per_sm_f = 0, per_sm_d = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, delete_resolve_kernel<float>, kThreads, 0);

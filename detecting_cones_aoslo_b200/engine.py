@@ -76,6 +76,28 @@ class Engine:
         view.copy_(torch.as_tensor(img), non_blocking=False)
         return view
 
+    def prepare_inputs(self, img, gt_minus1, region, boundary):
+        """Device-side np.round + crop_image + mirror_padding_image (reference
+        pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array; gt_minus1: (n,2) float64 host
+        array ALREADY shifted by -1 (the in-place side effect stays on the host).  Returns the padded
+        image view (pitch multiple of 16) and the cropped / shifted GT, both on the device."""
+        img = np.ascontiguousarray(img)
+        H0, W0 = img.shape
+        assert (0 <= region['x_min']) and (0 <= region['y_min'])                       # image_transformation.py:7
+        assert (W0 > region['x_max']) and (H0 > region['y_max'])                       # image_transformation.py:8
+        d_raw = torch.as_tensor(img).to(self.device, non_blocking=True)
+        g = np.ascontiguousarray(gt_minus1, dtype=np.float64).reshape(-1, 2)
+        d_gt_raw = torch.as_tensor(g).to(self.device, non_blocking=True)
+        pitch = (self.W + 15) // 16 * 16
+        buf = self.empty((self.H, pitch), torch.uint8)
+        d_gt = self.empty((max(1, g.shape[0]), 2), torch.float64)
+        check(lib.aoslo_prepare_inputs(self._h, self._stream(), self._p(d_raw), H0, W0, W0,
+                                       int(region['x_min']), int(region['x_max']), int(region['y_min']),
+                                       int(region['y_max']), int(boundary['x']), int(boundary['y']),
+                                       self._p(buf), pitch, self._p(d_gt_raw), g.shape[0], self._p(d_gt),
+                                       C.byref(self._n_out)), "aoslo_prepare_inputs")
+        return buf[:, :self.W], d_gt[: self._n_out.value]
+
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 

@@ -130,13 +130,15 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     t0 = time.time()
     np.random.seed(cur_config['random_seed'])          # reference :24 (no RNG is consumed afterwards)
 
-    img, GT_data = prepare_inputs(cur_config, GT_data, img, img_colorful)
-    H, W = img.shape
+    region, boundary = cur_config['region'], cur_config['boundary_size']
+    img = np.asarray(img)
+    assert (0 <= region['x_min']) and (0 <= region['y_min'])                            # crop_image asserts
+    assert (img.shape[1] > region['x_max']) and (img.shape[0] > region['y_max'])
+    H = (region['y_max'] - region['y_min']) + 2 * int(boundary['y'])
+    W = (region['x_max'] - region['x_min']) + 2 * int(boundary['x'])
     formula = cur_config['blobness_formula']
     if formula not in ('simple_div', 'custom', 'div_corrected'):
         raise NotImplementedError
-    if GT_data.shape[0] < 1:
-        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
     field_dtype = torch.float64 if _get(cur_config, 'field_dtype', 'f64') == 'f64' else torch.float32
     scales = tuple(_get(cur_config, 'blobness_scales', (1.0,)))
     mode = _get(cur_config, 'engine_mode', 'fused')
@@ -147,8 +149,12 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     if eng.H != H or eng.W != W or eng.gt_cap < GT_data.shape[0]:
         raise ValueError('engine was created for a different padded shape / GT capacity')
     eng.status(clear=True)
-    d_img = eng.upload_image(img)
-    d_gt = eng.dev(GT_data, torch.float64)
+    # reference :26-33: GT -= 1 on the CALLER's array (host side effect), then round / crop / mirror
+    # padding -- on the device (aoslo_prepare_inputs)
+    GT_data = GT_enumerate_from_zero(GT_data)
+    d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary)
+    if d_gt.shape[0] < 1:
+        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
     Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype)
     eng.raise_on_status()                               # assert (eigs[0] > eigs[1]).all()  (:43)
 

@@ -123,6 +123,16 @@ int aoslo_ctx_destroy(aoslo_ctx* ctx);
 int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear);
 int aoslo_ctx_capacity(aoslo_ctx* ctx);
 
+/* ---- L1 pre-processing on the device: np.round of the (already -1 shifted) GT, crop_image
+ * (image_transformation.py:6-21; the reference's region asserts -> AOSLO_ERR_INVALID) and
+ * mirror_padding_image (:23-35).  d_raw_img: (H0,W0) u8; d_img_out: (H,W) u8 with the given pitch,
+ * H = (y_max-y_min) + 2*by, W = (x_max-x_min) + 2*bx (must equal the context's shape);
+ * GT rows kept when strictly inside the region, order preserved; count -> *h_n_gt_out. */
+int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0, int pitch0_bytes,
+                         int x_min, int x_max, int y_min, int y_max, int bx, int by, uint8_t* d_img_out,
+                         int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw, double* d_gt_out,
+                         int* h_n_gt_out);
+
 /* ---- L2 field: replaces skimage.hessian_matrix + hessian_matrix_eigvals + the blobness
  * formula + utils.calc_grad_field (pipeline_with_delitions.py:36-38, :60-68, :91;
  * utils.py:152-163).  u8 image in, R_b and gradient out, one fused kernel.

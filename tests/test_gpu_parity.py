@@ -120,6 +120,27 @@ def test_errors_match_reference():
         gpu_utils.calc_grad_field(np.zeros((8, 8)), 'nope')
 
 
+def test_device_input_preparation_matches_host():
+    """aoslo_prepare_inputs (np.round + crop_image + mirror_padding_image on the device) == host path."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs
+    from detecting_cones_aoslo_b200.utils import get_engine
+    img, gt = load_dataset()
+    cases = [configs.zoo_config(), configs.main_config(),
+             configs.variant(configs.main_config(), region={'x_min': 301, 'x_max': 328, 'y_min': 320, 'y_max': 345},
+                             boundary_size={'x': 10, 'y': 5}),
+             configs.variant(configs.main_config(), region={'x_min': 0, 'x_max': 518, 'y_min': 500, 'y_max': 515},
+                             boundary_size={'x': 3, 'y': 15})]
+    for cfg in cases:
+        h_img, h_gt = prepare_inputs(cfg, gt.copy(), img)
+        eng = get_engine(*h_img.shape, n_gt=gt.shape[0])
+        g = gt.copy()
+        g -= 1.
+        d_img, d_gt = eng.prepare_inputs(img, g, cfg['region'], cfg['boundary_size'])
+        np.testing.assert_array_equal(d_img.cpu().numpy(), h_img)
+        np.testing.assert_array_equal(d_gt.cpu().numpy(), h_gt)
+        assert d_img.stride(0) % 16 == 0
+
+
 # ----------------------------------------------------------------------------------- seeds
 @pytest.mark.parametrize("thr", [4.95, 5.0, 5.01])
 def test_seeds_exact(zoo_field, thr):
