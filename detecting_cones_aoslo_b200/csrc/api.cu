@@ -337,6 +337,47 @@ extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_parti
     return AOSLO_OK;
 }
 
+// One loop iteration without the resample / metrics tail: distance force, move, deletion
+// (reference pipeline_with_delitions.py:173-253).  Same code path as inside aoslo_run, incl. the
+// non-stable-list fast path and its all-rows fallback in the canonical tie order.
+extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb,
+                             const void* d_grad, int field_dtype, const double* d_particles,
+                             const uint8_t* d_stable, int n, double* d_particles_out, uint8_t* d_stable_out,
+                             int* h_n_out) {
+    if (!ctx || !cfg || !d_Rb || !d_grad || !d_particles || !d_stable || !d_particles_out || !d_stable_out || !h_n_out)
+        return AOSLO_ERR_INVALID;
+    if (cfg->H != ctx->H || cfg->W != ctx->W || n > ctx->cap) return AOSLO_ERR_INVALID;
+    const int k = cfg->dist_n_neighbours;
+    if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (n < k + 1 || n < 2) return AOSLO_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
+    const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+    const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+    const double e2 = pit ? cfg->lambda_dist_func : 0.0;
+    const double* moved;
+    int mode;
+    if (cfg->tie_mode == AOSLO_TIE_CANONICAL) {
+        AOSLO_TRY(stage_force_move(ctx, s, d_particles, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2, d_grad,
+                                   field_dtype, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode,
+                                   ctx->d_pos_tmp, nullptr, false));
+        moved = ctx->d_pos_tmp;
+        mode = 2;
+    } else {
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos_tmp, d_particles, sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
+        AOSLO_TRY(stage_force(ctx, s, ctx->d_pos_tmp, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2,
+                              cfg->tie_mode, ctx->d_force, nullptr));
+        AOSLO_TRY(stage_move(ctx, s, ctx->d_pos_tmp, d_stable, n, d_grad, field_dtype, cfg->H, cfg->W, ctx->d_force,
+                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, nullptr));
+        moved = ctx->d_pos_tmp;
+        mode = 1;
+    }
+    AOSLO_TRY(stage_delete(ctx, s, moved, d_stable, n, d_Rb, field_dtype, cfg->H, cfg->W, cfg->threshhold_dist_del,
+                           cfg->tie_mode, d_particles_out, d_stable_out, nullptr, ctx->d_counters, nullptr, nullptr,
+                           mode));
+    return read_int(ctx, s, ctx->d_counters, h_n_out);
+}
+
 // ---------------------------------------------------------------------------------------
 // whole run
 // ---------------------------------------------------------------------------------------

@@ -272,6 +272,17 @@ class Engine:
                                 self._p(p2g), self._p(g2p)), "aoslo_metrics")
         return rec, p2g, g2p
 
+    def iterate(self, cfg_struct, Rb, grad, pos, stable):
+        """one epoch body: force + move + deletion -> (pos, stable) (reference :173-253)."""
+        n = pos.shape[0]
+        pos_out = self.empty((n, 2), torch.float64)
+        st_out = self.empty((n,), torch.uint8)
+        check(lib.aoslo_iterate(self._h, self._stream(), C.byref(cfg_struct), self._p(Rb), self._p(grad),
+                                self._fdt(Rb), self._p(pos), self._p(stable), n, self._p(pos_out), self._p(st_out),
+                                C.byref(self._n_out)), "aoslo_iterate")
+        m = self._n_out.value
+        return pos_out[:m], st_out[:m]
+
     # ------------------------------------------------------------------ L5 whole run
     def run(self, cfg_struct, Rb, grad, gt, max_records=None):
         if max_records is None:

@@ -193,6 +193,12 @@ int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_particles, const
                   const double* d_gt, int n_gt, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
                   aoslo_metrics_record* h_record_out, double* d_dist_p2g, double* d_dist_g2p);
 
+/* ---- one loop iteration: distance force + move + deletion (pipeline_with_delitions.py:173-253),
+ * the code path aoslo_run executes per epoch; out-of-place. */
+int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
+                  int field_dtype, const double* d_particles, const uint8_t* d_stable, int n,
+                  double* d_particles_out, uint8_t* d_stable_out, int* h_n_out);
+
 /* ---- L5 whole run: pipeline_with_delitions.find_blobs (:12-403) after crop/pad.
  * Seeds, thins, resamples and runs the epoch loop with every stage on the device; returns the
  * per-evaluation metric records, the final particles and a summary.  Stage timings (ms, CUDA

@@ -368,3 +368,121 @@ def test_find_blobs_mutates_gt_like_reference_and_f32_mode():
     cfg32 = configs.variant(configs.zoo_config(), field_dtype='f32', tie_mode='canonical')
     res, _ = find_blobs(cfg32, gt.copy(), img, None, False, False)
     assert abs(res["dice_coeff_2"] - 0.9343) < 0.01         # f32 fields: statistically equivalent F1
+
+
+# ----------------------------------------------------------------------------------- more whole-run branches
+@pytest.mark.parametrize("over", [
+    dict(step_mode="contin", lambda_blob=1.),
+    dict(dist_energy_type="exp"),
+    dict(gradient_type="sobel", lambda_blob=1.),
+    dict(dist_n_neighbours=6, lambda_blob=1., lambda_dist=0.1),
+    dict(early_stop=False, epoch_num=9, lambda_blob=1., lambda_dist=0.1, dist_n_neighbours=3),
+])
+@pytest.mark.parametrize("tie_mode", ["sklearn", "canonical"])
+def test_find_blobs_fused_branches_match_oracle(over, tie_mode):
+    """Non-default numeric branches through aoslo_run, both tie orders, 100x100 crop."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    cfg = configs.variant(configs.main_config(), tie_mode=tie_mode, **over)
+    ocfg = {k: v for k, v in cfg.items() if k != 'early_stop'}
+    ref, _ = orc.find_blobs(dict(ocfg), gt.copy(), img, None, False, False, tie_mode=tie_mode,
+                            early_stop=cfg.get('early_stop', True))
+    res, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    got = res["_final_particles"].cpu().numpy()
+    if cfg['step_mode'] == 'discrete':
+        np.testing.assert_array_equal(got, ref["final_particles"])
+    else:
+        np.testing.assert_allclose(got, ref["final_particles"], rtol=0, atol=1e-11)
+    assert res["_summary"]["n_iterations"] == ref["n_iterations"]
+    for key in ("dice_coeff_1", "dice_coeff_2"):
+        assert res[key] == ref[key]
+    np.testing.assert_allclose(res["best_lsa_mean"], ref["best_lsa_mean"], rtol=1e-12)
+
+
+def test_synthetic_frame_fixed_m_matches_oracle():
+    """The benchmark workload at reduced size (512^2 synthetic frame, M = 12, early stop off)."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = synth_aoslo(512, 512, 5.8, seed=7)
+    for tie_mode in ("canonical", "sklearn"):
+        cfg = synth_config(512, 512, 5.8, boundary=15, epoch_num=12, early_stop=False, tie_mode=tie_mode)
+        ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode')}
+        ref, _ = orc.find_blobs(ocfg, gt.copy(), img, None, False, False, tie_mode=tie_mode, early_stop=False)
+        res, ts = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+        np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
+        np.testing.assert_array_equal(res["_final_stable"].cpu().numpy(), ref["final_stable"])
+        assert res["_summary"]["n_iterations"] == 12
+        assert res["dice_coeff_2"] == ref["dice_coeff_2"] and res["dice_coeff_1"] == ref["dice_coeff_1"]
+
+
+def _iterate_oracle(p, st, Rb, grad, cfg, tie_mode):
+    f, _ = orc.calc_dist_energy_pit_optim(p, st, cfg['dist_n_neighbours'], cfg['mu_dist_func'],
+                                          cfg['sigma_dist_func'], cfg['lambda_dist_func'], tie_mode=tie_mode)
+    moved = orc.move_particles(p.copy(), st, grad, f, cfg)
+    return orc.del_close_particles(moved, st, Rb, cfg, threshold_dist=cfg['threshhold_dist_del'], tie_mode=tie_mode)
+
+
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+def test_iterate_matches_oracle_incl_coincidence_fallback(zoo_field, tie_mode):
+    """aoslo_iterate (= one epoch of aoslo_run).  Case B puts a non-stable particle next to a stable one
+    so that it steps ONTO it: the non-stable-list path must detect the coincidence, fall back to the
+    all-rows deletion and still agree with the oracle."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import make_config_struct
+    from detecting_cones_aoslo_b200.utils import get_engine
+    cfg, img, gt, Rb, grad = zoo_field
+    cfg = configs.variant(cfg, tie_mode=tie_mode)
+    gold = GoldenTrace("zoo")
+    a0 = gold.of("adding")[0]
+    pA = np.asarray(a0["particles_out"], dtype=np.float64)
+    stA = list(np.asarray(a0["stable_out"]).astype(int))
+    # case B: non-stable particles one pixel left of stable ones, a constant field pushing them one
+    # pixel to the right (lambda_dist = 0): they land exactly ON the stable particles.  Half of them
+    # precede their partner in the array (the stable partner gets deleted), half follow it (nothing is)
+    cfgB = configs.variant(cfg, lambda_dist=0.0, lambda_blob=1.0)
+    gradB = np.zeros_like(grad)
+    gradB[..., 1] = -1.0
+    stable_part = pA[:3000].copy()
+    first = stable_part[100:120] + np.array([-1.0, 0.0])
+    last = stable_part[200:220] + np.array([-1.0, 0.0])
+    pB = np.vstack([first, stable_part, last])
+    stB = [0] * 20 + [1] * 3000 + [0] * 20
+    eng = get_engine(*img.shape, n_gt=gt.shape[0])
+    d_Rb = eng.dev(Rb, torch.float64)
+    for p, st, c, g in ((pA, stA, cfg, grad), (pB, stB, cfgB, gradB)):
+        cs = make_config_struct(c, *img.shape)
+        d_grad = eng.dev(g, torch.float64)
+        ref_p, ref_del, ref_st = _iterate_oracle(p, st, Rb, g, c, tie_mode)
+        if p is pB and tie_mode == 'canonical':
+            assert ref_del[20:3020].sum() >= 20          # the coincident stable partners were deleted
+        got_p, got_st = eng.iterate(cs, d_Rb, d_grad, eng.dev(p, torch.float64),
+                                    eng.dev(np.asarray(st, dtype=np.uint8), torch.uint8))
+        eng.raise_on_status()
+        np.testing.assert_array_equal(got_p.cpu().numpy(), ref_p)
+        assert [int(v) for v in got_st.cpu().numpy()] == ref_st
+
+
+def test_escape_and_capacity_are_reported():
+    from detecting_cones_aoslo_b200.utils import get_engine
+    cfg = configs.zoo_config()
+    img, gt = _padded(cfg)
+    Rb = orc.calc_blobness(img, 'custom')
+    grad = orc.calc_grad_field(Rb, 'np_grad')
+    p = np.array([[5., 5.], [img.shape[1] + 3., 10.], [20., 20.]])     # one particle outside the padded image
+    with pytest.raises(IndexError):
+        gpu_utils.move_particles(p, [0, 0, 0], grad, np.zeros((3, 2)), cfg)
+    with pytest.raises(IndexError):
+        gpu_utils.calc_dist_to_neares(np.array([[-5., 1.], [2., 2.]]), np.array([[1., 1.]]), 1, True)
+
+
+def test_wandb_branch_records_every_iteration():
+    """USE_WANDB=True: metrics every iteration, wandb-branch result keys, records handed to log_fn."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    logs = []
+    res, _ = find_blobs(configs.main_config(), gt.copy(), img, None, False, True, experiment_idx=3,
+                        log_fn=logs.append)
+    assert len(logs) == res["_summary"]["n_iterations"]
+    assert {'step', '1_dice', '2_TP', 'linear_sum_assignment_mean', 'amount_particles',
+            'stable_particles_persentage'} <= set(logs[0])
+    assert res['experiment_idx'] == 3 and 'lsa_mean' in res and '#GT/#particles' in res
+    assert res['best_lsa_mean'] == np.inf                   # the wandb branch never updates it (reference :297-317)
