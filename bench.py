@@ -249,17 +249,29 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    from detecting_cones_aoslo_b200 import _lib
+    from detecting_cones_aoslo_b200.utils import metrics_from_record
+    cores = os.cpu_count() or 1
+    # lanes per GPU: every lane has a host thread that launches ~450 kernels per run and waits for the
+    # device; keep (lanes x ranks) within the host's cores (8 on a 1-GPU run, 4 per GPU on a 32-core 8-GPU box)
+    B = args.batch if args.batch > 0 else max(1, min(8, cores // max(1, world)))
+    # host wait policy: spin unless the lane threads of all ranks oversubscribe the cores, then yield
+    # (measured on the 8-GPU / 32-core box: 2938 runs/s with yield vs 2639 with spin at 4 lanes per GPU)
+    policy = os.environ.get("AOSLO_BENCH_WAIT_POLICY", "2" if world * B * 2 > cores else "")
+    if policy in ("1", "2", "3"):
+        st = _lib.lib.aoslo_set_wait_policy(local, int(policy))       # before the context is created
+        if st != 0:
+            sys.stderr.write("aoslo_set_wait_policy failed: %s\n" % _lib.lib.aoslo_last_cuda_error().decode())
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from detecting_cones_aoslo_b200 import _lib
-    from detecting_cones_aoslo_b200.utils import metrics_from_record
-
-    B = max(1, args.batch)
     lanes = [Lane(rank * B + j, dev) for j in range(B)]
+    if os.environ.get("AOSLO_BENCH_BLOCKING_SYNC", "0") == "1":
+        for ln in lanes:                 # measured slower than spinning on the 32-core box (wake-up latency)
+            ln.eng.set_blocking_sync(True)
     H, W = lanes[0].H, lanes[0].W
     pool = ThreadPoolExecutor(max_workers=B)
     main = torch.cuda.current_stream()
@@ -331,8 +343,9 @@ def run_gpu(args):
     total_ms = float(tt.item())
     value = world * args.steps * B / (total_ms / 1e3)
 
-    # ---- latency pass: one lane alone (single stream), K1 timed inside the step
+    # ---- latency pass: one lane alone (single stream, spinning waits), K1 timed inside the step
     lane0 = lanes[0]
+    lane0.eng.set_blocking_sync(False)
     for _ in range(2):
         timed_step(lambda ln: ln.run_resident(), [lane0])
     lane0.k1_events.clear()
@@ -383,7 +396,9 @@ def run_gpu(args):
                        "n_particles_final": int(summ.n_particles), "n_seeds": int(summ.n_seeds),
                        "iterations": int(summ.n_iterations), "thinning_rounds": int(summ.n_thinning_rounds),
                        "l2": "flushed between timed steps (256 MiB write, untimed)",
-                       "parallelism": "one frame per lane, %d lanes per rank, NCCL all-gather of metric records" % B},
+                       "parallelism": "one frame per lane, %d lanes per rank, NCCL all-gather of metric records" % B,
+                       "host": {"cores": cores, "wait_policy": {"": "spin (default)", "1": "spin", "2": "yield",
+                                                                 "3": "blocking"}.get(policy, policy)}},
             "clocks": clocks,
             "latency_ms_single_run": latency_ms,
             "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": int(lane0.h2d * B),
@@ -417,7 +432,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="frames run concurrently per step (lanes per GPU)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames run concurrently per step (lanes per GPU); 0 = min(8, host cores / ranks)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -67,10 +67,12 @@ SYMBOLS = {
     "aoslo_last_cuda_error": (C.c_char_p, []),
     "aoslo_device_count": (_i, []),
     "aoslo_launch_count": (C.c_longlong, []),
+    "aoslo_set_wait_policy": (_i, [_i, _i]),
     "aoslo_ctx_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "aoslo_ctx_destroy": (_i, [_vp]),
     "aoslo_ctx_status": (_i, [_vp, _vp, _ip, _i]),
     "aoslo_ctx_capacity": (_i, [_vp]),
+    "aoslo_ctx_set_blocking_sync": (_i, [_vp, _i]),
     "aoslo_prepare_inputs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _ip]),
     "aoslo_blobness": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_d), _ip, C.POINTER(_d), _i, _i, _i, _i, _vp, _vp]),
     "aoslo_grad_field": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

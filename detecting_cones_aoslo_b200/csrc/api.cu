@@ -107,10 +107,22 @@ static void free_cell_list(CellList& cl) {
     cudaFree(cl.sorted_idx); cudaFree(cl.sorted_pos);
 }
 
+// host waits for everything enqueued on `s`.  With many concurrent lanes (one host thread each)
+// spinning in cudaStreamSynchronize burns a core per lane; a blocking-sync event sleeps instead.
+int stream_wait(aoslo_ctx* ctx, cudaStream_t s) {
+    if (ctx->blocking_sync && ctx->ev_block) {
+        AOSLO_CUDA(cudaEventRecord(ctx->ev_block, s));
+        AOSLO_CUDA(cudaEventSynchronize(ctx->ev_block));
+    } else {
+        AOSLO_CUDA(cudaStreamSynchronize(s));
+    }
+    return AOSLO_OK;
+}
+
 // read a device int through the pinned mailbox (one stream sync)
 static int read_int(aoslo_ctx* ctx, cudaStream_t s, const int* d, int* out) {
     AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned, d, sizeof(int), cudaMemcpyDeviceToHost, s));
-    AOSLO_CUDA(cudaStreamSynchronize(s));
+    AOSLO_TRY(stream_wait(ctx, s));
     *out = ctx->h_pinned[0];
     return AOSLO_OK;
 }
@@ -126,6 +138,22 @@ extern "C" int aoslo_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+// Host wait policy of the device's primary context: 0 = auto, 1 = spin, 2 = yield, 3 = blocking sync
+// (cudaSetDeviceFlags).  Yield keeps oversubscribed hosts (more waiting lane threads than cores) moving.
+extern "C" int aoslo_set_wait_policy(int device, int policy) {
+    unsigned flags = cudaDeviceScheduleAuto;
+    if (policy == 1) flags = cudaDeviceScheduleSpin;
+    else if (policy == 2) flags = cudaDeviceScheduleYield;
+    else if (policy == 3) flags = cudaDeviceScheduleBlockingSync;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    AOSLO_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaSetDeviceFlags(flags);
+    cudaSetDevice(cur);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaSetDeviceFlags");
+    return AOSLO_OK;
 }
 
 extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int particle_capacity, int gt_capacity) {
@@ -191,6 +219,8 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)
     for (int i = 0; i < 12 && st == AOSLO_OK; ++i)
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
+        st = AOSLO_ERR_CUDA;
 #undef A
     if (st == AOSLO_OK && cudaMemset(c->d_status, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
@@ -217,12 +247,19 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFreeHost(kd.h_node_end); cudaFreeHost(kd.h_node_bounds);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     cudaGetLastError();
     delete c;
     return AOSLO_OK;
 }
 
 extern "C" int aoslo_ctx_capacity(aoslo_ctx* ctx) { return ctx ? ctx->cap : 0; }
+
+extern "C" int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable) {
+    if (!ctx) return AOSLO_ERR_INVALID;
+    ctx->blocking_sync = enable ? 1 : 0;
+    return AOSLO_OK;
+}
 
 extern "C" int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear) {
     if (!ctx || !h_status_out) return AOSLO_ERR_INVALID;
@@ -332,7 +369,7 @@ extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_parti
     AOSLO_TRY(stage_metrics(ctx, s, d_particles, d_stable, n, d_gt, n_gt, false, false, d_Rb, field_dtype, H, W, bx,
                             by, 0, ctx->d_record, p2g, g2p, nullptr));
     AOSLO_CUDA(cudaMemcpyAsync(ctx->h_record, ctx->d_record, sizeof(aoslo_metrics_record), cudaMemcpyDeviceToHost, s));
-    AOSLO_CUDA(cudaStreamSynchronize(s));
+    AOSLO_TRY(stream_wait(ctx, s));
     *h_record_out = *ctx->h_record;
     return AOSLO_OK;
 }

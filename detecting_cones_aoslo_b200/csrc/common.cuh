@@ -118,6 +118,8 @@ struct aoslo_ctx {
     int* d_active = nullptr;          // [cap] compact list of active deletion rows (non-stable path)
     int* d_active_b = nullptr;        // [cap] same, all-rows fallback
     int* d_ns_list = nullptr;         // [cap] compact list of non-stable particles
+    int blocking_sync = 0;            // 1: host waits sleep on a blocking event instead of spinning
+    cudaEvent_t ev_block = nullptr;
     unsigned int epoch = 0;           // deletion call counter (stamps `touch`, no per-call reset)
     int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
     double* d_knn_d2 = nullptr;
@@ -259,6 +261,7 @@ __device__ __forceinline__ double fld(const T* p, long long i) {
 // (kd_reserve: api.cu)
 // ---------------------------------------------------------------------------------------
 int kd_reserve(aoslo_ctx* ctx);
+int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,

@@ -512,7 +512,7 @@ int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_po
     if (n_points < k) return AOSLO_ERR_INVALID;   // sklearn: ValueError("Expected n_neighbors <= n_samples_fit")
     // host round trip: sklearn's idx_array is the residue of libstdc++ std::nth_element
     AOSLO_CUDA(cudaMemcpyAsync(kd.h_points, d_points, sizeof(double) * 2 * n_points, cudaMemcpyDeviceToHost, s));
-    AOSLO_CUDA(cudaStreamSynchronize(s));
+    AOSLO_TRY(stream_wait(ctx, s));
     int n_nodes = aoslo_kdtree_num_nodes(n_points);
     AOSLO_TRY(aoslo_kdtree_build_host(kd.h_points, n_points, kd.h_idx_array, kd.h_node_start, kd.h_node_end,
                                       kd.h_node_bounds, n_nodes));
@@ -528,7 +528,7 @@ int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_po
         AOSLO_LAUNCH_CHECK();
     }
     // the pinned staging buffers are reused by the next call
-    AOSLO_CUDA(cudaStreamSynchronize(s));
+    AOSLO_TRY(stream_wait(ctx, s));
     return AOSLO_OK;
 }
 

@@ -45,6 +45,10 @@ class Engine:
         self._h = h
         self._n_out = C.c_int(0)
 
+    def set_blocking_sync(self, enable=True):
+        """Host waits sleep instead of spinning: for many concurrent lanes (one host thread each)."""
+        check(lib.aoslo_ctx_set_blocking_sync(self._h, 1 if enable else 0), "aoslo_ctx_set_blocking_sync")
+
     def close(self):
         if getattr(self, "_h", None):
             lib.aoslo_ctx_destroy(self._h)

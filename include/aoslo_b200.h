@@ -117,11 +117,17 @@ int aoslo_device_count(void);
 /* number of kernels this library has launched in this process (monotonic counter) */
 long long aoslo_launch_count(void);
 
+/* host wait policy of `device` (cudaSetDeviceFlags): 0 auto, 1 spin, 2 yield, 3 blocking sync */
+int aoslo_set_wait_policy(int device, int policy);
+
 /* ---- context: owns all scratch (cell lists, kNN tables, scan spines, status word) ------ */
 int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int particle_capacity, int gt_capacity);
 int aoslo_ctx_destroy(aoslo_ctx* ctx);
 int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear);
 int aoslo_ctx_capacity(aoslo_ctx* ctx);
+/* 1: host-side waits of this context sleep on a blocking-sync event instead of spinning (use when many
+ * contexts run concurrently, one host thread each); 0 (default): lowest-latency spinning sync */
+int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable);
 
 /* ---- L1 pre-processing on the device: np.round of the (already -1 shifted) GT, crop_image
  * (image_transformation.py:6-21; the reference's region asserts -> AOSLO_ERR_INVALID) and
