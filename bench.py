@@ -404,7 +404,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": int(lane0.h2d * B),
                     "d2h_bytes_per_step": int(d2h * B), "latency_ms_single_run": float(np.mean(e2e_lat))},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "blobness_kernel<double> (K1, fused Hessian/eig/blobness/gradient)",
+            "roofline": {"kernel": "blobness_band_kernel<double> (K1, fused Gaussian/Hessian/eigenvalues/blobness/gradient)",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_f64, "ms_per_launch": k1_ms,
