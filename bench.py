@@ -107,6 +107,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def k1_dram_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per K1 launch from the committed ncu --set full capture
+    (profiles/r01_k1_traffic.json, written by scripts/summarise_profiles.py); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"][key])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -406,7 +416,9 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "blobness_band_kernel<double> (K1, fused Gaussian/Hessian/eigenvalues/blobness/gradient)",
                          "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": k1_dram_traffic("f64"), "peak_source": peak_src,
+                         "traffic_note": "ncu dram bytes of one launch (profiles/r01_k1_ncu.md); below the algorithmic "
+                                         "bytes because part of the output is still in the 126 MB L2 at kernel end",
                          "algorithmic_bytes_per_launch": bytes_f64, "ms_per_launch": k1_ms,
                          "share_of_step": k1_ms / latency_ms,
                          "timed": "CUDA events on the launch stream inside the single-lane latency pass"},
