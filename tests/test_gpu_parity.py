@@ -486,3 +486,71 @@ def test_wandb_branch_records_every_iteration():
             'stable_particles_persentage'} <= set(logs[0])
     assert res['experiment_idx'] == 3 and 'lsa_mean' in res and '#GT/#particles' in res
     assert res['best_lsa_mean'] == np.inf                   # the wandb branch never updates it (reference :297-317)
+
+
+# ----------------------------------------------------------------------------------- full-size properties
+def _pairwise_min_dist(p):
+    from scipy.spatial import cKDTree
+    d, _ = cKDTree(p).query(p, k=2)
+    return d[:, 1]
+
+
+@pytest.mark.parametrize("size", [2048, 4096])
+def test_full_size_run_properties(size):
+    """BASELINE.json configs 3/5 at full size (4096^2: ~580 k particles), where the oracle is too slow
+    to replay.  Size-independent checks instead: (1) the fused run loop (non-stable list, warp queries,
+    single-block resolve, device-resident count) and the staged path (one C-ABI call per reference
+    function: all-rows kNN tables, cooperative resolve, separate force / move kernels) are two independent
+    implementations of the same arithmetic and must agree bit for bit; (2) the run is deterministic;
+    (3) record bookkeeping is consistent; (4) detection quality on the synthetic lattice."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = synth_aoslo(size, size, 5.8, seed=2022)
+    cfg = synth_config(size, size, 5.8, boundary=15, epoch_num=8, early_stop=False, tie_mode='canonical')
+    res, ts = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    p = res["_final_particles"].cpu().numpy()
+    st = res["_final_stable"].cpu().numpy()
+    summ = res["_summary"]
+    assert summ["status"] == 0 and summ["n_iterations"] == 8 and p.shape[0] == summ["n_particles"]
+    assert np.array_equal(p, np.round(p)) and p.min() >= 0 and p[:, 0].max() < size + 29 and p[:, 1].max() < size + 29
+    assert (_pairwise_min_dist(p) > 0).all()                      # no coincident particles
+    res2, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    np.testing.assert_array_equal(res2["_final_particles"].cpu().numpy(), p)
+    assert res2["dice_coeff_2"] == res["dice_coeff_2"] and res2["best_lsa_mean"] == res["best_lsa_mean"]
+    staged, _ = find_blobs(dict(cfg, engine_mode='staged'), gt.copy(), img, None, False, False)
+    np.testing.assert_array_equal(staged["_final_particles"].cpu().numpy(), p)
+    np.testing.assert_array_equal(staged["_final_stable"].cpu().numpy(), st)
+    assert staged["dice_coeff_1"] == res["dice_coeff_1"] and staged["dice_coeff_2"] == res["dice_coeff_2"]
+    np.testing.assert_allclose(staged["best_lsa_mean"], res["best_lsa_mean"], rtol=1e-12)
+    assert res["dice_coeff_2"] > 0.99 and res["dice_coeff_1"] > 0.98
+    n_gt_inner = ((gt[:, 0] > 1) & (gt[:, 0] < size) & (gt[:, 1] > 1) & (gt[:, 1] < size)).sum()
+    assert abs(p.shape[0] - n_gt_inner) < 0.03 * n_gt_inner
+    assert set(ts) == {'dist_energy_calc', 'moving_particles', 'deleting_particles', 'fix_resample',
+                       'metrics_logging'}
+
+
+def test_batch_of_frames_and_sweep_trials():
+    """configs 4/5 in miniature: a batch of 512^2 frames and sweep trials on one image through the
+    sharded runner (1 rank), each record equal to the oracle's result for that unit."""
+    from detecting_cones_aoslo_b200 import sweep
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = load_dataset()
+    base = configs.zoo_config()
+    table = sweep.run_sweep_on_image(img, gt, base, n_trials=3)
+    assert table.shape == (3, sweep.RECORD_LEN) and (table[:, 1] == 0).all()
+    for i in range(3):
+        cfg = sweep.sample_trial(base, i)
+        ref, _ = orc.find_blobs(dict(cfg), gt.copy(), img, None, False, False, tie_mode='canonical')
+        assert table[i, sweep.RECORD_FIELDS.index('dice_coeff_2')] == ref['dice_coeff_2']
+        assert table[i, sweep.RECORD_FIELDS.index('dice_coeff_1')] == ref['dice_coeff_1']
+        assert table[i, sweep.RECORD_FIELDS.index('n_particles')] == ref['final_particles'].shape[0]
+        assert table[i, sweep.RECORD_FIELDS.index('n_iterations')] == ref['n_iterations']
+    # batch of frames: different seeds, same shape -> one cached context
+    for seed in (2022, 2023):
+        im, g = synth_aoslo(512, 512, 5.8, seed=seed)
+        cfg = synth_config(512, 512, 5.8, boundary=15, epoch_num=6, tie_mode='canonical')
+        ref, _ = orc.find_blobs({k: v for k, v in cfg.items() if k != 'tie_mode'}, g.copy(), im, None, False, False,
+                                tie_mode='canonical')
+        res, _ = find_blobs(dict(cfg), g.copy(), im, None, False, False)
+        np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
