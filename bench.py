@@ -51,7 +51,7 @@ def make_workload(rank, size=SIZE):
     from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
     img, gt = synth_aoslo(size, size, PITCH, seed=2022 + rank)
     cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS, early_stop=False,
-                       tie_mode='canonical', field_dtype='f64')
+                       tie_mode='canonical', field_dtype='f64', collect_stage_times=False)
     return img, gt, cfg
 
 
@@ -222,6 +222,7 @@ class Lane:
         self.n_gt = int(pgt.shape[0])
         self.k1_events = []
         self.last = None
+        self.collect_times = False       # stage timings off: aoslo_run replays its cached CUDA graph
 
     def run_resident(self, time_k1=False):
         """frame + GT resident in HBM: aoslo_blobness + aoslo_run (the whole loop)."""
@@ -236,7 +237,7 @@ class Lane:
             if time_k1:
                 e1.record()
                 self.k1_events.append((e0, e1))
-            summ, recs, pos, st, ms = self.eng.run(self.cs, self.Rb, self.grad, self.d_gt)
+            summ, recs, pos, st, ms = self.eng.run(self.cs, self.Rb, self.grad, self.d_gt, collect_times=self.collect_times)
         if summ.status:
             _lib.raise_device_status(summ.status)
         self.last = (summ, recs, ms)
@@ -362,7 +363,10 @@ def run_gpu(args):
     lat_ms = [timed_step(lambda ln: ln.run_resident(time_k1=True), [lane0]) for _ in range(args.steps)]
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in lane0.k1_events]))
     latency_ms = float(np.mean(lat_ms))
+    lane0.collect_times = True                      # one eager run for the reference's five stage buckets
+    lane0.run_resident()
     summ, recs, stage_ms = lane0.last
+    lane0.collect_times = False
 
     # ---- end to end through the reference-facing entry point, HOST buffers in, records out
     for _ in range(min(2, args.warmup)):

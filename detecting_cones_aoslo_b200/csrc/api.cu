@@ -15,6 +15,7 @@ static thread_local char g_last_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int set_cuda_error(cudaError_t e, const char* where) {
     snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -188,6 +189,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         A(alloc_links(c->lk_p, H, W, cap, lshift));
     }
     A(dmalloc(&c->d_pos_tmp, (size_t)cap * 2));
+    A(dmalloc(&c->d_epoch, 1));
     A(dmalloc(&c->d_active, cap));
     A(dmalloc(&c->d_active_b, cap));
     A(dmalloc(&c->d_ns_list, cap));
@@ -221,9 +223,11 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         if (cudaEventCreate(&c->ev[i]) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) st = AOSLO_ERR_CUDA;
 #undef A
     if (st == AOSLO_OK && cudaMemset(c->d_status, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK) { unsigned int one = 1u; if (cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice) != cudaSuccess) st = AOSLO_ERR_CUDA; }
     if (st == AOSLO_OK && cudaMemset(c->d_counters, 0, sizeof(int) * 32) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st != AOSLO_OK) { aoslo_ctx_destroy(c); return st; }
     *out = c;
@@ -248,6 +252,9 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    cudaFree(c->d_epoch);
     cudaGetLastError();
     delete c;
     return AOSLO_OK;
@@ -460,6 +467,7 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
 
     int cur = 0, n = 0;
     int* d_cnt[2] = {ctx->d_counters + 4, ctx->d_counters + 5};   // count of buffer 0 / 1
+    AOSLO_TRY(epoch_guard(ctx, s, (unsigned)cfg->epoch_num + 1u));
     // ---- seeds (:101) and flags (:113)
     AOSLO_TRY(stage_seed(ctx, s, d_Rb, field_dtype, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold, ctx->d_pos[cur],
                          cap, d_cnt[cur]));
@@ -488,84 +496,158 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     // ---- all stable, gravity field, adding (:130-152)
     AOSLO_TRY(stage_lut(ctx, s, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, ctx->d_lut));
-    // resample: needs the exact count on the host afterwards (it bounds every later launch)
     bool packed_ready = false;                       // rank-packed LUT: derived once per run
-    auto resample = [&](const int* d_n_in) -> int {
-        AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 1, d_n_in));
-        AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, ctx->d_pos[cur], n, d_n_in));
-        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
+    // resample; with `sync` the exact count comes back to the host (it bounds later launch sizes),
+    // without it `n` stays an upper-bound hint -- every kernel takes the real count from the device
+    cudaStream_t qs = s;                             // stream the loop is enqueued on (the capture stream while recording)
+    auto resample = [&](const int* d_n_in, bool sync) -> int {
+        AOSLO_TRY(stage_set_stable(ctx, qs, ctx->d_stable[cur], n, 1, d_n_in));
+        AOSLO_TRY(build_cell_list(ctx, qs, ctx->cl_p, ctx->d_pos[cur], n, d_n_in));
+        AOSLO_TRY(stage_gravity(ctx, qs, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
         packed_ready = true;
-        AOSLO_TRY(stage_add(ctx, s, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
+        AOSLO_TRY(stage_add(ctx, qs, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
                             cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, d_n_in, cap,
                             ctx->d_counters + 6));
         // the appended count lands in a scratch scalar, then becomes this buffer's count
-        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[cur], ctx->d_counters + 6, sizeof(int), cudaMemcpyDeviceToDevice, s));
-        AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
-        if (n > cap) return AOSLO_ERR_CAPACITY;
+        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[cur], ctx->d_counters + 6, sizeof(int), cudaMemcpyDeviceToDevice, qs));
+        if (sync) {
+            AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
+            if (n > cap) return AOSLO_ERR_CAPACITY;
+        }
         return AOSLO_OK;
     };
-    AOSLO_TRY(resample(nullptr));
-    AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));      // GT cell list once
+    AOSLO_TRY(resample(nullptr, true));
+    AOSLO_TRY(build_cell_list(ctx, qs, ctx->cl_g, d_gt, n_gt, nullptr));      // GT cell list once
 
     const int k = cfg->dist_n_neighbours;
     const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
     int n_rec = 0, it_done = 0;
-    bool links_valid = false;                        // ctx->lk_p describes d_pos[cur]
-    AOSLO_TRY(mark(-1));
-    for (int it = 0; it < cfg->epoch_num; ++it) {
-        ++it_done;
-        if (n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
-        // `n` is exact in the synchronising mode and an upper bound of the device count otherwise
-        const int* dn = on_device ? d_cnt[cur] : nullptr;
-        const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
-        const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
-        const double e2 = pit ? cfg->lambda_dist_func : 0.0;
-        const double* moved;
-        if (on_device) {
-            // one launch: kNN on the linked cells + force + Jacobi move into d_pos_tmp
-            AOSLO_TRY(stage_force_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0,
-                                       e1, e2, d_grad, field_dtype, H, W, cfg->lambda_blob, cfg->lambda_dist,
-                                       cfg->step_mode, ctx->d_pos_tmp, dn, links_valid));
-            links_valid = false;
-            moved = ctx->d_pos_tmp;
-            AOSLO_TRY(mark(0));
-            AOSLO_TRY(mark(1));
+    // The epoch loop.  In the canonical tie order without the early stop it contains no host decision:
+    // it is then captured once into a CUDA graph (cached in the context, keyed by everything baked into
+    // the nodes) and replayed -- one graph launch instead of ~350 kernel launches per run.
+    const bool graphable = on_device && !cfg->early_stop && !h_stage_ms && n >= k + 1 &&
+                           !getenv("AOSLO_NO_GRAPH");
+    if (graphable && cur != 0) {                     // the graph is recorded for buffer parity 0
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos[0], ctx->d_pos[1], sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, qs));
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_stable[0], ctx->d_stable[1], n, cudaMemcpyDeviceToDevice, qs));
+        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[0], d_cnt[1], sizeof(int), cudaMemcpyDeviceToDevice, qs));
+        cur = 0;
+    }
+    auto enqueue_loop = [&](bool syncfree) -> int {
+        bool links_valid = false;                    // ctx->lk_p describes d_pos[cur]
+        if (!syncfree) AOSLO_TRY(mark(-1));
+        for (int it = 0; it < cfg->epoch_num; ++it) {
+            ++it_done;
+            if (!syncfree && n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
+            // `n` is exact in the synchronising mode and an upper-bound hint of the device count otherwise
+            const int* dn = on_device ? d_cnt[cur] : nullptr;
+            const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+            const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+            const double e2 = pit ? cfg->lambda_dist_func : 0.0;
+            const double* moved;
+            if (on_device) {
+                // non-stable list, warp-kNN on the linked cells + force + Jacobi move into d_pos_tmp
+                AOSLO_TRY(stage_force_move(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type,
+                                           e0, e1, e2, d_grad, field_dtype, H, W, cfg->lambda_blob, cfg->lambda_dist,
+                                           cfg->step_mode, ctx->d_pos_tmp, dn, links_valid));
+                links_valid = false;
+                moved = ctx->d_pos_tmp;
+                if (!syncfree) { AOSLO_TRY(mark(0)); AOSLO_TRY(mark(1)); }
+            } else {
+                AOSLO_TRY(stage_force(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0,
+                                      e1, e2, cfg->tie_mode, ctx->d_force, dn));
+                AOSLO_TRY(mark(0));
+                AOSLO_TRY(stage_move(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W,
+                                     ctx->d_force, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
+                AOSLO_TRY(mark(1));
+                moved = ctx->d_pos[cur];
+            }
+            AOSLO_TRY(stage_delete(ctx, qs, moved, ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
+                                   cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1],
+                                   ctx->d_stable[cur ^ 1], nullptr, d_cnt[cur ^ 1], nullptr, dn, on_device ? 2 : 1));
+            cur ^= 1;
+            if (!on_device) AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
+            dn = on_device ? d_cnt[cur] : nullptr;
+            if (!syncfree) AOSLO_TRY(mark(2));
+            if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample(dn, !syncfree));
+            if (!syncfree) AOSLO_TRY(mark(3));
+            if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) {
+                AOSLO_TRY(stage_metrics(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
+                                        field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec,
+                                        ctx->d_dist_p2g, ctx->d_dist_g2p, dn));
+                links_valid = on_device;             // the metrics pass left links of d_pos[cur] behind
+                ++n_rec;
+            }
+            if (cfg->early_stop) {
+                int n_stable = 0;
+                AOSLO_TRY(stage_count_stable(ctx, qs, ctx->d_stable[cur], n, ctx->d_counters + 2, dn));
+                AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, qs));
+                AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
+                n_stable = ctx->h_pinned[1];
+                h_summary->n_stable = n_stable;
+                // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
+                if ((double)n_stable / (double)n > 0.997) break;
+            }
+            if (!syncfree) AOSLO_TRY(mark(4));
+        }
+        return AOSLO_OK;
+    };
+    if (!graphable) {
+        AOSLO_TRY(enqueue_loop(false));
+    } else {
+        // launch-size hint: next power of two above 1.25 n, so that runs of similar size share the graph
+        int hint = 1024;
+        while (hint < n + n / 4 && hint < cap) hint <<= 1;
+        if (hint > cap) hint = cap;
+        struct Key {
+            aoslo_config cfg; const void* Rb; const void* grad; const void* gt; int n_gt, fdt, hint, max_rec;
+            const void* recs;
+        } key;
+        memset(&key, 0, sizeof(key));
+        key.cfg = *cfg; key.Rb = d_Rb; key.grad = d_grad; key.gt = d_gt; key.n_gt = n_gt; key.fdt = field_dtype;
+        key.hint = hint; key.max_rec = max_records; key.recs = h_records ? (const void*)ctx->d_records : nullptr;
+        const bool hit = ctx->graph_exec && ctx->graph_key.size() == sizeof(key) &&
+                         memcmp(ctx->graph_key.data(), &key, sizeof(key)) == 0;
+        const int n_exact = n;
+        if (!hit) {
+            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
+            n = hint;
+            // record on the context's own stream (the caller's may be the legacy default stream, which
+            // cannot capture); nothing executes during capture, the graph is launched on the caller's stream
+            qs = ctx->cap_stream;
+            AOSLO_CUDA(cudaStreamBeginCapture(qs, cudaStreamCaptureModeThreadLocal));
+            int st_loop = enqueue_loop(true);
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(qs, &graph);
+            qs = s;
+            if (st_loop != AOSLO_OK) { if (graph) cudaGraphDestroy(graph); return st_loop; }
+            if (ce != cudaSuccess) return set_cuda_error(ce, "cudaStreamEndCapture");
+            size_t n_nodes = 0;
+            cudaGraphGetNodes(graph, nullptr, &n_nodes);
+            std::vector<cudaGraphNode_t> nodes(n_nodes);
+            cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
+            int kernels = 0;
+            for (size_t i = 0; i < n_nodes; ++i) {
+                cudaGraphNodeType t;
+                if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++kernels;
+            }
+            ce = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { ctx->graph_exec = nullptr; return set_cuda_error(ce, "cudaGraphInstantiate"); }
+            ctx->graph_kernel_nodes = kernels;
+            ctx->graph_key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+            // capture ran the bookkeeping of the loop once; replaying needs the same values
         } else {
-            AOSLO_TRY(stage_force(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0, e1,
-                                  e2, cfg->tie_mode, ctx->d_force, dn));
-            AOSLO_TRY(mark(0));
-            AOSLO_TRY(stage_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W,
-                                 ctx->d_force, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
-            AOSLO_TRY(mark(1));
-            moved = ctx->d_pos[cur];
+            // bookkeeping the captured loop would have done
+            for (int it = 0; it < cfg->epoch_num; ++it)
+                if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) ++n_rec;
+            it_done = cfg->epoch_num;
+            if (cfg->epoch_num & 1) cur ^= 1;
+            ctx->epoch += (unsigned)cfg->epoch_num;
         }
-        AOSLO_TRY(stage_delete(ctx, s, moved, ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
-                               cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
-                               nullptr, d_cnt[cur ^ 1], nullptr, dn, on_device ? 2 : 1));
-        cur ^= 1;
-        if (!on_device) AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
-        dn = on_device ? d_cnt[cur] : nullptr;
-        AOSLO_TRY(mark(2));
-        if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample(dn));
-        AOSLO_TRY(mark(3));
-        if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) {
-            AOSLO_TRY(stage_metrics(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
-                                    field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec, ctx->d_dist_p2g,
-                                    ctx->d_dist_g2p, dn));
-            links_valid = on_device;                 // the metrics pass left links of d_pos[cur] behind
-            ++n_rec;
-        }
-        if (cfg->early_stop) {
-            int n_stable = 0;
-            AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, dn));
-            AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
-            AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
-            n_stable = ctx->h_pinned[1];
-            h_summary->n_stable = n_stable;
-            // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
-            if ((double)n_stable / (double)n > 0.997) break;
-        }
-        AOSLO_TRY(mark(4));
+        n = n_exact;
+        AOSLO_CUDA(cudaGraphLaunch(ctx->graph_exec, s));
+        count_launches(ctx->graph_kernel_nodes);
     }
     // ---- results: records, final particles, status -- one synchronisation
     if (n_rec)

@@ -19,6 +19,7 @@ namespace aoslo {
 
 int set_cuda_error(cudaError_t e, const char* where);
 void count_launch();
+void count_launches(int n);
 
 #define AOSLO_CUDA(call)                                                         \
     do {                                                                         \
@@ -120,7 +121,13 @@ struct aoslo_ctx {
     int* d_ns_list = nullptr;         // [cap] compact list of non-stable particles
     int blocking_sync = 0;            // 1: host waits sleep on a blocking event instead of spinning
     cudaEvent_t ev_block = nullptr;
-    unsigned int epoch = 0;           // deletion call counter (stamps `touch`, no per-call reset)
+    unsigned int epoch = 1;           // host-side upper estimate of *d_epoch
+    unsigned int* d_epoch = nullptr;  // device call counter of the in-loop deletion (stamps `touch`)
+    // cached CUDA graph of the epoch loop (canonical tie order, no early stop)
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t cap_stream = nullptr;   // recording stream of the capture
+    std::vector<unsigned char> graph_key;
+    int graph_kernel_nodes = 0;
     int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
     double* d_knn_d2 = nullptr;
     int* d_block_sums = nullptr;      // [kMaxScanBlocks + 1]
@@ -261,6 +268,7 @@ __device__ __forceinline__ double fld(const T* p, long long i) {
 // (kd_reserve: api.cu)
 // ---------------------------------------------------------------------------------------
 int kd_reserve(aoslo_ctx* ctx);
+int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead);
 int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);

@@ -697,9 +697,11 @@ template <typename T>
 __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
     const double2* __restrict__ pos, const int32_t* __restrict__ knn_idx, const int* __restrict__ active_a,
     int* n_active_a, const int* __restrict__ active_b, int* n_active_b, int* fallback, int* n_ns,
-    unsigned int epoch, int W, int H, const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del,
+    unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del,
     uint8_t* astate, int* status) {
     __shared__ int s_pending;
+    // per-call epoch from a device counter (so the call can be replayed from a CUDA graph)
+    const unsigned int epoch = *d_epoch;
     // list B (all-rows fallback) supersedes list A (non-stable rows) when the fallback ran
     const bool use_b = active_b != nullptr && fallback != nullptr && *fallback != 0;
     const int* __restrict__ active = use_b ? active_b : active_a;
@@ -745,6 +747,7 @@ __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
     }
     __syncthreads();
     if (threadIdx.x == 0) {                   // ready for the next call
+        *d_epoch = epoch + 1;
         *n_active_a = 0;
         if (n_active_b) *n_active_b = 0;
         if (fallback) *fallback = 0;
@@ -1308,14 +1311,16 @@ int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_poin
     return knn_links(ctx, s, link_view(ctx->lk_p, d_points), d_query, n_query, d_n, k, d_idx, d_d2);
 }
 
-static unsigned int next_epoch(aoslo_ctx* ctx, cudaStream_t s, int* err) {
-    *err = AOSLO_OK;
-    if (++ctx->epoch >= (1u << 20)) {              // 20-bit epoch in the touch keys: restart from a clean slate
-        if (cudaMemsetAsync(ctx->d_touch, 0, sizeof(unsigned long long) * ctx->cap, s) != cudaSuccess)
-            *err = AOSLO_ERR_CUDA;
-        ctx->epoch = 1;
-    }
-    return ctx->epoch;
+// The 20-bit epoch field of the touch keys must never wrap inside a run: called at the start of a run
+// (stream ordered) when the host-side estimate gets close; `calls_ahead` = resolve calls the run may make.
+int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead) {
+    if (ctx->epoch + calls_ahead + 16u < (1u << 20)) return AOSLO_OK;
+    AOSLO_CUDA(cudaMemsetAsync(ctx->d_touch, 0, sizeof(unsigned long long) * ctx->cap, s));
+    const unsigned int one = 1u;
+    AOSLO_CUDA(cudaMemcpyAsync(ctx->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+    AOSLO_CUDA(cudaStreamSynchronize(s));
+    ctx->epoch = 1;
+    return AOSLO_OK;
 }
 
 // small = true: in-loop variant (compact active list + one resolving block, no cooperative launch)
@@ -1357,13 +1362,11 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                                                                ctx->d_del, ctx->d_active, n_active);
             AOSLO_LAUNCH_CHECK();
         }
-        int err;
-        unsigned int epoch = next_epoch(ctx, s, &err);
-        if (err != AOSLO_OK) return err;
         delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
             (const double2*)d_pos, ctx->d_knn_idx, ctx->d_active, n_active, use_ns ? ctx->d_active_b : nullptr,
-            use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr, use_ns ? n_ns : nullptr, epoch, W, H, d_Rb,
-            ctx->d_touch, ctx->d_del, ctx->d_rowstate, ctx->d_status);
+            use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr, use_ns ? n_ns : nullptr, ctx->d_epoch, W, H,
+            d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate, ctx->d_status);
+        ++ctx->epoch;                               // host-side upper estimate of the device epoch
         AOSLO_LAUNCH_CHECK();
     } else {
         AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));

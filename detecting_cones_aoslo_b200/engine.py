@@ -44,6 +44,8 @@ class Engine:
               "aoslo_ctx_create")
         self._h = h
         self._n_out = C.c_int(0)
+        self._fields = {}
+        self._in_bufs = None
 
     def set_blocking_sync(self, enable=True):
         """Host waits sleep instead of spinning: for many concurrent lanes (one host thread each)."""
@@ -93,8 +95,11 @@ class Engine:
         g = np.ascontiguousarray(gt_minus1, dtype=np.float64).reshape(-1, 2)
         d_gt_raw = torch.as_tensor(g).to(self.device, non_blocking=True)
         pitch = (self.W + 15) // 16 * 16
-        buf = self.empty((self.H, pitch), torch.uint8)
-        d_gt = self.empty((max(1, g.shape[0]), 2), torch.float64)
+        if self._in_bufs is None:          # context-owned: stable addresses (CUDA-graph replay in aoslo_run)
+            self._in_bufs = (self.empty((self.H, pitch), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
+        buf, d_gt = self._in_bufs
+        if g.shape[0] > self.gt_cap:
+            raise MemoryError("GT capacity of the context exceeded")
         check(lib.aoslo_prepare_inputs(self._h, self._stream(), self._p(d_raw), H0, W0, W0,
                                        int(region['x_min']), int(region['x_max']), int(region['y_min']),
                                        int(region['y_max']), int(boundary['x']), int(boundary['y']),
@@ -288,16 +293,26 @@ class Engine:
         return pos_out[:m], st_out[:m]
 
     # ------------------------------------------------------------------ L5 whole run
-    def run(self, cfg_struct, Rb, grad, gt, max_records=None):
+    def field_buffers(self, dtype):
+        """Context-owned (H,W) / (H,W,2) field buffers: stable addresses let aoslo_run replay its cached
+        CUDA graph instead of re-capturing it."""
+        key = str(dtype)
+        if key not in self._fields:
+            self._fields[key] = (self.empty((self.H, self.W), dtype), self.empty((self.H, self.W, 2), dtype))
+        return self._fields[key]
+
+    def run(self, cfg_struct, Rb, grad, gt, max_records=None, collect_times=True):
+        """aoslo_run.  collect_times=False skips the five stage timings, which lets the library run the
+        epoch loop from a cached CUDA graph (canonical tie order, early stop off)."""
         if max_records is None:
             max_records = cfg_struct.epoch_num // max(1, cfg_struct.metric_measure_freq) + 2
         recs = (_lib.MetricsRecord * max_records)()
         summ = _lib.RunSummary()
-        ms = (C.c_float * 5)()
+        ms = (C.c_float * 5)() if collect_times else None
         pos = self.empty((self.cap, 2), torch.float64)
         st = self.empty((self.cap,), torch.uint8)
         check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._p(Rb), self._p(grad), self._fdt(Rb),
                             self._p(gt), gt.shape[0], recs, max_records, self._p(pos), self._p(st), C.byref(summ), ms),
               "aoslo_run")
         n = summ.n_particles
-        return summ, [recs[i] for i in range(summ.n_records)], pos[:n], st[:n], list(ms)
+        return summ, [recs[i] for i in range(summ.n_records)], pos[:n], st[:n], (list(ms) if ms is not None else [0.0] * 5)

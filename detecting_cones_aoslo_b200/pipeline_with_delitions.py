@@ -16,6 +16,9 @@ Extension keys (optional, absent == reference behaviour):
     blobness_scales   [1.0] (default) -- multi-scale extension
     early_stop        True (default; reference :381-382) | False (run all epoch_num iterations)
     engine_mode       'fused' (default: one aoslo_run call) | 'staged' (stage calls from Python)
+    collect_stage_times  True (default: the five `time_spended` buckets are measured) | False (zeros; lets
+                      aoslo_run replay its epoch loop from a cached CUDA graph when tie_mode='canonical' and
+                      early_stop=False)
 VERBOSE (matplotlib figures), write_gif and save_best_result_visualisation are visualisation
 side effects outside the accelerated path and are ignored.
 """
@@ -155,7 +158,8 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary)
     if d_gt.shape[0] < 1:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
-    Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype)
+    Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype,
+                            out=eng.field_buffers(field_dtype))
     eng.raise_on_status()                               # assert (eigs[0] > eigs[1]).all()  (:43)
 
     if mode == 'fused':
@@ -190,7 +194,7 @@ def _run_fused(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_id
         if cur_config['metric_algo'] == 'hangarian':
             raise NotImplementedError("metric_algo='hangarian' is outside the accelerated hot path")
         raise ValueError
-    summ, recs, pos, st, ms = eng.run(cfg, Rb, grad, d_gt)
+    summ, recs, pos, st, ms = eng.run(cfg, Rb, grad, d_gt, collect_times=bool(_get(cur_config, 'collect_stage_times', True)))
     if summ.status:
         _lib.raise_device_status(summ.status)
     for rec in recs:

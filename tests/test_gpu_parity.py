@@ -554,3 +554,33 @@ def test_batch_of_frames_and_sweep_trials():
                                 tie_mode='canonical')
         res, _ = find_blobs(dict(cfg), g.copy(), im, None, False, False)
         np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
+
+
+def test_graph_replay_equals_eager_loop():
+    """aoslo_run replays the epoch loop from a cached CUDA graph when nothing in it needs the host
+    (canonical order, early stop off, stage timing off): same particles / records as the eager loop, on the
+    capture run, on replays, after a config change (re-capture) and for another frame of the same shape."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    frames = [synth_aoslo(512, 512, 5.8, seed=s) for s in (5, 6)]
+
+    def run(img, gt, **over):
+        cfg = synth_config(512, 512, 5.8, boundary=15, epoch_num=9, early_stop=False, tie_mode='canonical', **over)
+        res, ts = find_blobs(cfg, gt.copy(), img, None, False, False)
+        return res, ts
+
+    for img, gt in frames:
+        eager, ts_e = run(img, gt, collect_stage_times=True)
+        assert sum(ts_e.values()) > 0
+        for _ in range(3):                                   # capture, then two replays
+            g, ts_g = run(img, gt, collect_stage_times=False)
+            np.testing.assert_array_equal(g["_final_particles"].cpu().numpy(), eager["_final_particles"].cpu().numpy())
+            np.testing.assert_array_equal(g["_final_stable"].cpu().numpy(), eager["_final_stable"].cpu().numpy())
+            assert g["_summary"] == eager["_summary"]
+            for key in ("dice_coeff_1", "dice_coeff_2", "best_lsa_mean", "best_blobEn_mean"):
+                assert g[key] == eager[key]
+        # another configuration on the same context: the cached graph must not be reused
+        e2, _ = run(img, gt, collect_stage_times=True, threshhold_dist_del=4.2, lambda_dist=0.3)
+        g2, _ = run(img, gt, collect_stage_times=False, threshhold_dist_del=4.2, lambda_dist=0.3)
+        np.testing.assert_array_equal(g2["_final_particles"].cpu().numpy(), e2["_final_particles"].cpu().numpy())
+        assert g2["dice_coeff_2"] == e2["dice_coeff_2"]
