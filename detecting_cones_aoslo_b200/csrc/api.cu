@@ -92,11 +92,13 @@ int aoslo::kd_reserve(aoslo_ctx* c) {
 }
 namespace aoslo {
 
-static int alloc_links(CellLinks& lk, int H, int W, int cap, int shift) {
-    lk.shift = shift;
-    lk.gw = (W + (1 << shift) - 1) >> shift;
-    lk.gh = (H + (1 << shift) - 1) >> shift;
-    lk.ncell = lk.gw * lk.gh;
+static int alloc_links(CellLinks& lk, int H, int W, int cap, int fixed_shift) {
+    lk.fixed_shift = fixed_shift;
+    lk.min_shift = fixed_shift > 0 ? fixed_shift : 1;
+    lk.shift = lk.min_shift;
+    lk.gw = (W + (1 << lk.shift) - 1) >> lk.shift;
+    lk.gh = (H + (1 << lk.shift) - 1) >> lk.shift;
+    lk.ncell = lk.gw * lk.gh;                       // the finest grid: head[] is sized for it
     lk.cap = cap;
     AOSLO_TRY(dmalloc(&lk.head, lk.ncell));
     AOSLO_TRY(dmalloc(&lk.next, cap));
@@ -184,7 +186,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(alloc_cell_list(c->cl_p, H, W, cap, shift));
     A(alloc_cell_list(c->cl_g, H, W, gcap, shift));
     {
-        int lshift = 3;
+        int lshift = 0;                              // 0 = density adaptive
         if (const char* e = getenv("AOSLO_LINK_SHIFT")) { int v = atoi(e); if (v >= 1 && v <= 6) lshift = v; }
         A(alloc_links(c->lk_p, H, W, cap, lshift));
     }

@@ -70,6 +70,8 @@ inline CellView view_of(const CellList& c) {
 // Built by one memset + one kernel (atomicExch); chain order is arbitrary, which is fine because
 // neighbour selection uses the strict total order (d^2, index).
 struct CellLinks {
+    int fixed_shift = 0;         // > 0: pinned cell edge (log2); 0: chosen per build from the density
+    int min_shift = 1;           // head[] is allocated for this finest grid
     int shift = 3;
     int gw = 0, gh = 0, ncell = 0;
     int* head = nullptr;         // [ncell]  -1 = empty

@@ -249,6 +249,20 @@ __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restric
 }
 
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n) {
+    // cell edge from the point density (n_host is the count or its launch-size hint): about two points
+    // per cell, 2..16 px.  Dense seed sets (thinning: every other pixel) get 2-4 px cells, the steady
+    // state (one particle per ~34 px^2) 8 px cells.  AOSLO_LINK_SHIFT pins it.
+    int shift = lk.fixed_shift;
+    if (shift <= 0) {
+        const double area = 2.0 * (double)ctx->H * (double)ctx->W / (double)(n_host > 0 ? n_host : 1);
+        shift = 1;
+        while (shift < 4 && (double)(1 << (shift + 1)) * (double)(1 << (shift + 1)) <= area * 1.5) ++shift;
+    }
+    if (shift < lk.min_shift) shift = lk.min_shift;
+    lk.shift = shift;
+    lk.gw = (ctx->W + (1 << shift) - 1) >> shift;
+    lk.gh = (ctx->H + (1 << shift) - 1) >> shift;
+    lk.ncell = lk.gw * lk.gh;
     AOSLO_CUDA(cudaMemsetAsync(lk.head, 0xff, sizeof(int) * lk.ncell, s));
     link_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh, ctx->W,
                                              ctx->H, lk.head, lk.next, ctx->d_status);
@@ -1157,6 +1171,16 @@ struct MetricsPartial {          // one per block
     double energy;
 };
 
+// L2-coherent read of another block's partial (written before its __threadfence + ticket)
+__device__ __forceinline__ MetricsPartial __ldcg_partial(const MetricsPartial* p) {
+    const double* d = reinterpret_cast<const double*>(p);
+    MetricsPartial r;
+    r.p2g.n = __ldcg(d + 0); r.p2g.mean = __ldcg(d + 1); r.p2g.m2 = __ldcg(d + 2); r.p2g.sum = __ldcg(d + 3);
+    r.g2p.n = __ldcg(d + 4); r.g2p.mean = __ldcg(d + 5); r.g2p.m2 = __ldcg(d + 6); r.g2p.sum = __ldcg(d + 7);
+    r.energy = __ldcg(d + 8);
+    return r;
+}
+
 // One grid pass over [0, n) particles (nearest GT, in-image test, FP counts, blob energy) and
 // [n, n + n_gt) ground-truth points (nearest particle, TP / FN counts).  Integer counts go to
 // global atomics (order independent); FP64 moments are merged in a fixed tree per block and
@@ -1165,7 +1189,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
     CellView cl_g, LinkView lk_p, const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host,
     const int* d_n, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W, int bx, int by,
-    double* d_p2g, double* d_g2p, int* icount /*[8]*/, MetricsPartial* partials, int* status) {
+    double* d_p2g, double* d_g2p, int* icount /*[9]: 8 counts + block ticket*/, MetricsPartial* partials,
+    int iteration, aoslo_metrics_record* rec, int* status) {
     const int n = d_n ? *d_n : n_host;
     const int total = n + n_gt;
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tp1 tp2 fn1 fn2 fp1 fp2 nin nst
@@ -1231,6 +1256,53 @@ __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
         partials[blockIdx.x] = acc;
     }
     if (threadIdx.x < 8 && s_c[threadIdx.x]) atomicAdd(&icount[threadIdx.x], s_c[threadIdx.x]);
+    // ---- the last block to finish merges the per-block partials (fixed order: independent of WHICH block
+    // is last) and writes the record -- no separate finalize launch
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&icount[8], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    MetricsPartial acc;
+    acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        const MetricsPartial pb = __ldcg_partial(partials + b);
+        acc.p2g.merge(pb.p2g);
+        acc.g2p.merge(pb.g2p);
+        acc.energy += pb.energy;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
+        double e = __shfl_down_sync(0xffffffffu, acc.energy, o);
+        acc.p2g.merge(a); acc.g2p.merge(g); acc.energy += e;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        if (threadIdx.x < kThreads / 32) acc = s_part[threadIdx.x];
+        else { acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0; }
+        for (int o = 16; o > 0; o >>= 1) {
+            Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
+            double e = __shfl_down_sync(0xffffffffu, acc.energy, o);
+            acc.p2g.merge(a); acc.g2p.merge(g); acc.energy += e;
+        }
+    }
+    if (threadIdx.x != 0) return;
+    rec->iteration = iteration;
+    rec->n_particles = n;
+    rec->n_stable = __ldcg(&icount[7]);
+    rec->n_gt = n_gt;
+    rec->tp[0] = __ldcg(&icount[0]); rec->tp[1] = __ldcg(&icount[1]);
+    rec->fn[0] = __ldcg(&icount[2]); rec->fn[1] = __ldcg(&icount[3]);
+    rec->fp[0] = __ldcg(&icount[4]); rec->fp[1] = __ldcg(&icount[5]);
+    rec->n_in_image = __ldcg(&icount[6]);
+    rec->pad_ = 0;
+    rec->sum_p2g = acc.p2g.sum; rec->sum_g2p = acc.g2p.sum;
+    rec->var_p2g = acc.p2g.m2 / acc.p2g.n; rec->var_g2p = acc.g2p.m2 / acc.g2p.n;
+    rec->blob_energy_sum = acc.energy;
 }
 
 // one block: merges the per-block partials in a fixed shuffle tree (deterministic) -> record
@@ -1517,20 +1589,18 @@ int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uin
     // one pass: particle -> nearest GT ("gt_to_particles", :322) and GT -> nearest particle
     // ("particles_to_gt", :323), counts, moments and blob energy
     int* icount = ctx->d_counters + 16;
-    AOSLO_CUDA(cudaMemsetAsync(icount, 0, sizeof(int) * 8, s));
+    AOSLO_CUDA(cudaMemsetAsync(icount, 0, sizeof(int) * 9, s));
     MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
     if (field_dtype == AOSLO_F32)
         metrics_pass_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
             view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
-            (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials,
-            ctx->d_status);
+            (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, iteration,
+            d_rec, ctx->d_status);
     else
         metrics_pass_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
             view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
-            (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials,
-            ctx->d_status);
-    AOSLO_LAUNCH_CHECK();
-    metrics_finalize_kernel<<<1, kScanThreads, 0, s>>>(partials, ctx->nb, icount, n, d_n, n_gt, iteration, d_rec);
+            (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, iteration,
+            d_rec, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
