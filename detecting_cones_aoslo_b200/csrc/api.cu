@@ -44,6 +44,8 @@ int stage_metrics(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, 
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t*, int, uint8_t, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int*, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
+int stage_classify(aoslo_ctx*, cudaStream_t, const double*, int, const double*, const double*, int, int, int, int, int,
+                   double, uint8_t*, uint8_t*);
 int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int, int, int, int, int, int, int, int, uint8_t*, int,
                   const double*, int, double*, int*);
 int sqrt_inplace(cudaStream_t, double*, size_t);
@@ -381,6 +383,15 @@ extern "C" int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_parti
     AOSLO_TRY(stream_wait(ctx, s));
     *h_record_out = *ctx->h_record;
     return AOSLO_OK;
+}
+
+extern "C" int aoslo_classify(aoslo_ctx* ctx, void* stream, const double* d_dist_g2p, int n_gt,
+                              const double* d_dist_p2g, const double* d_particles, int n, int bx, int by, int H,
+                              int W, double threshold, uint8_t* d_gt_is_tp, uint8_t* d_particle_is_fp) {
+    if (!ctx || !d_dist_g2p || !d_dist_p2g || !d_particles || !d_gt_is_tp || !d_particle_is_fp || n < 0 || n_gt < 0)
+        return AOSLO_ERR_INVALID;
+    return stage_classify(ctx, (cudaStream_t)stream, d_dist_g2p, n_gt, d_dist_p2g, d_particles, n, bx, by, W, H,
+                          threshold, d_gt_is_tp, d_particle_is_fp);
 }
 
 // One loop iteration without the resample / metrics tail: distance force, move, deletion

@@ -194,42 +194,6 @@ __device__ __forceinline__ void knn_cells_query(const CellView& cl, double qx, d
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) knn_cells_kernel(CellView cl, const double2* __restrict__ q,
-                                                             int nq_host, const int* d_nq, int k,
-                                                             int32_t* out_idx, double* out_d2, int* status) {
-    int nq = d_nq ? *d_nq : nq_host;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += gridDim.x * blockDim.x) {
-        double2 p = q[i];
-        TopK<K> top;
-        knn_cells_query<K>(cl, p.x, p.y, top);
-        bool shortfall = false;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < k) {
-                bool empty = top.idx[j] == 0x7fffffff;
-                shortfall |= empty;
-                out_idx[(size_t)i * k + j] = empty ? -1 : top.idx[j];
-                out_d2[(size_t)i * k + j] = top.d2[j];
-            }
-        }
-        if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-    }
-}
-
-int knn_cells(aoslo_ctx* ctx, cudaStream_t s, const CellList& cl, const double* d_query, int nq_host,
-              const int* d_nq, int k, int32_t* d_idx, double* d_d2, int, const int*) {
-    CellView v = view_of(cl);
-    const double2* q = (const double2*)d_query;
-    if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
-    if (k == 1) knn_cells_kernel<1><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
-    else if (k == 2) knn_cells_kernel<2><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
-    else if (k <= 4) knn_cells_kernel<4><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
-    else knn_cells_kernel<8><<<ctx->nb, kThreads, 0, s>>>(v, q, nq_host, d_nq, k, d_idx, d_d2, ctx->d_status);
-    AOSLO_LAUNCH_CHECK();
-    return AOSLO_OK;
-}
-
 // =======================================================================================
 // scan-free linked cells: build (memset + 1 kernel) and the same exact ring search
 // =======================================================================================
@@ -1012,31 +976,6 @@ __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint
     }
 }
 
-// fused force + move of the run loop: kNN on the linked cells, force, Jacobi move into pos_out.
-// Stable particles neither need a force (their move is skipped, :216) nor a neighbour search.
-template <int K, typename T>
-__global__ void __launch_bounds__(kThreads) knn_force_move_kernel(
-    LinkView lv, const uint8_t* __restrict__ stable, int n_host, const int* d_n, int kk, int energy_type, double p0,
-    double p1, double p2, const T* __restrict__ grad, int H, int W, double lb, double ld, int step_mode,
-    double2* __restrict__ pos_out, int* status) {
-    int n = d_n ? *d_n : n_host;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double2 p = lv.pos[i];
-        if (!stable[i]) {
-            TopK<K> top;
-            knn_links_query<K>(lv, p.x, p.y, top);
-            bool shortfall = false;
-#pragma unroll
-            for (int j = 0; j < K; ++j)
-                if (j == kk - 1 && top.idx[j] == 0x7fffffff) shortfall = true;
-            if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-            double2 f = force_from_neighbours<K>(p, top.idx, kk, lv.pos, energy_type, p0, p1, p2);
-            if (step_mode >= 0) move_one<T>(p, f, grad, H, W, lb, ld, step_mode, status);
-        }
-        pos_out[i] = p;
-    }
-}
-
 // ---- non-stable list path of the run loop (canonical tie order) --------------------------------
 // Only non-stable particles move (:216) and only rows whose `from` is non-stable can delete
 // (utils.py:253); `from` is the row's own particle unless two particles coincide.  So the loop works
@@ -1679,6 +1618,36 @@ int stage_prepare(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_raw, int H0, 
                     (double)bx, (double)by, (double2*)d_gt_out};
         AOSLO_TRY(ordered_scan(ctx, s, op, n_gt_raw, n_gt_raw, nullptr, d_n_gt_out, nullptr, 0, nullptr));
     }
+    return AOSLO_OK;
+}
+
+// classification arrays of utils.visualize_all (utils.py:174-203): per GT point TP (nearest particle
+// strictly closer than the threshold) / FN, per particle FP (nearest GT farther than the threshold AND
+// strictly inside the original image, get_particles_in_image)
+__global__ void __launch_bounds__(kThreads) classify_kernel(const double* __restrict__ d_g2p, int n_gt,
+                                                            const double* __restrict__ d_p2g,
+                                                            const double2* __restrict__ pos, int n, int bx, int by,
+                                                            int W, int H, double thr, uint8_t* gt_is_tp,
+                                                            uint8_t* particle_is_fp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_gt + n; i += gridDim.x * blockDim.x) {
+        if (i < n_gt) {
+            gt_is_tp[i] = (d_g2p[i] < thr) ? 1 : 0;
+        } else {
+            const int j = i - n_gt;
+            const double2 p = pos[j];
+            const bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) &&
+                                (p.y < (double)(H - by));
+            particle_is_fp[j] = (inside && d_p2g[j] > thr) ? 1 : 0;
+        }
+    }
+}
+
+int stage_classify(aoslo_ctx* ctx, cudaStream_t s, const double* d_g2p, int n_gt, const double* d_p2g,
+                   const double* d_pos, int n, int bx, int by, int W, int H, double thr, uint8_t* gt_is_tp,
+                   uint8_t* particle_is_fp) {
+    classify_kernel<<<ctx->nb, kThreads, 0, s>>>(d_g2p, n_gt, d_p2g, (const double2*)d_pos, n, bx, by, W, H, thr,
+                                                 gt_is_tp, particle_is_fp);
+    AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
 

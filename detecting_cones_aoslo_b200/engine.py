@@ -281,6 +281,15 @@ class Engine:
                                 self._p(p2g), self._p(g2p)), "aoslo_metrics")
         return rec, p2g, g2p
 
+    def classify(self, g2p, p2g, pos, bx, by, threshold):
+        """TP / FN flags per GT point and FP flags per particle (reference utils.visualize_all)."""
+        gt_tp = self.empty((g2p.shape[0],), torch.uint8)
+        p_fp = self.empty((pos.shape[0],), torch.uint8)
+        check(lib.aoslo_classify(self._h, self._stream(), self._p(g2p), g2p.shape[0], self._p(p2g), self._p(pos),
+                                 pos.shape[0], int(bx), int(by), self.H, self.W, float(threshold), self._p(gt_tp),
+                                 self._p(p_fp)), "aoslo_classify")
+        return gt_tp, p_fp
+
     def iterate(self, cfg_struct, Rb, grad, pos, stable):
         """one epoch body: force + move + deletion -> (pos, stable) (reference :173-253)."""
         n = pos.shape[0]

@@ -121,3 +121,13 @@ def run_sweep_on_image(img, gt, base_config, n_trials, rank=0, world_size=1, dev
         return pack_record(i, res, res.get('_summary'))
 
     return run_sharded(shard_units(n_trials, rank, world_size), one, n_trials, device=device)
+
+
+def write_results_table(results, path="benchmarking_chamfer.csv"):
+    """The grid driver's output (reference main_with_delitions.py:174-176): one row per `result` dict,
+    sorted by `dice_coeff_1`, written as CSV.  Device tensors / private keys are dropped."""
+    import pandas as pd
+    rows = [{k: v for k, v in r.items() if not k.startswith('_')} for r in results]
+    table = pd.DataFrame(rows).sort_values('dice_coeff_1')
+    table.to_csv(path, index=False)
+    return table

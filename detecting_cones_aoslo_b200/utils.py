@@ -324,3 +324,22 @@ def detection_metrics(particles, GT_particles, R_b, cur_config, is_stable_partic
                             cur_config['boundary_size']['y'])
     eng.raise_on_status()
     return metrics_from_record(rec)
+
+
+def classify_detections(particles, GT_particles, R_b, cur_config, metric='2'):
+    """NEW: the index sets the reference's visualize_all draws (utils.py:174-203) -- TP_idx / FN_idx over the
+    GT points and FP_idx over the particles -- computed on the device; plotting is left to the caller."""
+    metric_2_dist_map = {'1': 1.42, '2': 2.83}
+    particles = np.asarray(particles, dtype=np.float64)
+    GT_particles = np.asarray(GT_particles, dtype=np.float64)
+    Rb = np.ascontiguousarray(R_b)
+    eng = get_engine(*Rb.shape, n_particles=particles.shape[0], n_gt=GT_particles.shape[0])
+    tdt = torch.float32 if Rb.dtype == np.float32 else torch.float64
+    pos = _pts(eng, particles)
+    bx, by = cur_config['boundary_size']['x'], cur_config['boundary_size']['y']
+    rec, p2g, g2p = eng.metrics(pos, _stable(eng, None, particles.shape[0]), _pts(eng, GT_particles),
+                                eng.dev(Rb, tdt), bx, by, want_dists=True)
+    gt_tp, p_fp = eng.classify(g2p, p2g, pos, bx, by, metric_2_dist_map[metric])
+    eng.raise_on_status()
+    gt_tp = gt_tp.cpu().numpy().astype(bool)
+    return np.nonzero(gt_tp)[0], np.nonzero(~gt_tp)[0], np.nonzero(p_fp.cpu().numpy())[0]

@@ -199,6 +199,13 @@ int aoslo_metrics(aoslo_ctx* ctx, void* stream, const double* d_particles, const
                   const double* d_gt, int n_gt, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
                   aoslo_metrics_record* h_record_out, double* d_dist_p2g, double* d_dist_g2p);
 
+/* classification arrays of utils.visualize_all (utils.py:174-203) from the two nearest-distance arrays of
+ * aoslo_metrics: per GT point TP (d < threshold) / FN, per particle FP (d > threshold and strictly inside
+ * the original image).  Plotting stays on the host. */
+int aoslo_classify(aoslo_ctx* ctx, void* stream, const double* d_dist_g2p, int n_gt, const double* d_dist_p2g,
+                   const double* d_particles, int n, int bx, int by, int H, int W, double threshold,
+                   uint8_t* d_gt_is_tp, uint8_t* d_particle_is_fp);
+
 /* ---- one loop iteration: distance force + move + deletion (pipeline_with_delitions.py:173-253),
  * the code path aoslo_run executes per epoch; out-of-place. */
 int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,

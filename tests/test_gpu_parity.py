@@ -584,3 +584,22 @@ def test_graph_replay_equals_eager_loop():
         g2, _ = run(img, gt, collect_stage_times=False, threshhold_dist_del=4.2, lambda_dist=0.3)
         np.testing.assert_array_equal(g2["_final_particles"].cpu().numpy(), e2["_final_particles"].cpu().numpy())
         assert g2["dice_coeff_2"] == e2["dice_coeff_2"]
+
+
+def test_classification_sets_match_visualize_all(zoo_field):
+    """aoslo_classify == the TP / FN / FP index sets of the reference's visualize_all (utils.py:174-203)."""
+    cfg, img, gt, Rb, grad = zoo_field
+    gold = GoldenTrace("zoo")
+    p = np.asarray(gold.of("acc")[-1]["particles"], dtype=np.float64)
+    for metric, thr in (('1', 1.42), ('2', 2.83)):
+        particles_to_gt = orc.calc_dist_to_neares(p, gt)[:, 0]          # per GT point
+        gt_to_particles = orc.calc_dist_to_neares(gt, p)[:, 0]          # per particle
+        tp_ref = np.nonzero(particles_to_gt < thr)[0]
+        fn_ref = np.nonzero(~(particles_to_gt < thr))[0]
+        fp_all = np.nonzero(gt_to_particles > thr)[0]
+        _, inside = orc.get_particles_in_image(p[fp_all], cfg, img.shape)
+        fp_ref = fp_all[inside] if len(fp_all) else fp_all
+        tp, fn, fp = gpu_utils.classify_detections(p, gt, Rb, cfg, metric=metric)
+        np.testing.assert_array_equal(tp, tp_ref)
+        np.testing.assert_array_equal(fn, fn_ref)
+        np.testing.assert_array_equal(fp, fp_ref)
