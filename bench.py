@@ -263,11 +263,12 @@ def run_gpu(args):
     from detecting_cones_aoslo_b200 import _lib
     from detecting_cones_aoslo_b200.utils import metrics_from_record
     cores = os.cpu_count() or 1
-    # lanes per GPU: every lane has a host thread that launches ~450 kernels per run and waits for the
-    # device; keep (lanes x ranks) within the host's cores (8 on a 1-GPU run, 4 per GPU on a 32-core 8-GPU box)
-    B = args.batch if args.batch > 0 else max(1, min(8, cores // max(1, world)))
+    # lanes per GPU: every lane has a host thread that enqueues one run (a CUDA graph + ~90 eager launches)
+    # and waits for the device.  8 lanes saturate one B200 (1/2/4/8 lanes: 295/450/600/690 runs/s) and were
+    # also the best setting on the 8-GPU / 32-core box (4388 runs/s vs 3826 with 4 lanes per GPU).
+    B = args.batch if args.batch > 0 else max(1, min(8, cores))
     # host wait policy: spin unless the lane threads of all ranks oversubscribe the cores, then yield
-    # (measured on the 8-GPU / 32-core box: 2938 runs/s with yield vs 2639 with spin at 4 lanes per GPU)
+    # (measured on the 8-GPU / 32-core box before the CUDA-graph loop: 2938 runs/s with yield vs 2639 with spin)
     policy = os.environ.get("AOSLO_BENCH_WAIT_POLICY", "2" if world * B * 2 > cores else "")
     if policy in ("1", "2", "3"):
         st = _lib.lib.aoslo_set_wait_policy(local, int(policy))       # before the context is created
@@ -449,7 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0,
-                    help="frames run concurrently per step (lanes per GPU); 0 = min(8, host cores / ranks)")
+                    help="frames run concurrently per step (lanes per GPU); 0 = min(8, host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
