@@ -272,7 +272,8 @@ __device__ __forceinline__ double fld(const T* p, long long i) {
 int kd_reserve(aoslo_ctx* ctx);
 int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead);
 int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
-int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n);
+int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
+                const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
                 int n_query, int k, int32_t* d_idx, double* d_d2);

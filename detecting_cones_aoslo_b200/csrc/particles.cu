@@ -197,12 +197,22 @@ __device__ __forceinline__ void knn_cells_query(const CellView& cl, double qx, d
 // =======================================================================================
 // scan-free linked cells: build (memset + 1 kernel) and the same exact ring search
 // =======================================================================================
+// PREP additionally does ns_prepare_kernel's work in the same pass (copy to the move buffer, clear the
+// deletion flags, collect the non-stable list)
+template <bool PREP>
 __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restrict__ pos, int n_host,
                                                         const int* d_n, int shift, int gw, int gh, int W, int H,
-                                                        int* head, int* next, int* status) {
+                                                        int* head, int* next, int* status,
+                                                        const uint8_t* __restrict__ stable, double2* pos_out,
+                                                        uint8_t* del, int* ns_list, int* n_ns) {
     int n = d_n ? *d_n : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double2 p = pos[i];
+        if (PREP) {
+            pos_out[i] = p;
+            del[i] = 0;
+            if (!stable[i]) ns_list[atomicAdd(n_ns, 1)] = i;
+        }
         bool bad = false;
         int cx = cell_coord(p.x, shift, gw, bad);
         int cy = cell_coord(p.y, shift, gh, bad);
@@ -212,7 +222,8 @@ __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restric
     }
 }
 
-int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n) {
+int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
+                const uint8_t* prep_stable, double* prep_pos_out) {
     // cell edge from the point density (n_host is the count or its launch-size hint): about two points
     // per cell, 2..16 px.  Dense seed sets (thinning: every other pixel) get 2-4 px cells, the steady
     // state (one particle per ~34 px^2) 8 px cells.  AOSLO_LINK_SHIFT pins it.
@@ -228,8 +239,15 @@ int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_p
     lk.gh = (ctx->H + (1 << shift) - 1) >> shift;
     lk.ncell = lk.gw * lk.gh;
     AOSLO_CUDA(cudaMemsetAsync(lk.head, 0xff, sizeof(int) * lk.ncell, s));
-    link_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh, ctx->W,
-                                             ctx->H, lk.head, lk.next, ctx->d_status);
+    if (prep_stable)
+        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh,
+                                                       ctx->W, ctx->H, lk.head, lk.next, ctx->d_status, prep_stable,
+                                                       (double2*)prep_pos_out, ctx->d_del, ctx->d_ns_list,
+                                                       ctx->d_counters + 13);
+    else
+        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh,
+                                                        ctx->W, ctx->H, lk.head, lk.next, ctx->d_status, nullptr,
+                                                        nullptr, nullptr, nullptr, nullptr);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
@@ -673,27 +691,43 @@ __global__ void __launch_bounds__(kThreads) collect_active_kernel(const int32_t*
 // running next to it).  `touch` is never reset: keys carry a per-call epoch.
 template <typename T>
 __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
-    const double2* __restrict__ pos, const int32_t* __restrict__ knn_idx, const int* __restrict__ active_a,
-    int* n_active_a, const int* __restrict__ active_b, int* n_active_b, int* fallback, int* n_ns,
-    unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del,
-    uint8_t* astate, int* status) {
+    const double2* __restrict__ pos, int32_t* knn_idx, double* knn_d2, const int* __restrict__ active_a,
+    int* n_active_a, const int* __restrict__ active_b, int* n_active_b, int* fallback, int* n_ns, int n_host,
+    const int* d_n, unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb,
+    unsigned long long* touch, uint8_t* del, uint8_t* astate, int* block_sums, int nb_scan, int* d_n_out,
+    int* status) {
     __shared__ int s_pending;
+    __shared__ int s_hist[kMaxScanBlocks];      // deletions per block of the compaction that follows
+    __shared__ int sw[33];
+    const int m = d_n ? *d_n : n_host;
     // per-call epoch from a device counter (so the call can be replayed from a CUDA graph)
     const unsigned int epoch = *d_epoch;
-    // list B (all-rows fallback) supersedes list A (non-stable rows) when the fallback ran
-    const bool use_b = active_b != nullptr && fallback != nullptr && *fallback != 0;
+    for (int b = threadIdx.x; b < kMaxScanBlocks; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    // list B (all-rows fallback, built by the gated knn2_rows_kernel) supersedes list A (rows of the
+    // non-stable particles) when some particle had another one at distance 0.  The fallback
+    // stays a grid-wide kernel: it does fire (a moved particle landing on an occupied pixel), and one
+    // block redoing 145 k queries was measured at 1.7 ms.
+    const bool use_b = (fallback != nullptr) && (*fallback != 0);
     const int* __restrict__ active = use_b ? active_b : active_a;
     const int na = use_b ? *n_active_b : *n_active_a;
+    // span of one compaction block (scan_span with blockDim = kScanThreads, gridDim = nb_scan)
+    int per = 1;
+    if (block_sums) {
+        per = (m + nb_scan - 1) / nb_scan;
+        per = ((per + kScanThreads - 1) / kScanThreads) * kScanThreads;
+        if (per < 1) per = kScanThreads;
+    }
     for (int a = threadIdx.x; a < na; a += blockDim.x) astate[a] = 1;
     __syncthreads();
-    for (unsigned int round = 1;; ++round) {
+    for (unsigned int round = 1; na > 0; ++round) {
         const unsigned long long hi = ((unsigned long long)epoch << 44) | ((unsigned long long)round << 32);
         for (int a = threadIdx.x; a < na; a += blockDim.x) {
             if (!astate[a]) continue;
             int i = active[a];
             unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
-            atomicMax(&touch[knn_idx[2 * (size_t)i]], key);
-            atomicMax(&touch[knn_idx[2 * (size_t)i + 1]], key);
+            atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i])], key);
+            atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i + 1])], key);
         }
         if (threadIdx.x == 0) s_pending = 0;
         __threadfence();
@@ -702,13 +736,15 @@ __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
         for (int a = threadIdx.x; a < na; a += blockDim.x) {
             if (!astate[a]) continue;
             int i = active[a];
-            int from = knn_idx[2 * (size_t)i], to = knn_idx[2 * (size_t)i + 1];
+            int from = __ldcg(&knn_idx[2 * (size_t)i]), to = __ldcg(&knn_idx[2 * (size_t)i + 1]);
             unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
             if (__ldcg(&touch[from]) == key && __ldcg(&touch[to]) == key) {
                 if (!__ldcg(&del[from]) && !__ldcg(&del[to])) {
                     double e1 = energy_at<T>(Rb, pos[from], W, H, status);
                     double e2 = energy_at<T>(Rb, pos[to], W, H, status);
-                    __stcg(&del[(e1 < e2) ? from : to], (uint8_t)1);
+                    const int victim = (e1 < e2) ? from : to;
+                    __stcg(&del[victim], (uint8_t)1);     // every deletion is performed exactly once
+                    if (block_sums) atomicAdd(&s_hist[victim / per], 1);
                 }
                 astate[a] = 0;
             } else {
@@ -724,6 +760,20 @@ __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
         if (round >= 4000u) { if (threadIdx.x == 0) atomicOr(status, AOSLO_DEV_CAPACITY); break; }
     }
     __syncthreads();
+    // offsets of the order-preserving compaction that follows (scan_emit_kernel<KeepOp> with nb_scan
+    // blocks): kept elements before block b = min(b * per, m) - deletions before it.  Replaces the count and
+    // spine launches of the generic three-phase scan.
+    if (block_sums) {
+        const int v = (threadIdx.x < nb_scan) ? s_hist[threadIdx.x] : 0;
+        int total;
+        const int excl = block_excl_scan(v, sw, total);
+        if (threadIdx.x < nb_scan) {
+            long long lo = (long long)threadIdx.x * per;
+            if (lo > m) lo = m;
+            block_sums[threadIdx.x] = (int)lo - excl;
+        }
+        if (threadIdx.x == 0 && d_n_out) *d_n_out = m - total;
+    }
     if (threadIdx.x == 0) {                   // ready for the next call
         *d_epoch = epoch + 1;
         *n_active_a = 0;
@@ -1373,12 +1423,21 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                                                                ctx->d_del, ctx->d_active, n_active);
             AOSLO_LAUNCH_CHECK();
         }
+        // the resolving block also prepares the compaction offsets, so only the emit phase of the
+        // ordered scan has to be launched afterwards
+        const int nb_scan = scan_blocks_for(n);
         delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
-            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_active, n_active, use_ns ? ctx->d_active_b : nullptr,
-            use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr, use_ns ? n_ns : nullptr, ctx->d_epoch, W, H,
-            d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate, ctx->d_status);
-        ++ctx->epoch;                               // host-side upper estimate of the device epoch
+            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active,
+            use_ns ? ctx->d_active_b : nullptr, use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr,
+            use_ns ? n_ns : nullptr, n, d_n, ctx->d_epoch, W, H, d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate,
+            ctx->d_block_sums, nb_scan, d_n_out, ctx->d_status);
         AOSLO_LAUNCH_CHECK();
+        ++ctx->epoch;                               // host-side upper estimate of the device epoch
+        if (d_deleted_out) AOSLO_CUDA(cudaMemcpyAsync(d_deleted_out, ctx->d_del, n, cudaMemcpyDeviceToDevice, s));
+        KeepOp op{(const double2*)d_pos, d_stable, ctx->d_del, (double2*)d_pos_out, d_stable_out};
+        scan_emit_kernel<KeepOp><<<nb_scan, kScanThreads, 0, s>>>(op, n, d_n, ctx->d_block_sums);
+        AOSLO_LAUNCH_CHECK();
+        return AOSLO_OK;
     } else {
         AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
         DeleteParams p;
@@ -1418,12 +1477,16 @@ int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const 
                      bool links_ready) {
     if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
-    if (!links_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
-    LinkView lv = link_view(ctx->lk_p, d_pos);
     int* n_ns = ctx->d_counters + 13;
-    ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
-                                                   ctx->d_del, ctx->d_ns_list, n_ns);
-    AOSLO_LAUNCH_CHECK();
+    if (!links_ready) {
+        // one pass: link the particles and do ns_prepare's work (copy, clear flags, non-stable list)
+        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, d_stable, d_pos_out));
+    } else {
+        ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
+                                                       ctx->d_del, ctx->d_ns_list, n_ns);
+        AOSLO_LAUNCH_CHECK();
+    }
+    LinkView lv = link_view(ctx->lk_p, d_pos);
     const int kk = k + 1;
 #define AOSLO_FM(KT, TT)                                                                                          \
     ns_force_move_kernel<KT, TT><<<ctx->nb, kThreads, 0, s>>>(lv, ctx->d_ns_list, n_ns, kk, energy_type, p0, p1, p2, \
