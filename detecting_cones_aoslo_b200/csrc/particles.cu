@@ -373,17 +373,25 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
     cx = min(cx, lv.gw - 1);
     cy = min(cy, lv.gh - 1);
     const int rmax = max(lv.gw, lv.gh);
-    for (int r = 0; r <= rmax; ++r) {
-        const int ncells = (r == 0) ? 1 : 8 * r;
-        for (int j = lane; j < ncells; j += 32) {
-            int dx, dy;
-            if (r == 0) { dx = 0; dy = 0; }
-            else if (j <= 2 * r) { dx = -r + j; dy = -r; }
-            else if (j <= 4 * r + 1) { dx = -r + (j - 2 * r - 1); dy = r; }
-            else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
-            else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
-            const int x = cx + dx, y = cy + dy;
-            if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+    // rings 0 and 1 (the 3x3 block) are visited together -- lane j takes cell j -- so the common case costs
+    // one round of dependent loads and one merge; further rings follow one at a time
+    for (int r = 1; r <= rmax; ++r) {
+        if (r == 1) {
+            if (lane < 9) {
+                const int x = cx + (lane % 3) - 1, y = cy + (lane / 3) - 1;
+                if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+            }
+        } else {
+            const int ncells = 8 * r;
+            for (int j = lane; j < ncells; j += 32) {
+                int dx, dy;
+                if (j <= 2 * r) { dx = -r + j; dy = -r; }
+                else if (j <= 4 * r + 1) { dx = -r + (j - 2 * r - 1); dy = r; }
+                else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
+                else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
+                const int x = cx + dx, y = cy + dy;
+                if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+            }
         }
         warp_merge_topk<K>(mine, out);
         const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
