@@ -1,0 +1,83 @@
+"""K1 microbenchmark: every implementation of the fused blobness kernel on one synthetic frame,
+CUDA events, L2 flushed between launches, plus the deviation of each f32 variant from the f64 kernel.
+
+    python scripts/k1_bench.py [--size 2048] [--iters 20]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from detecting_cones_aoslo_b200.engine import Engine
+from detecting_cones_aoslo_b200.synth import synth_aoslo
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=2048)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--flush", default="write", choices=["write", "write+read", "none"],
+                    help="L2 state before each timed launch: 256 MiB write (dirty lines), the same followed by a "
+                         "256 MiB read sweep (cold and clean), or nothing (warm)")
+    ap.add_argument("--dbg", default="0")
+    ap.add_argument("--variants", default="band,pair:16,pair:20,pair:24,pair:28,pair:32,pair:36,pair:24:2,pair:auto")
+    args = ap.parse_args()
+    os.environ["AOSLO_K1_DBG"] = args.dbg
+    b = 15
+    img, _ = synth_aoslo(args.size, args.size, 5.8, 2022)
+    pimg = np.pad(img, b, mode='symmetric')[: args.size + 2 * b - 1, : args.size + 2 * b - 1]   # odd width like 2077
+    H, W = pimg.shape
+    eng = Engine(H, W, particle_capacity=1024, gt_capacity=1024, device=0)
+    d_img = eng.upload_image(pimg)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    flush2 = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device='cuda')
+    Rb64 = eng.empty((H, W), torch.float64)
+    g64 = eng.empty((H, W, 2), torch.float64)
+    eng.blobness(d_img, 'custom', 'np_grad', (1.0,), torch.float64, out=(Rb64, g64))
+    torch.cuda.synchronize()
+    out = {"shape": [H, W], "flush": args.flush, "results": {}}
+    for var in args.variants.split(","):
+        os.environ.pop("AOSLO_BLOBNESS_KERNEL", None)
+        os.environ.pop("AOSLO_PAIR_TH", None)
+        os.environ.pop("AOSLO_PAIR_OCC", None)
+        if var == "band":
+            os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
+        elif var.startswith("pair:") and var != "pair:auto":
+            os.environ["AOSLO_PAIR_TH"] = var.split(":")[1]
+            if len(var.split(":")) > 2:
+                os.environ["AOSLO_PAIR_OCC"] = var.split(":")[2]
+        Rb = eng.empty((H, W), torch.float32)
+        g = eng.empty((H, W, 2), torch.float32)
+        Rb.fill_(float('nan'))
+        g.fill_(float('nan'))
+        ms = []
+        for i in range(3 + args.iters):
+            if args.flush != "none":
+                flush.fill_(1)
+            if args.flush == "write+read":
+                sink = flush2.sum()
+            torch.cuda._sleep(200000)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.blobness(d_img, 'custom', 'np_grad', (1.0,), torch.float32, out=(Rb, g))
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ms.append(a.elapsed_time(e))
+        st = eng.status(clear=True)
+        err_rb = float((Rb.double() - Rb64).abs().max() / Rb64.abs().max())
+        err_g = float((g.double() - g64).abs().max() / g64.abs().max())
+        us = float(np.median(ms)) * 1e3
+        out["results"][var] = {"us_median": us, "us_min": float(np.min(ms)) * 1e3, "gbs_13B": 13.0 * H * W / us / 1e3,
+                               "frac_of_6459.6": 13.0 * H * W / us / 1e3 / 6459.6, "rel_err_Rb": err_rb,
+                               "rel_err_grad": err_g, "status": st,
+                               "nan": bool(torch.isnan(Rb).any() or torch.isnan(g).any())}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
