@@ -37,6 +37,7 @@ def main():
     flush2 = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device='cuda')
     Rb64 = eng.empty((H, W), torch.float64)
     g64 = eng.empty((H, W, 2), torch.float64)
+    os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
     eng.blobness(d_img, 'custom', 'np_grad', (1.0,), torch.float64, out=(Rb64, g64))
     torch.cuda.synchronize()
     out = {"shape": [H, W], "flush": args.flush, "results": {}}
@@ -44,14 +45,22 @@ def main():
         os.environ.pop("AOSLO_BLOBNESS_KERNEL", None)
         os.environ.pop("AOSLO_PAIR_TH", None)
         os.environ.pop("AOSLO_PAIR_OCC", None)
-        if var == "band":
+        os.environ.pop("AOSLO_DTILE_TH", None)
+        f64 = var.startswith("d:")
+        dt = torch.float64 if f64 else torch.float32
+        bpp = 25.0 if f64 else 13.0
+        if var == "d:band":
+            os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
+        elif f64:
+            os.environ["AOSLO_DTILE_TH"] = var.split(":")[1]
+        elif var == "band":
             os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
         elif var.startswith("pair:") and var != "pair:auto":
             os.environ["AOSLO_PAIR_TH"] = var.split(":")[1]
             if len(var.split(":")) > 2:
                 os.environ["AOSLO_PAIR_OCC"] = var.split(":")[2]
-        Rb = eng.empty((H, W), torch.float32)
-        g = eng.empty((H, W, 2), torch.float32)
+        Rb = eng.empty((H, W), dt)
+        g = eng.empty((H, W, 2), dt)
         Rb.fill_(float('nan'))
         g.fill_(float('nan'))
         ms = []
@@ -63,18 +72,47 @@ def main():
             torch.cuda._sleep(200000)
             a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            eng.blobness(d_img, 'custom', 'np_grad', (1.0,), torch.float32, out=(Rb, g))
+            eng.blobness(d_img, 'custom', 'np_grad', (1.0,), dt, out=(Rb, g))
             e.record()
             torch.cuda.synchronize()
             if i >= 3:
                 ms.append(a.elapsed_time(e))
+        # streamed: NB distinct frames (inputs + outputs 8 x 56 MB > the 126 MB L2) back to back between ONE event
+        # pair, the GPU parked behind a sleep kernel while the host enqueues, so that neither launch latency nor
+        # the ~1 us event resolution enters the per-launch figure
+        NB, REP = 8, 4
+        if not hasattr(main, "_bufs"):
+            main._bufs = {}
+        if dt not in main._bufs:
+            main._bufs.clear()
+            main._bufs[dt] = ([eng.upload_image(pimg) for _ in range(NB)],
+                              [eng.empty((H, W), dt) for _ in range(NB)],
+                              [eng.empty((H, W, 2), dt) for _ in range(NB)])
+        imgs, rbs, gs = main._bufs[dt]
+        stream_us = []
+        for it in range(3):
+            flush.fill_(1)
+            torch.cuda._sleep(6000000)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for rep in range(REP):
+                for f in range(NB):
+                    eng.blobness(imgs[f], 'custom', 'np_grad', (1.0,), dt, out=(rbs[f], gs[f]))
+            e.record()
+            torch.cuda.synchronize()
+            stream_us.append(a.elapsed_time(e) * 1e3 / (NB * REP))
+        sus = float(np.min(stream_us))
         st = eng.status(clear=True)
         err_rb = float((Rb.double() - Rb64).abs().max() / Rb64.abs().max())
         err_g = float((g.double() - g64).abs().max() / g64.abs().max())
+        if f64:          # against the band kernel: must be bit identical
+            err_rb = float((Rb != Rb64).sum())
+            err_g = float((g != g64).sum())
         us = float(np.median(ms)) * 1e3
-        out["results"][var] = {"us_median": us, "us_min": float(np.min(ms)) * 1e3, "gbs_13B": 13.0 * H * W / us / 1e3,
-                               "frac_of_6459.6": 13.0 * H * W / us / 1e3 / 6459.6, "rel_err_Rb": err_rb,
-                               "rel_err_grad": err_g, "status": st,
+        out["results"][var] = {"us_median": us, "us_min": float(np.min(ms)) * 1e3, "gbs": bpp * H * W / us / 1e3, "bytes_per_px": bpp,
+                               "frac_of_6459.6": bpp * H * W / us / 1e3 / 6459.6, "rel_err_Rb": err_rb,
+                               "rel_err_grad": err_g, "status": st, "stream_us": sus, "stream_all": stream_us,
+                               "stream_frac_of_6459.6": bpp * H * W / sus / 1e3 / 6459.6,
                                "nan": bool(torch.isnan(Rb).any() or torch.isnan(g).any())}
     print(json.dumps(out))
 
