@@ -210,6 +210,12 @@ class Lane:
         from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs, make_config_struct
         self.torch = torch
         self.img, self.gt, self.cfg = make_workload(frame_seed_index)
+        # the e2e leg hands find_blobs HOST arrays that live in pinned memory (the frame, and a scratch copy of
+        # the GT that is refreshed before every call because find_blobs shifts its GT argument in place)
+        self._img_pin = torch.from_numpy(self.img).pin_memory()
+        self.img = self._img_pin.numpy()
+        self._gt_pin = torch.from_numpy(self.gt.copy()).pin_memory()
+        self.gt_scratch = self._gt_pin.numpy()
         pimg, pgt = prepare_inputs(self.cfg, self.gt.copy(), self.img)
         self.H, self.W = pimg.shape
         self.h2d = self.img.nbytes + self.gt.nbytes       # what find_blobs copies host->device per call
@@ -250,7 +256,8 @@ class Lane:
         """the reference-facing call with HOST buffers (crop/pad, H2D, run, D2H of the records)."""
         from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
         with self.torch.cuda.stream(self.stream):
-            res, _ = find_blobs(dict(self.cfg), self.gt.copy(), self.img, None, False, False, engine=self.eng)
+            np.copyto(self.gt_scratch, self.gt)
+            res, _ = find_blobs(dict(self.cfg), self.gt_scratch, self.img, None, False, False, engine=self.eng)
         return res
 
 
