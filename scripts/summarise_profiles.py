@@ -48,7 +48,13 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
         'smsp__warps_eligible.avg.per_cycle_active', 'smsp__warps_active.avg.per_cycle_active',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+        'sm__cycles_active.avg', 'sm__cycles_elapsed.max', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active']
 
 
 def rep_summary(path):
@@ -88,14 +94,22 @@ if __name__ == '__main__':
     with open(os.path.join(ROOT, 'profiles', '%s_launches.md' % tag), 'w') as f:
         f.write(launch_summary(launch_csv, tag))
     parts, traffic = ["# %s: ncu --set full --clock-control none captures of the fused blobness kernel (K1)\n" % tag], {}
+    others = ["# %s: ncu --set full --clock-control none captures of particle-system kernels (one launch each, "
+              "2048^2 synthetic frame)\n" % tag]
     for rep in sys.argv[3:]:
         text, facts = rep_summary(rep)
+        if 'k1' not in os.path.basename(rep):
+            others.append(text)
+            continue
         parts.append(text)
         if 'dram__bytes_read.sum' in facts:
             key = 'f64' if 'f64' in rep else 'f32'
             traffic[key] = to_bytes(*facts['dram__bytes_read.sum']) + to_bytes(*facts['dram__bytes_write.sum'])
     with open(os.path.join(ROOT, 'profiles', '%s_k1_ncu.md' % tag), 'w') as f:
         f.write("\n".join(parts))
+    if len(others) > 1:
+        with open(os.path.join(ROOT, 'profiles', '%s_particles_ncu.md' % tag), 'w') as f:
+            f.write("\n".join(others))
     with open(os.path.join(ROOT, 'profiles', '%s_k1_traffic.json' % tag), 'w') as f:
         json.dump({"dram_bytes_per_launch": traffic,
                    "note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on the 2077x2077 frame; "

@@ -80,6 +80,52 @@ def test_blobness_f32_fast_path_ragged_shapes(shape):
     assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
 
 
+@pytest.mark.parametrize("shape", [(8, 8), (9, 130), (130, 9), (97, 229), (100, 229), (48, 117), (49, 118), (50, 119),
+                                   (51, 120), (233, 341), (64, 224), (72, 225), (600, 700)])
+@pytest.mark.parametrize("variant", ["auto", "16:3", "20:3", "24:2", "28:2", "36:2"])
+def test_blobness_f32_pair_kernel_shapes_and_tilings(shape, variant, monkeypatch):
+    """The f32 pair kernel (two tiles per CTA, ghost-value borders, zero-filled staging) at every tile height /
+    residency it is built for, on shapes that put the image border at every position of a tile pair (tile B
+    partly or wholly outside, the right border inside the halo columns, one to seven tile columns)."""
+    if variant != "auto":
+        th, occ = variant.split(":")
+        monkeypatch.setenv("AOSLO_PAIR_TH", th)
+        monkeypatch.setenv("AOSLO_PAIR_OCC", occ)
+    rng = np.random.default_rng(shape[0] * 7919 + shape[1])
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
+    gref = orc.calc_grad_field(ref, 'np_grad')
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                    dtype=np.float32, return_grad=True)
+    assert np.isfinite(rb).all() and np.isfinite(g).all()
+    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()            # north_star: 1e-4 relative in fp32
+    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (9, 130), (130, 9), (97, 229), (49, 118), (51, 120), (233, 341), (600, 700)])
+@pytest.mark.parametrize("th", ["16", "24", "32", "48", "band"])
+def test_blobness_f64_tile_kernel_shapes_and_tilings(shape, th, monkeypatch):
+    """The f64 tile kernel at every tile height, and the band kernel it replaced, against the oracle (5e-14:
+    CUDA's exp is 1 ulp) with identical seed decisions."""
+    if th == "band":
+        monkeypatch.setenv("AOSLO_BLOBNESS_KERNEL", "band")
+    else:
+        monkeypatch.setenv("AOSLO_DTILE_TH", th)
+    rng = np.random.default_rng(shape[0] * 104729 + shape[1])
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'}, return_grad=True)
+    assert np.abs(rb - ref).max() <= 5e-14
+    assert np.abs(g - orc.calc_grad_field(ref, 'np_grad')).max() <= 5e-14
+    assert np.array_equal(rb > 5.0, ref > 5.0)
+
+
+def test_blobness_f32_flat_patch_raises_like_reference():
+    img = np.zeros((64, 160), np.uint8)         # e0 == e1 everywhere: pipeline_with_delitions.py:43 asserts
+    with pytest.raises(AssertionError):
+        gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'}, dtype=np.float32)
+
+
 def test_blobness_sobel_and_simple_div(zoo_field):
     cfg, img, gt, Rb, grad = zoo_field
     rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'sobel'},

@@ -136,3 +136,20 @@ def test_two_rank_gather_equals_single_rank(tmp_path):
     np.testing.assert_array_equal(t0, t1)
     np.testing.assert_array_equal(t0, single)
     assert t0[5, 1] == -1 and np.isnan(t0[5, 2])           # the failed unit is recorded, not fatal
+
+
+def test_u8_over_255_by_reciprocal_and_one_fma_correction_is_correctly_rounded():
+    """blobness_dtile_kernel evaluates img_as_float's v / 255 as q = v * r, q + fma(-q, 255, v) * r with
+    r = fl(1 / 255); exact rational arithmetic shows that this is the correctly rounded quotient for every byte
+    (the plain product v * r is wrong for 24 of them)."""
+    from fractions import Fraction
+    r = 1.0 / 255.0
+    wrong_plain = 0
+    for v in range(256):
+        exact = float(Fraction(v, 255))                       # float(Fraction) rounds to nearest even
+        q = float(v) * r
+        wrong_plain += q != exact
+        e = float(Fraction(v) - Fraction(q) * 255)            # fma(-q, 255, v): one rounding
+        q2 = float(Fraction(e) * Fraction(r) + Fraction(q))   # fma(e, r, q): one rounding
+        assert q2 == exact == v / 255.0
+    assert wrong_plain == 24
