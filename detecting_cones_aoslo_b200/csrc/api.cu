@@ -219,7 +219,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_record, sizeof(aoslo_metrics_record), cudaHostAllocDefault) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_lut, 64 * 64));
-    A(dmalloc(&c->d_lut_packed, 64 * 64));
+    A(dmalloc(&c->d_lut_packed, 12288));         // >= grav_table_words(63): rank table of the gravity gather
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
     c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)

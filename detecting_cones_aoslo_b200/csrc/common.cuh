@@ -148,7 +148,7 @@ struct aoslo_ctx {
     aoslo_metrics_record* h_records = nullptr;  // pinned
     int max_records = 0;
     double* d_lut = nullptr;          // [64*64]
-    uint32_t* d_lut_packed = nullptr; // [64*64] (rank + 1) << 16 | index
+    uint32_t* d_lut_packed = nullptr; // [12288] 16-bit rank table of the gravity gather (lut_pack16_kernel)
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd;

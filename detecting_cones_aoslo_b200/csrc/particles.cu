@@ -829,45 +829,69 @@ __global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, do
 // gravity field (utils.py:310-333) as a per-pixel gather over the cell list
 // =======================================================================================
 // field[y][x] = max(-0.48, max over particles p with |x-px|<=h, |y-py|<=h of T[y-py+h][x-px+h]).
-// The max of LUT ENTRIES is taken on their ranks: `packed[i] = (rank(T[i]) + 1) << 16 | i` where
-// rank = number of strictly smaller entries, so an integer max selects exactly the entry a float
-// max would (ties have equal rank and equal value).  A thread owns kGravRows consecutive rows of
-// one column; the packed LUT is staged in shared memory with kGravRows-1 zero rows above and
-// below, so every candidate particle updates all rows with one LDS + IMNMX each and no
-// per-row range test.
+// The max of LUT ENTRIES is taken on their ranks (rank = number of strictly smaller entries, so an integer max
+// selects exactly the entry a float max would; ties have equal rank and equal value).  A thread owns kGravRows
+// consecutive rows of one column and keeps the running maxima of two rows per register as 16-bit ranks: sm_100a
+// has a per-halfword maximum (VIMNMX.U16x2), so one candidate particle updates all 16 rows with 8 LDS + 8 VIMNMX.
+// The rank table is laid out column major with kGravRows-1 zero rows above and below each LUT column, so a
+// candidate's 16 entries are 8 consecutive words and need no per-row range test; a second copy shifted by one
+// row serves the candidates whose first row is odd.  lut_pack16_kernel builds that layout once per LUT in global
+// memory ([2][rfs][ROWS] u16, then the index of one entry per rank), every CTA copies it with 128-bit loads.
 constexpr int kGravRows = 16;
 constexpr int kGravCols = 128;
 
-__global__ void lut_rank_kernel(const double* __restrict__ lut, int n, uint32_t* packed) {
+__host__ __device__ inline int grav_rows_stride(int rfs) {       // even, ROWS / 2 odd (bank spread), >= rows + 1
+    int r = rfs + 2 * (kGravRows - 1) + 1;
+    r += r & 1;
+    if (((r / 2) & 1) == 0) r += 2;
+    return r;
+}
+__host__ __device__ inline int grav_table_words(int rfs) {       // u32 words of the packed table (16-byte multiple)
+    int u16s = 2 * rfs * grav_rows_stride(rfs) + rfs * rfs + 1;
+    return ((u16s + 1) / 2 + 3) & ~3;
+}
+
+// table must be zeroed before the launch
+__global__ void lut_pack16_kernel(const double* __restrict__ lut, int rfs, uint16_t* table) {
+    const int n = rfs * rfs, ROWS = grav_rows_stride(rfs), pad = kGravRows - 1;
+    uint16_t* idx_by_rank = table + 2 * rfs * ROWS;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double v = lut[i];
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += (lut[j] < v) ? 1 : 0;
-        packed[i] = ((uint32_t)(rank + 1) << 16) | (uint32_t)i;
+        const int ry = i / rfs, cx = i - ry * rfs;
+        const uint16_t rk = (uint16_t)(rank + 1);
+        table[cx * ROWS + ry + pad] = rk;                                  // copy A: padded row r at index r
+        table[rfs * ROWS + cx * ROWS + ry + pad - 1] = rk;                 // copy B: padded row r at index r - 1
+        idx_by_rank[rank + 1] = (uint16_t)i;                               // ties: equal values, any of them
     }
 }
 
 __global__ void __launch_bounds__(kGravCols) gravity_field_kernel(CellView cl, const double* __restrict__ lut,
-                                                                 const uint32_t* __restrict__ packed, int rfs,
+                                                                 const uint32_t* __restrict__ table, int rfs,
                                                                  int H, int W, double* field) {
-    extern __shared__ uint32_t s_pk[];                // (rfs + 2*(kGravRows-1)) * rfs
+    extern __shared__ __align__(16) uint32_t s_tab[];
     const int h = rfs / 2;
     const int pad = kGravRows - 1;
-    const int rows = rfs + 2 * pad;
-    for (int i = threadIdx.x; i < rows * rfs; i += blockDim.x) {
-        int r = i / rfs - pad;
-        s_pk[i] = (r >= 0 && r < rfs) ? packed[r * rfs + (i % rfs)] : 0u;
+    const int ROWS = grav_rows_stride(rfs);
+    {
+        const int nq = grav_table_words(rfs) / 4;
+        const uint4* src = reinterpret_cast<const uint4*>(table);
+        uint4* dst = reinterpret_cast<uint4*>(s_tab);
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    const uint16_t* s_idx = reinterpret_cast<const uint16_t*>(s_tab) + 2 * rfs * ROWS;
     const int x = blockIdx.x * kGravCols + threadIdx.x;
     const int y0 = blockIdx.y * kGravRows;
     if (x >= W) return;
-    uint32_t best[kGravRows];
+    uint32_t best[kGravRows / 2];
 #pragma unroll
-    for (int r = 0; r < kGravRows; ++r) best[r] = 0u;
+    for (int r = 0; r < kGravRows / 2; ++r) best[r] = 0u;
     const int cxa = max(x - h, 0) >> cl.shift, cxb = min(min(x + h, W - 1) >> cl.shift, cl.gw - 1);
     const int cya = max(y0 - h, 0) >> cl.shift;
     const int cyb = min(min(y0 + kGravRows - 1 + h, H - 1) >> cl.shift, cl.gh - 1);
+    const int copy_b = rfs * ROWS;                    // u16 offset of the shifted copy
     for (int cy = cya; cy <= cyb; ++cy) {
         int p0 = cl.start[cy * cl.gw + cxa], p1 = cl.start[cy * cl.gw + cxb + 1];
         for (int p = p0; p < p1; ++p) {
@@ -875,18 +899,21 @@ __global__ void __launch_bounds__(kGravCols) gravity_field_kernel(CellView cl, c
             int dx = x - (int)pp.x;                    // int(particle[0]) truncation
             int dyb = y0 - (int)pp.y + h + pad;        // padded LUT row of this thread's row 0
             if (dx < -h || dx > h || dyb < 0 || dyb > 2 * h + pad) continue;
-            const uint32_t* col = s_pk + dyb * rfs + (dx + h);
+            // u16 index of the candidate's first entry: even by construction (ROWS even, odd dyb -> copy B at dyb-1)
+            const int e = (dx + h) * ROWS + (dyb & ~1) + (dyb & 1) * copy_b;
+            const uint32_t* col = s_tab + (e >> 1);
 #pragma unroll
-            for (int r = 0; r < kGravRows; ++r) best[r] = max(best[r], col[r * rfs]);
+            for (int r = 0; r < kGravRows / 2; ++r) best[r] = __vmaxu2(best[r], col[r]);
         }
     }
 #pragma unroll
     for (int r = 0; r < kGravRows; ++r) {
         int y = y0 + r;
         if (y >= H) break;
+        const uint32_t rk = (best[r >> 1] >> (16 * (r & 1))) & 0xffffu;
         double v = -0.48;
-        if (best[r]) {
-            double t = lut[best[r] & 0xffffu];
+        if (rk) {
+            double t = lut[s_idx[rk]];
             v = (t > v) ? t : v;
         }
         field[(size_t)y * W + x] = v;
@@ -1536,14 +1563,15 @@ int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, 
     if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
     if ((rfs & 1) == 0) return AOSLO_ERR_INVALID;     // even rfs: shape mismatch in the reference (utils.py:329)
     if (ctx->cl_p.shift < 1) return AOSLO_ERR_UNSUPPORTED;
+    const size_t tab_bytes = sizeof(uint32_t) * grav_table_words(rfs);
     if (!packed_ready) {
-        lut_rank_kernel<<<(rfs * rfs + 127) / 128, 128, 0, s>>>(d_lut, rfs * rfs, ctx->d_lut_packed);
+        AOSLO_CUDA(cudaMemsetAsync(ctx->d_lut_packed, 0, tab_bytes, s));
+        lut_pack16_kernel<<<(rfs * rfs + 127) / 128, 128, 0, s>>>(d_lut, rfs, reinterpret_cast<uint16_t*>(ctx->d_lut_packed));
         AOSLO_LAUNCH_CHECK();
     }
     dim3 grid((W + kGravCols - 1) / kGravCols, (H + kGravRows - 1) / kGravRows);
-    size_t smem = sizeof(uint32_t) * (rfs + 2 * (kGravRows - 1)) * rfs;
-    gravity_field_kernel<<<grid, kGravCols, smem, s>>>(view_of(ctx->cl_p), d_lut, ctx->d_lut_packed, rfs, H, W,
-                                                       d_field);
+    gravity_field_kernel<<<grid, kGravCols, tab_bytes, s>>>(view_of(ctx->cl_p), d_lut, ctx->d_lut_packed, rfs, H, W,
+                                                            d_field);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
