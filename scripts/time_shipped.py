@@ -1,11 +1,10 @@
-"""Latency of the drop-in find_blobs on the shipped annotated image (config_zoo), both tie orders, next to
-the CPU oracle on the same host."""
+"""Latency of the drop-in find_blobs on the shipped annotated image (config_zoo), both tie orders.  (The CPU
+oracle is test infrastructure: its timing on the same inputs comes from bench.py's cpu_baseline leg and tests/.)"""
 import os, sys, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from detecting_cones_aoslo_b200 import configs
 from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
-from oracle import aoslo_oracle as orc
 d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "dataset.npz"))
 img, gt = d["img"], d["gt"].astype(np.float64)
 out = {}
@@ -20,8 +19,4 @@ for tie in ("sklearn", "canonical"):
     torch.cuda.synchronize()
     out[tie] = {"ms_per_run": (time.perf_counter() - t) / 10 * 1e3, "dice_2": res["dice_coeff_2"],
                 "n": res["_summary"]["n_particles"], "iters": res["_summary"]["n_iterations"]}
-t = time.perf_counter()
-ref, _ = orc.find_blobs(configs.zoo_config(), gt.copy(), img, None, False, False, tie_mode="sklearn")
-out["cpu_oracle_s"] = time.perf_counter() - t
-out["cpu_dice_2"] = ref["dice_coeff_2"]
 print(json.dumps(out))
