@@ -87,6 +87,7 @@ SYMBOLS = {
     "aoslo_metrics": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, C.POINTER(MetricsRecord),
                            _vp, _vp]),
     "aoslo_classify": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _vp]),
+    "aoslo_hungarian": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "aoslo_iterate": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _ip]),
     "aoslo_run": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _i, C.POINTER(MetricsRecord), _i, _vp, _vp,
                        C.POINTER(RunSummary), C.POINTER(C.c_float)]),

@@ -22,6 +22,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 UNITS = [
     ("blobness.cu", []),
     ("particles.cu", ["-fmad=false"]),
+    ("hungarian.cu", ["-fmad=false"]),
     ("api.cu", []),
     ("kdtree_host.cpp", []),
 ]

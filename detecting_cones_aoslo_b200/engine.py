@@ -281,6 +281,16 @@ class Engine:
                                 self._p(p2g), self._p(g2p)), "aoslo_metrics")
         return rec, p2g, g2p
 
+    def hungarian(self, gt, pos, want_costs=False):
+        """calc_metrics(mode='hangarian') (reference utils.py:228-234): distance matrix + scipy's rectangular
+        assignment solver restated on the device.  Returns (sum, mean, var, assigned costs or None, steps)."""
+        g, n = gt.shape[0], pos.shape[0]
+        out = (C.c_double * 4)()
+        sel = self.empty((min(g, n),), torch.float64) if want_costs else None
+        check(lib.aoslo_hungarian(self._h, self._stream(), self._p(gt), g, self._p(pos), n, out, self._p(sel)),
+              "aoslo_hungarian")
+        return out[0], out[1], out[2], sel, int(out[3])
+
     def classify(self, g2p, p2g, pos, bx, by, threshold):
         """TP / FN flags per GT point and FP flags per particle (reference utils.visualize_all)."""
         gt_tp = self.empty((g2p.shape[0],), torch.uint8)

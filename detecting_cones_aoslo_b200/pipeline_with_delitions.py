@@ -145,8 +145,8 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     field_dtype = torch.float64 if _get(cur_config, 'field_dtype', 'f64') == 'f64' else torch.float32
     scales = tuple(_get(cur_config, 'blobness_scales', (1.0,)))
     mode = _get(cur_config, 'engine_mode', 'fused')
-    if trace is not None:
-        mode = 'staged'
+    if trace is not None or cur_config['metric_algo'] == 'hangarian':
+        mode = 'staged'          # the assignment solve is a stage of its own (aoslo_hungarian)
 
     eng = engine if engine is not None else get_engine(H, W, n_gt=GT_data.shape[0])
     if eng.H != H or eng.W != W or eng.gt_cap < GT_data.shape[0]:
@@ -191,9 +191,7 @@ def _run_fused(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_id
     if cfg.step_mode < 0:
         raise NotImplementedError("unknown step_mode is a silent no-op in the reference; use engine_mode='staged'")
     if cur_config['metric_algo'] != 'Chamfer':
-        if cur_config['metric_algo'] == 'hangarian':
-            raise NotImplementedError("metric_algo='hangarian' is outside the accelerated hot path")
-        raise ValueError
+        raise ValueError                                   # 'hangarian' runs in the staged driver (find_blobs)
     summ, recs, pos, st, ms = eng.run(cfg, Rb, grad, d_gt, collect_times=bool(_get(cur_config, 'collect_stage_times', True)))
     if summ.status:
         _lib.raise_device_status(summ.status)
@@ -285,12 +283,13 @@ def _run_staged(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_i
             pos, stable = resample(pos, stable)
         t1 = sync_time(t1, 'fix_resample')
         if use_wandb or iteration % cur_config['metric_measure_freq'] == 0:
-            if cur_config['metric_algo'] != 'Chamfer':
-                if cur_config['metric_algo'] == 'hangarian':
-                    raise NotImplementedError("metric_algo='hangarian' is outside the accelerated hot path")
+            if cur_config['metric_algo'] not in ('Chamfer', 'hangarian'):
                 raise ValueError
             rec, p2g, g2p = eng.metrics(pos, stable, d_gt, Rb, bx, by, want_dists=trace is not None)
             pm, lsa_sum, lsa_mean, lsa_var, blob_mean = metrics_from_record(rec)
+            if cur_config['metric_algo'] == 'hangarian':       # calc_metrics(mode='hangarian'), utils.py:228-234
+                lsa_sum, lsa_mean, lsa_var, _, _ = eng.hungarian(d_gt, pos)
+                eng.raise_on_status()
             _track(result, pm, lsa_mean, lsa_var, blob_mean, rec.n_gt, rec.n_particles, use_wandb, experiment_idx)
             if use_wandb:
                 _log_record(log_fn, iteration, pm, lsa_sum, lsa_mean, lsa_var, rec.blob_energy_sum, blob_mean,

@@ -292,16 +292,22 @@ def metrics_from_record(rec):
 
 
 def calc_metrics(particles, GT_particles, gt_to_particles, particles_to_gt, mode='hangarian'):
-    """reference utils.py:225-242.  'Chamfer' is the hot-path mode; 'hangarian' (assignment solve)
-    is outside the accelerated path and is not implemented here."""
+    """reference utils.py:225-242.  'Chamfer' adds the moments of the two nearest-distance arrays;
+    'hangarian' solves the GT x particles assignment problem on the device (aoslo_hungarian: scipy's
+    distance_matrix + linear_sum_assignment restated, same assignment incl. ties) and returns the assigned
+    distances (in the order of the smaller point set) with their sum / mean / var."""
     if mode == 'Chamfer':
         return (gt_to_particles, particles_to_gt), \
             np.sum(gt_to_particles) + np.sum(particles_to_gt), \
             np.mean(gt_to_particles) + np.mean(particles_to_gt), \
             np.var(gt_to_particles) + np.var(particles_to_gt)
     if mode == 'hangarian':
-        raise NotImplementedError("metric_algo='hangarian' (scipy linear_sum_assignment) is outside the "
-                                  "accelerated hot path (SURVEY.md 8f-f3)")
+        particles = np.asarray(particles, dtype=np.float64)
+        GT_particles = np.asarray(GT_particles, dtype=np.float64)
+        eng = _bbox_engine(particles, GT_particles)
+        lsa_sum, lsa_mean, lsa_var, sel, _ = eng.hungarian(_pts(eng, GT_particles), _pts(eng, particles),
+                                                           want_costs=True)
+        return sel.cpu().numpy(), lsa_sum, lsa_mean, lsa_var
     raise ValueError
 
 

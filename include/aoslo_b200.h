@@ -206,6 +206,14 @@ int aoslo_classify(aoslo_ctx* ctx, void* stream, const double* d_dist_g2p, int n
                    const double* d_particles, int n, int bx, int by, int H, int W, double threshold,
                    uint8_t* d_gt_is_tp, uint8_t* d_particle_is_fp);
 
+/* ---- calc_metrics(mode='hangarian') (utils.py:228-234): scipy.spatial.distance_matrix(GT, particles) +
+ * scipy.optimize.linear_sum_assignment restated step by step (same optimal assignment, incl. scipy's tie rule) +
+ * sum / mean / var of the assigned distances.  h_out4: sum, mean, var, number of search steps (diagnostic).
+ * d_assigned_cost (may be NULL): min(n_gt, n) assigned distances in the order of the smaller point set.
+ * Synchronous; allocates the reference's dense n_gt x n matrix for the duration of the call. */
+int aoslo_hungarian(aoslo_ctx* ctx, void* stream, const double* d_gt, int n_gt, const double* d_particles, int n,
+                    double* h_out4, double* d_assigned_cost);
+
 /* ---- one loop iteration: distance force + move + deletion (pipeline_with_delitions.py:173-253),
  * the code path aoslo_run executes per epoch; out-of-place. */
 int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,

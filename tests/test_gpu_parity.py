@@ -649,3 +649,59 @@ def test_classification_sets_match_visualize_all(zoo_field):
         np.testing.assert_array_equal(tp, tp_ref)
         np.testing.assert_array_equal(fn, fn_ref)
         np.testing.assert_array_equal(fp, fp_ref)
+
+
+# ----------------------------------------------------------------------------------- hangarian metric
+@pytest.mark.parametrize("n_gt,n_p,span", [(1, 1, 5), (1, 7, 5), (7, 1, 5), (40, 40, 12), (60, 45, 14), (45, 60, 14),
+                                           (300, 330, 40), (330, 300, 40), (1500, 1600, 90)])
+def test_hungarian_matches_scipy_assignment(n_gt, n_p, span):
+    """aoslo_hungarian against scipy.spatial.distance_matrix + linear_sum_assignment on lattice point sets
+    (distance ties everywhere): the multiset of assigned distances is identical (same assignment up to the row
+    order of the transposed case), sum / mean / var to 1e-12 relative."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial import distance_matrix
+    rng = np.random.default_rng(n_gt * 1009 + n_p)
+    gt = rng.integers(0, span, (n_gt, 2)).astype(np.float64)
+    pts = rng.integers(0, span, (n_p, 2)).astype(np.float64)
+    dm = distance_matrix(gt, pts)
+    r, c = linear_sum_assignment(dm)
+    ref = dm[r, c]
+    sel, s, m, v = gpu_utils.calc_metrics(pts, gt, None, None, mode='hangarian')
+    assert sel.shape == ref.shape
+    assert np.array_equal(np.sort(sel), np.sort(ref))
+    if n_gt <= n_p:
+        assert np.array_equal(sel, ref)                 # same assignment, row by row
+    assert abs(s - ref.sum()) <= 1e-12 * max(1.0, abs(ref.sum()))
+    assert abs(m - ref.mean()) <= 1e-12 * max(1.0, abs(ref.mean()))
+    assert abs(v - ref.var()) <= 1e-12 * max(1.0, abs(ref.var()))
+
+
+def test_find_blobs_hangarian_matches_executed_reference():
+    """metric_algo='hangarian' end to end on the reference's `__main__` crop: the trace of the executed reference
+    (tests/golden, BASELINE.md: best_lsa_mean 1.1107059036299682) and the oracle."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    cfg = configs.variant(configs.main_config(), metric_algo='hangarian')
+    ref, _ = orc.find_blobs(dict(cfg), gt.copy(), img, None, False, False, tie_mode='sklearn')
+    res, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    assert abs(ref['best_lsa_mean'] - 1.1107059036299682) < 1e-12
+    assert abs(res['best_lsa_mean'] - ref['best_lsa_mean']) <= 1e-12
+    assert res['dice_coeff_1'] == ref['dice_coeff_1'] and res['dice_coeff_2'] == ref['dice_coeff_2']
+    assert np.array_equal(res['_final_particles'].cpu().numpy(), ref['final_particles'])
+
+
+def test_hungarian_on_the_shipped_image_problem():
+    """The 7 602 x 8 1xx assignment problem of the shipped image (final particles of the config_zoo run)."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial import distance_matrix
+    cfg = configs.zoo_config()
+    img, gt = load_dataset()
+    ref, _ = orc.find_blobs(dict(cfg), gt.copy(), img, None, False, False, tie_mode='sklearn')
+    pts = ref['final_particles']
+    _, g = _padded(cfg)
+    g = np.asarray(g.cpu().numpy() if hasattr(g, 'cpu') else g, dtype=np.float64)
+    dm = distance_matrix(g, pts)
+    r, c = linear_sum_assignment(dm)
+    sel, s, m, v = gpu_utils.calc_metrics(pts, g, None, None, mode='hangarian')
+    assert np.array_equal(sel, dm[r, c])
+    assert abs(v - dm[r, c].var()) <= 1e-12 * dm[r, c].var()

@@ -153,3 +153,24 @@ def test_u8_over_255_by_reciprocal_and_one_fma_correction_is_correctly_rounded()
         q2 = float(Fraction(e) * Fraction(r) + Fraction(q))   # fma(e, r, q): one rounding
         assert q2 == exact == v / 255.0
     assert wrong_plain == 24
+
+
+def test_lsap_restatement_equals_scipy_on_tie_heavy_instances():
+    """csrc/hungarian.cu restates scipy's linear_sum_assignment (an un-vendored dependency of the reference's
+    calc_metrics('hangarian'), utils.py:228-234); the same restatement in NumPy returns scipy's assignment --
+    not just its cost -- on integer matrices and lattice distances, where optimal assignments are far from unique."""
+    from scipy.optimize import linear_sum_assignment
+    from lsap_restated import lsa_restated
+    rng = np.random.default_rng(0)
+    for t in range(240):
+        nr, nc = rng.integers(1, 36, 2)
+        if t % 3 == 0:
+            c = rng.integers(0, 4, (nr, nc)).astype(float)
+        elif t % 3 == 1:
+            a, b = rng.integers(0, 12, (nr, 2)), rng.integers(0, 12, (nc, 2))
+            c = np.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1).astype(float))
+        else:
+            c = rng.random((nr, nc))
+        r0, c0 = linear_sum_assignment(c)
+        r1, c1, _ = lsa_restated(c)
+        assert np.array_equal(r0, r1) and np.array_equal(c0, c1), (t, nr, nc)
