@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 #include "aoslo_b200.h"
@@ -34,7 +35,12 @@ struct Builder {
     double* bounds;
     int n_nodes;
 
-    void build(int i_node, int idx_start, int idx_end) {
+    // depth < kParallelDepth: the two subtrees (disjoint ranges of idx, disjoint nodes) are built by two threads --
+    // the result is the same sequence of std::nth_element calls on the same ranges, only not one after the other
+    static constexpr int kParallelDepth = 3;
+    static constexpr int kParallelMinPoints = 2048;
+
+    void build(int i_node, int idx_start, int idx_end, int depth = 0) {
         // init_node (sklearn/neighbors/_kd_tree.pyx.tp:72-104): bounds = min/max of the members
         double lo0 = INFINITY, lo1 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY;
         for (int i = idx_start; i < idx_end; ++i) {
@@ -50,23 +56,23 @@ struct Builder {
         if (idx_end - idx_start < 2) return;            // "too many nodes allocated" guard: leaf
         int n_points = idx_end - idx_start;
         int n_mid = n_points / 2;
-        // find_node_split_dim (:600-644): first dimension with the strictly largest spread
+        // find_node_split_dim (:600-644): first dimension with the strictly largest spread; max - min of the
+        // members per dimension is exactly the bounds just computed (fmax / fmin of the same values)
         int j_max = 0;
         double max_spread = 0;
-        for (int j = 0; j < 2; ++j) {
-            double mx = data[(size_t)idx[idx_start] * 2 + j], mn = mx;
-            for (int i = idx_start + 1; i < idx_end; ++i) {
-                double v = data[(size_t)idx[i] * 2 + j];
-                mx = std::fmax(mx, v);
-                mn = std::fmin(mn, v);
-            }
-            double spread = mx - mn;
-            if (spread > max_spread) { max_spread = spread; j_max = j; }
-        }
+        const double spread[2] = {hi0 - lo0, hi1 - lo1};
+        for (int j = 0; j < 2; ++j)
+            if (spread[j] > max_spread) { max_spread = spread[j]; j_max = j; }
         IndexComparator cmp{data, j_max};
         std::nth_element(idx + idx_start, idx + idx_start + n_mid, idx + idx_end, cmp);
-        build(2 * i_node + 1, idx_start, idx_start + n_mid);
-        build(2 * i_node + 2, idx_start + n_mid, idx_end);
+        if (depth < kParallelDepth && n_points >= kParallelMinPoints) {
+            std::thread left([=] { build(2 * i_node + 1, idx_start, idx_start + n_mid, depth + 1); });
+            build(2 * i_node + 2, idx_start + n_mid, idx_end, depth + 1);
+            left.join();
+        } else {
+            build(2 * i_node + 1, idx_start, idx_start + n_mid, depth + 1);
+            build(2 * i_node + 2, idx_start + n_mid, idx_end, depth + 1);
+        }
     }
 };
 
