@@ -75,10 +75,8 @@ static int alloc_cell_list(CellList& cl, int H, int W, int cap, int shift) {
 
 }  // namespace aoslo
 // device + pinned-host mirrors of the sklearn-order KD tree; only the sklearn tie mode needs them
-int aoslo::kd_reserve(aoslo_ctx* c) {
-    KdTreeDev& kd = c->kd;
-    if (kd.cap >= c->cap) return AOSLO_OK;
-    int cap = c->cap;
+static int kd_alloc(aoslo::KdTreeDev& kd, int cap) {
+    using namespace aoslo;
     size_t nn = (size_t)2 * cap + 2;
     AOSLO_TRY(dmalloc(&kd.idx_array, cap));
     AOSLO_TRY(dmalloc(&kd.node_start, nn));
@@ -90,6 +88,20 @@ int aoslo::kd_reserve(aoslo_ctx* c) {
     AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_node_end, sizeof(int32_t) * nn, cudaHostAllocDefault));
     AOSLO_CUDA(cudaHostAlloc((void**)&kd.h_node_bounds, sizeof(double) * 4 * nn, cudaHostAllocDefault));
     kd.cap = cap;
+    kd.cached_n = -1;
+    return AOSLO_OK;
+}
+static void kd_free(aoslo::KdTreeDev& kd) {
+    cudaFree(kd.idx_array); cudaFree(kd.node_start); cudaFree(kd.node_end); cudaFree(kd.node_bounds);
+    cudaFreeHost(kd.h_points); cudaFreeHost(kd.h_idx_array); cudaFreeHost(kd.h_node_start);
+    cudaFreeHost(kd.h_node_end); cudaFreeHost(kd.h_node_bounds);
+}
+
+int aoslo::kd_reserve(aoslo_ctx* c) {
+    if (c->kd.cap >= c->cap) return AOSLO_OK;
+    AOSLO_TRY(kd_alloc(c->kd, c->cap));
+    AOSLO_TRY(kd_alloc(c->kd2, c->cap));
+    AOSLO_CUDA(cudaHostAlloc((void**)&c->kd_stage, sizeof(double) * 2 * c->cap, cudaHostAllocDefault));
     return AOSLO_OK;
 }
 namespace aoslo {
@@ -249,10 +261,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
     cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_packed); cudaFree(c->d_field); cudaFree(c->d_win);
-    KdTreeDev& kd = c->kd;
-    cudaFree(kd.idx_array); cudaFree(kd.node_start); cudaFree(kd.node_end); cudaFree(kd.node_bounds);
-    cudaFreeHost(kd.h_points); cudaFreeHost(kd.h_idx_array); cudaFreeHost(kd.h_node_start);
-    cudaFreeHost(kd.h_node_end); cudaFreeHost(kd.h_node_bounds);
+    kd_free(c->kd); kd_free(c->kd2); cudaFreeHost(c->kd_stage);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_block) cudaEventDestroy(c->ev_block);

@@ -100,6 +100,7 @@ struct KdTreeDev {
     int32_t* h_node_end = nullptr;
     double* h_node_bounds = nullptr;
     int cap = 0;
+    int cached_n = -1;                // the device arrays hold the tree of the cached_n points in h_points
 };
 
 }  // namespace aoslo
@@ -151,7 +152,9 @@ struct aoslo_ctx {
     uint32_t* d_lut_packed = nullptr; // [12288] 16-bit rank table of the gravity gather (lut_pack16_kernel)
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
-    aoslo::KdTreeDev kd;
+    aoslo::KdTreeDev kd, kd2;         // two cached trees (sklearn-order tie mode): typically particles and GT
+    double* kd_stage = nullptr;       // pinned [cap*2]: the points of the current call, compared with the caches
+    int kd_lru = 0;                   // slot to overwrite on a miss
     cudaEvent_t ev[12] = {};
     std::vector<cudaEvent_t> ev_pool;   // stage-timing events of aoslo_run
 };

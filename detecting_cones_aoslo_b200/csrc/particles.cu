@@ -511,20 +511,35 @@ int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_po
                 int n_query, int k, int32_t* d_idx, double* d_d2) {
     if (n_points > ctx->cap) return AOSLO_ERR_CAPACITY;
     AOSLO_TRY(kd_reserve(ctx));
-    KdTreeDev& kd = ctx->kd;
     if (k < 1 || k > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (n_points < k) return AOSLO_ERR_INVALID;   // sklearn: ValueError("Expected n_neighbors <= n_samples_fit")
-    // host round trip: sklearn's idx_array is the residue of libstdc++ std::nth_element
-    AOSLO_CUDA(cudaMemcpyAsync(kd.h_points, d_points, sizeof(double) * 2 * n_points, cudaMemcpyDeviceToHost, s));
+    // host round trip: sklearn's idx_array is the residue of libstdc++ std::nth_element.  Two trees stay cached
+    // (typically the particles and the GT): the positions do not change between the metrics of one iteration and the
+    // force step of the next, and the GT never changes
+    AOSLO_CUDA(cudaMemcpyAsync(ctx->kd_stage, d_points, sizeof(double) * 2 * n_points, cudaMemcpyDeviceToHost, s));
     AOSLO_TRY(stream_wait(ctx, s));
+    KdTreeDev* slots[2] = {&ctx->kd, &ctx->kd2};
+    KdTreeDev* hit = nullptr;
+    for (KdTreeDev* c : slots)
+        if (c->cached_n == n_points && memcmp(c->h_points, ctx->kd_stage, sizeof(double) * 2 * n_points) == 0) hit = c;
     int n_nodes = aoslo_kdtree_num_nodes(n_points);
-    AOSLO_TRY(aoslo_kdtree_build_host(kd.h_points, n_points, kd.h_idx_array, kd.h_node_start, kd.h_node_end,
-                                      kd.h_node_bounds, n_nodes));
-    AOSLO_CUDA(cudaMemcpyAsync(kd.idx_array, kd.h_idx_array, sizeof(int32_t) * n_points, cudaMemcpyHostToDevice, s));
-    AOSLO_CUDA(cudaMemcpyAsync(kd.node_start, kd.h_node_start, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
-    AOSLO_CUDA(cudaMemcpyAsync(kd.node_end, kd.h_node_end, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
-    AOSLO_CUDA(cudaMemcpyAsync(kd.node_bounds, kd.h_node_bounds, sizeof(double) * 4 * n_nodes,
-                               cudaMemcpyHostToDevice, s));
+    if (hit) {
+        ctx->kd_lru = (hit == slots[0]) ? 1 : 0;
+    } else {
+        hit = slots[ctx->kd_lru];
+        ctx->kd_lru ^= 1;
+        hit->cached_n = -1;
+        memcpy(hit->h_points, ctx->kd_stage, sizeof(double) * 2 * n_points);
+        AOSLO_TRY(aoslo_kdtree_build_host(hit->h_points, n_points, hit->h_idx_array, hit->h_node_start, hit->h_node_end,
+                                          hit->h_node_bounds, n_nodes));
+        AOSLO_CUDA(cudaMemcpyAsync(hit->idx_array, hit->h_idx_array, sizeof(int32_t) * n_points, cudaMemcpyHostToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(hit->node_start, hit->h_node_start, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(hit->node_end, hit->h_node_end, sizeof(int32_t) * n_nodes, cudaMemcpyHostToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(hit->node_bounds, hit->h_node_bounds, sizeof(double) * 4 * n_nodes,
+                                   cudaMemcpyHostToDevice, s));
+        hit->cached_n = n_points;
+    }
+    KdTreeDev& kd = *hit;
     KdView v{n_points, n_nodes, kd.idx_array, kd.node_start, kd.node_end, kd.node_bounds, (const double2*)d_points};
     int blocks = (n_query + 127) / 128;
     if (blocks > 0) {

@@ -52,6 +52,7 @@ def main():
         if var == "d:band":
             os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
         elif f64:
+            os.environ["AOSLO_BLOBNESS_KERNEL"] = "dtile"
             os.environ["AOSLO_DTILE_TH"] = var.split(":")[1]
         elif var == "band":
             os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"

@@ -110,6 +110,7 @@ def test_blobness_f64_tile_kernel_shapes_and_tilings(shape, th, monkeypatch):
     if th == "band":
         monkeypatch.setenv("AOSLO_BLOBNESS_KERNEL", "band")
     else:
+        monkeypatch.setenv("AOSLO_BLOBNESS_KERNEL", "dtile")
         monkeypatch.setenv("AOSLO_DTILE_TH", th)
     rng = np.random.default_rng(shape[0] * 104729 + shape[1])
     img = rng.integers(0, 256, size=shape, dtype=np.uint8)
