@@ -429,6 +429,30 @@ def run_gpu(args):
         if i >= 2:
             stream_ms.append(a.elapsed_time(b) / (NB * REP))
     k1_f32_stream_ms = float(np.mean(stream_ms))
+    # the same 32 launches alternating on two CUDA streams (what concurrent lanes do): the ramp / tail of one launch
+    # overlaps the body of the next
+    two = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    two_ms = []
+    for i in range(2 + 3):
+        evict_l2()
+        torch.cuda._sleep(6000000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for st_ in two:
+            st_.wait_event(a)
+        for _ in range(REP):
+            for j in range(NB):
+                with torch.cuda.stream(two[j & 1]):
+                    eng.blobness(s_img[j], 'custom', 'np_grad', (1.0,), torch.float32, out=(s_rb[j], s_g[j]))
+        for st_ in two:
+            d = torch.cuda.Event()
+            d.record(st_)
+            main.wait_event(d)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            two_ms.append(a.elapsed_time(b) / (NB * REP))
+    k1_f32_two_ms = float(np.mean(two_ms))
     del s_img, s_rb, s_g
 
     if rank == 0:
@@ -463,6 +487,8 @@ def run_gpu(args):
                                          "bytes because most of the output is still in the 126 MB L2 at kernel end",
                          "algorithmic_bytes_per_launch": bytes_f32, "ms_per_launch": k1_f32_stream_ms,
                          "ms_single_launch_l2_flushed": k1_f32_ms,
+                         "ms_per_frame_two_streams": k1_f32_two_ms,
+                         "frac_two_streams": bytes_f32 / (k1_f32_two_ms / 1e3) / 1e9 / peak,
                          "frac_single_launch": bytes_f32 / (k1_f32_ms / 1e3) / 1e9 / peak,
                          "timed": "CUDA events on the launch stream around 32 back-to-back launches over 8 distinct "
                                   "frames (working set 450 MB > L2), GPU parked while the host enqueues",
