@@ -226,8 +226,8 @@ class Lane:
         self.d_img = self.eng.upload_image(pimg)
         self.d_gt = self.eng.dev(pgt, torch.float64)
         self.cs = make_config_struct(self.cfg, self.H, self.W)
-        self.Rb = self.eng.empty((self.H, self.W), torch.float64)
-        self.grad = self.eng.empty((self.H, self.W, 2), torch.float64)
+        self.Rb = self.eng.field(self.H, self.W, torch.float64)
+        self.grad = self.eng.field(self.H, self.W, torch.float64, 2)
         self.n_gt = int(pgt.shape[0])
         self.k1_events = []
         self.last = None
@@ -398,8 +398,8 @@ def run_gpu(args):
     #            HBM and its stores push older frames out) x 4 rounds back to back between ONE event pair, the GPU
     #            parked behind a sleep kernel while the host enqueues: the kernel's average launch duration
     eng = lane0.eng
-    Rb32 = eng.empty((H, W), torch.float32)
-    g32 = eng.empty((H, W, 2), torch.float32)
+    Rb32 = eng.field(H, W, torch.float32)
+    g32 = eng.field(H, W, torch.float32, 2)
     f32_ms = []
     for i in range(3 + 10):
         evict_l2()
@@ -413,8 +413,8 @@ def run_gpu(args):
     k1_f32_ms = float(np.mean(f32_ms))
     NB, REP = 8, 4
     s_img = [eng.upload_image(lanes[j % len(lanes)].pimg) for j in range(NB)]
-    s_rb = [eng.empty((H, W), torch.float32) for _ in range(NB)]
-    s_g = [eng.empty((H, W, 2), torch.float32) for _ in range(NB)]
+    s_rb = [eng.field(H, W, torch.float32) for _ in range(NB)]
+    s_g = [eng.field(H, W, torch.float32, 2) for _ in range(NB)]
     stream_ms = []
     for i in range(2 + 3):
         evict_l2()

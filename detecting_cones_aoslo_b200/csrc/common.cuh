@@ -38,6 +38,11 @@ void count_launches(int n);
         AOSLO_CUDA(cudaGetLastError());                                          \
     } while (0)
 
+// Row pitch (in pixels) of every blobness / gradient FIELD buffer: rows are padded to a multiple of 4 pixels so
+// that a row starts 16-byte aligned in f32 (32-byte in f64) whatever the frame width -- the alignment TMA tensor
+// stores need.  R_b is (H, fpitch(W)), the gradient (H, fpitch(W), 2); only the first W pixels of a row are data.
+__host__ __device__ inline int fpitch(int W) { return (W + 3) & ~3; }
+
 constexpr int kThreads = 256;          // block size of the grid-stride kernels
 constexpr int kScanThreads = 1024;     // block size of the ordered-compaction kernels
 constexpr int kMaxScanBlocks = 1024;   // spine length of the 3-phase scan

@@ -564,7 +564,7 @@ struct SeedOp {
     int* status;
     __device__ int value(int m) const {
         int y = by + m / wi, x = bx + m % wi;
-        return ((double)Rb[(size_t)y * W + x] > thr) ? 1 : 0;
+        return ((double)Rb[(size_t)y * fpitch(W) + x] > thr) ? 1 : 0;
     }
     __device__ void emit(int m, int v, int dst) const {
         if (!v) return;
@@ -608,7 +608,7 @@ __device__ __forceinline__ double energy_at(const T* Rb, double2 p, int W, int H
         atomicOr(status, (p.x != p.x || p.y != p.y) ? AOSLO_DEV_NAN : AOSLO_DEV_ESCAPED);
         return 0.0;
     }
-    return (double)Rb[(size_t)iy * W + ix];
+    return (double)Rb[(size_t)iy * fpitch(W) + ix];
 }
 
 template <typename T>
@@ -1039,7 +1039,7 @@ __device__ __forceinline__ bool move_one(double2& p, double2 f, const T* __restr
         atomicOr(status, AOSLO_DEV_ESCAPED);
         return false;
     }
-    size_t o = ((size_t)iy * W + ix) * 2;
+    size_t o = ((size_t)iy * fpitch(W) + ix) * 2;
     double g0 = (double)grad[o], g1 = (double)grad[o + 1];
     if (step_mode == AOSLO_STEP_CONTIN) {
         double dy = (-1.0 * lb) * g0 + (-ld) * f.x;

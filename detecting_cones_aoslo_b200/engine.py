@@ -110,6 +110,34 @@ class Engine:
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
+    # FIELD buffers (R_b (H,W), gradient (H,W,2)): the library stores their rows with a pitch of fpitch(W) pixels
+    # (W rounded up to a multiple of 4: 16-byte aligned rows for the TMA stores of the blobness kernel).  Tensors
+    # are VIEWS [:, :W] of the padded buffers; .cpu() / .contiguous() give the dense array.
+    @staticmethod
+    def fpitch(W):
+        return (int(W) + 3) // 4 * 4
+
+    def field(self, H, W, dtype, components=1):
+        if components == 1:
+            return self.empty((H, self.fpitch(W)), dtype)[:, :W]
+        return self.empty((H, self.fpitch(W), components), dtype)[:, :W, :]
+
+    def to_field(self, a, dtype):
+        """dense (H,W) / (H,W,2) host array or device tensor -> padded device field view."""
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+        out = self.field(t.shape[0], t.shape[1], dtype, 1 if t.dim() == 2 else t.shape[2])
+        out.copy_(t.to(device=self.device, dtype=dtype))
+        return out
+
+    def _pf(self, t):
+        """pointer of a field view; a dense tensor whose width is not a multiple of 4 is a caller bug."""
+        if t is None:
+            return C.c_void_p(0)
+        per_px = 1 if t.dim() == 2 else t.shape[2]
+        if t.stride(0) != self.fpitch(t.shape[1]) * per_px or t.stride(1) != per_px:
+            raise ValueError("field tensors must come from Engine.field / Engine.to_field (padded row pitch)")
+        return C.c_void_p(t.data_ptr())
+
     @staticmethod
     def _p(t):
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
@@ -172,8 +200,8 @@ class Engine:
         ns = len(scales)
         wts, radii, s2 = self._scale_tables(tuple(float(s) for s in scales))
         if out is None:
-            Rb = self.empty((H, W), dtype)
-            grad = self.empty((H, W, 2), dtype) if want_grad else None
+            Rb = self.field(H, W, dtype)
+            grad = self.field(H, W, dtype, 2) if want_grad else None
         else:
             Rb, grad = out
         check(lib.aoslo_blobness(self._h, self._stream(), self._p(img_u8), H, W, img_u8.stride(0),
@@ -181,22 +209,22 @@ class Engine:
                                  radii.ctypes.data_as(C.POINTER(C.c_int)),
                                  s2.ctypes.data_as(C.POINTER(C.c_double)), ns,
                                  _lib.FORMULA[formula], _lib.GRAD[grad_type], self._fdt(Rb),
-                                 self._p(Rb), self._p(grad)), "aoslo_blobness")
+                                 self._pf(Rb), self._pf(grad)), "aoslo_blobness")
         return Rb, grad
 
     def grad_field(self, field, grad_type):
         if grad_type not in _lib.GRAD:
             raise AttributeError('grad_type {0} is not implemented'.format(grad_type))
         H, W = field.shape
-        out = self.empty((H, W, 2), field.dtype)
-        check(lib.aoslo_grad_field(self._h, self._stream(), self._p(field), H, W, _lib.GRAD[grad_type],
-                                   self._fdt(field), self._p(out)), "aoslo_grad_field")
+        out = self.field(H, W, field.dtype, 2)
+        check(lib.aoslo_grad_field(self._h, self._stream(), self._pf(field), H, W, _lib.GRAD[grad_type],
+                                   self._fdt(field), self._pf(out)), "aoslo_grad_field")
         return out
 
     # ------------------------------------------------------------------ L3 particle system
     def seed(self, Rb, bx, by, threshold):
         pos = self.empty((self.cap, 2), torch.float64)
-        check(lib.aoslo_seed(self._h, self._stream(), self._p(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by),
+        check(lib.aoslo_seed(self._h, self._stream(), self._pf(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by),
                              float(threshold), self._p(pos), self.cap, C.byref(self._n_out)), "aoslo_seed")
         return pos[: self._n_out.value]
 
@@ -217,7 +245,7 @@ class Engine:
         pos_out = self.empty((n, 2), torch.float64)
         st_out = self.empty((n,), torch.uint8)
         deleted = self.empty((n,), torch.uint8)
-        check(lib.aoslo_delete_close(self._h, self._stream(), self._p(pos), self._p(stable), n, self._p(Rb),
+        check(lib.aoslo_delete_close(self._h, self._stream(), self._p(pos), self._p(stable), n, self._pf(Rb),
                                      self._fdt(Rb), self.H, self.W, float(threshold), _lib.TIE[tie_mode],
                                      self._p(pos_out), self._p(st_out), self._p(deleted), C.byref(self._n_out)),
               "aoslo_delete_close")
@@ -265,7 +293,7 @@ class Engine:
         return force
 
     def move(self, pos, stable, grad, force, lambda_blob, lambda_dist, step_mode):
-        check(lib.aoslo_move(self._h, self._stream(), self._p(pos), self._p(stable), pos.shape[0], self._p(grad),
+        check(lib.aoslo_move(self._h, self._stream(), self._p(pos), self._p(stable), pos.shape[0], self._pf(grad),
                              self._fdt(grad), self.H, self.W, self._p(force), float(lambda_blob), float(lambda_dist),
                              _lib.STEP[step_mode]), "aoslo_move")
         return pos
@@ -277,7 +305,7 @@ class Engine:
         p2g = self.empty((n,), torch.float64) if want_dists else None
         g2p = self.empty((g,), torch.float64) if want_dists else None
         check(lib.aoslo_metrics(self._h, self._stream(), self._p(pos), self._p(stable), n, self._p(gt), g,
-                                self._p(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by), C.byref(rec),
+                                self._pf(Rb), self._fdt(Rb), self.H, self.W, int(bx), int(by), C.byref(rec),
                                 self._p(p2g), self._p(g2p)), "aoslo_metrics")
         return rec, p2g, g2p
 
@@ -305,7 +333,7 @@ class Engine:
         n = pos.shape[0]
         pos_out = self.empty((n, 2), torch.float64)
         st_out = self.empty((n,), torch.uint8)
-        check(lib.aoslo_iterate(self._h, self._stream(), C.byref(cfg_struct), self._p(Rb), self._p(grad),
+        check(lib.aoslo_iterate(self._h, self._stream(), C.byref(cfg_struct), self._pf(Rb), self._pf(grad),
                                 self._fdt(Rb), self._p(pos), self._p(stable), n, self._p(pos_out), self._p(st_out),
                                 C.byref(self._n_out)), "aoslo_iterate")
         m = self._n_out.value
@@ -317,7 +345,7 @@ class Engine:
         CUDA graph instead of re-capturing it."""
         key = str(dtype)
         if key not in self._fields:
-            self._fields[key] = (self.empty((self.H, self.W), dtype), self.empty((self.H, self.W, 2), dtype))
+            self._fields[key] = (self.field(self.H, self.W, dtype), self.field(self.H, self.W, dtype, 2))
         return self._fields[key]
 
     def run(self, cfg_struct, Rb, grad, gt, max_records=None, collect_times=True):
@@ -330,7 +358,7 @@ class Engine:
         ms = (C.c_float * 5)() if collect_times else None
         pos = self.empty((self.cap, 2), torch.float64)
         st = self.empty((self.cap,), torch.uint8)
-        check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._p(Rb), self._p(grad), self._fdt(Rb),
+        check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._pf(Rb), self._pf(grad), self._fdt(Rb),
                             self._p(gt), gt.shape[0], recs, max_records, self._p(pos), self._p(st), C.byref(summ), ms),
               "aoslo_run")
         n = summ.n_particles

@@ -116,7 +116,7 @@ def calc_grad_field(img, grad_type):
     img = np.ascontiguousarray(img)
     tdt = torch.float32 if img.dtype == np.float32 else torch.float64
     eng = get_engine(*img.shape)
-    return eng.grad_field(eng.dev(img, tdt), grad_type).cpu().numpy()
+    return eng.grad_field(eng.to_field(img, tdt), grad_type).cpu().numpy()
 
 
 # ------------------------------------------------------------------------------ L3 particle system
@@ -125,7 +125,7 @@ def initialize_high_prop_location(blobness_values, init_blob_threshold, img_shap
     Rb = np.ascontiguousarray(blobness_values)
     eng = get_engine(*Rb.shape)
     tdt = torch.float32 if Rb.dtype == np.float32 else torch.float64
-    pos = eng.seed(eng.dev(Rb, tdt), cur_config['boundary_size']['x'], cur_config['boundary_size']['y'],
+    pos = eng.seed(eng.to_field(Rb, tdt), cur_config['boundary_size']['x'], cur_config['boundary_size']['y'],
                    init_blob_threshold)
     return pos.cpu().numpy().astype(np.int64)
 
@@ -153,7 +153,7 @@ def del_close_particles(particles, is_stable_particle_index, R_b, cur_config, th
     tdt = torch.float32 if Rb.dtype == np.float32 else torch.float64
     pos, st, deleted = eng.delete_close(_pts(eng, particles), _stable(eng, is_stable_particle_index,
                                                                       particles.shape[0]),
-                                        eng.dev(Rb, tdt), threshold_dist, _tie(cur_config, tie_mode))
+                                        eng.to_field(Rb, tdt), threshold_dist, _tie(cur_config, tie_mode))
     eng.raise_on_status()
     deleted = deleted.cpu().numpy().astype(bool)
     to_delete = {i: bool(d) for i, d in enumerate(deleted)}
@@ -245,7 +245,7 @@ def move_particles(particles, is_stable_particle_index, blobness_grad, force, cu
     eng = get_engine(g.shape[0], g.shape[1], n_particles=particles.shape[0])
     tdt = torch.float32 if g.dtype == np.float32 else torch.float64
     pos = _pts(eng, particles)
-    eng.move(pos, _stable(eng, is_stable_particle_index, particles.shape[0]), eng.dev(g, tdt),
+    eng.move(pos, _stable(eng, is_stable_particle_index, particles.shape[0]), eng.to_field(g, tdt),
              eng.dev(np.asarray(force, dtype=np.float64), torch.float64), cur_config['lambda_blob'],
              cur_config['lambda_dist'], cur_config['step_mode'])
     eng.raise_on_status()
@@ -326,7 +326,7 @@ def detection_metrics(particles, GT_particles, R_b, cur_config, is_stable_partic
     eng = get_engine(*Rb.shape, n_particles=particles.shape[0], n_gt=GT_particles.shape[0])
     tdt = torch.float32 if Rb.dtype == np.float32 else torch.float64
     rec, _, _ = eng.metrics(_pts(eng, particles), _stable(eng, is_stable_particle_index, particles.shape[0]),
-                            _pts(eng, GT_particles), eng.dev(Rb, tdt), cur_config['boundary_size']['x'],
+                            _pts(eng, GT_particles), eng.to_field(Rb, tdt), cur_config['boundary_size']['x'],
                             cur_config['boundary_size']['y'])
     eng.raise_on_status()
     return metrics_from_record(rec)
@@ -344,7 +344,7 @@ def classify_detections(particles, GT_particles, R_b, cur_config, metric='2'):
     pos = _pts(eng, particles)
     bx, by = cur_config['boundary_size']['x'], cur_config['boundary_size']['y']
     rec, p2g, g2p = eng.metrics(pos, _stable(eng, None, particles.shape[0]), _pts(eng, GT_particles),
-                                eng.dev(Rb, tdt), bx, by, want_dists=True)
+                                eng.to_field(Rb, tdt), bx, by, want_dists=True)
     gt_tp, p_fp = eng.classify(g2p, p2g, pos, bx, by, metric_2_dist_map[metric])
     eng.raise_on_status()
     gt_tp = gt_tp.cpu().numpy().astype(bool)

@@ -12,8 +12,12 @@
  *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
  *   - particles are (n,2) float64 rows [x, y] exactly like the reference's ndarray;
- *   - fields are row-major (H,W); the gradient field is (H,W,2) interleaved with
- *     [...,0] = d/drow and [...,1] = -d/dcol (reference utils.py:152-163);
+ *   - blobness / gradient fields (every d_Rb, d_grad, and the d_field of aoslo_grad_field) are row-major
+ *     (H,W) with a ROW PITCH of AOSLO_FIELD_PITCH(W) pixels -- W rounded up to a multiple of 4, so that
+ *     rows start 16-byte aligned (the blobness kernel's TMA stores); the pad pixels are never read; the
+ *     gradient field is (H,W,2) interleaved with [...,0] = d/drow and [...,1] = -d/dcol (reference
+ *     utils.py:152-163), pitch AOSLO_FIELD_PITCH(W) pixel pairs.  The gravity field of aoslo_gravity_field
+ *     / aoslo_add_particles is dense (H,W);
  *   - field element type is selected by `field_dtype`: AOSLO_F32 or AOSLO_F64;
  *   - device-side conditions (particle left the padded image, NaN position, capacity
  *     overflow, eigenvalue assert, too few points for kNN) are accumulated in the
@@ -56,6 +60,7 @@ enum { AOSLO_TIE_CANONICAL = 0, AOSLO_TIE_SKLEARN = 1 };           /* kNN tie or
 #define AOSLO_KMAX 8            /* max neighbours per query incl. self (dist_n_neighbours <= 7) */
 #define AOSLO_MAX_SCALES 8
 #define AOSLO_MAX_RADIUS 16
+#define AOSLO_FIELD_PITCH(W) (((W) + 3) & ~3)   /* row pitch of R_b / gradient fields, in pixels */
 
 typedef struct aoslo_ctx aoslo_ctx;
 

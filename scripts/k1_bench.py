@@ -35,8 +35,8 @@ def main():
     d_img = eng.upload_image(pimg)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
     flush2 = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device='cuda')
-    Rb64 = eng.empty((H, W), torch.float64)
-    g64 = eng.empty((H, W, 2), torch.float64)
+    Rb64 = eng.field(H, W, torch.float64)
+    g64 = eng.field(H, W, torch.float64, 2)
     os.environ["AOSLO_BLOBNESS_KERNEL"] = "band"
     eng.blobness(d_img, 'custom', 'np_grad', (1.0,), torch.float64, out=(Rb64, g64))
     torch.cuda.synchronize()
@@ -60,8 +60,8 @@ def main():
             os.environ["AOSLO_PAIR_TH"] = var.split(":")[1]
             if len(var.split(":")) > 2:
                 os.environ["AOSLO_PAIR_OCC"] = var.split(":")[2]
-        Rb = eng.empty((H, W), dt)
-        g = eng.empty((H, W, 2), dt)
+        Rb = eng.field(H, W, dt)
+        g = eng.field(H, W, dt, 2)
         Rb.fill_(float('nan'))
         g.fill_(float('nan'))
         ms = []
@@ -87,8 +87,8 @@ def main():
         if dt not in main._bufs:
             main._bufs.clear()
             main._bufs[dt] = ([eng.upload_image(pimg) for _ in range(NB)],
-                              [eng.empty((H, W), dt) for _ in range(NB)],
-                              [eng.empty((H, W, 2), dt) for _ in range(NB)])
+                              [eng.field(H, W, dt) for _ in range(NB)],
+                              [eng.field(H, W, dt, 2) for _ in range(NB)])
         imgs, rbs, gs = main._bufs[dt]
         stream_us = []
         for it in range(3):

@@ -15,7 +15,7 @@ d_img = eng.upload_image(pimg)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=eng.device)
 out = {}
 for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
-    Rb = eng.empty((H, W), dt); g = eng.empty((H, W, 2), dt)
+    Rb = eng.field(H, W, dt); g = eng.field(H, W, dt, 2)
     ms = []
     for i in range(13):
         flush.fill_(1); torch.cuda._sleep(300000)

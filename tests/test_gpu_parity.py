@@ -494,10 +494,10 @@ def test_iterate_matches_oracle_incl_coincidence_fallback(zoo_field, tie_mode):
     pB = np.vstack([first, stable_part, last])
     stB = [0] * 20 + [1] * 3000 + [0] * 20
     eng = get_engine(*img.shape, n_gt=gt.shape[0])
-    d_Rb = eng.dev(Rb, torch.float64)
+    d_Rb = eng.to_field(Rb, torch.float64)
     for p, st, c, g in ((pA, stA, cfg, grad), (pB, stB, cfgB, gradB)):
         cs = make_config_struct(c, *img.shape)
-        d_grad = eng.dev(g, torch.float64)
+        d_grad = eng.to_field(g, torch.float64)
         ref_p, ref_del, ref_st = _iterate_oracle(p, st, Rb, g, c, tie_mode)
         if p is pB and tie_mode == 'canonical':
             assert ref_del[20:3020].sum() >= 20          # the coincident stable partners were deleted
