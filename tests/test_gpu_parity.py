@@ -102,6 +102,25 @@ def test_blobness_f32_pair_kernel_shapes_and_tilings(shape, variant, monkeypatch
     assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
 
 
+@pytest.mark.parametrize("shape", [(8, 8), (97, 229), (51, 120), (233, 341), (600, 700)])
+@pytest.mark.parametrize("tma", ["0", "2"])
+@pytest.mark.parametrize("th", ["24", "36"])
+def test_blobness_f32_pair_kernel_staging_and_store_variants(shape, tma, th, monkeypatch):
+    """AOSLO_K1_TMA = 0 (cp.async staging, plain stores) and 2 (TMA tensor loads AND stores, clipped at the image
+    border); the default (TMA loads, plain stores) is what every other f32 test runs."""
+    monkeypatch.setenv("AOSLO_K1_TMA", tma)
+    monkeypatch.setenv("AOSLO_PAIR_TH", th)
+    rng = np.random.default_rng(shape[0] * 31 + shape[1])
+    img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
+    gref = orc.calc_grad_field(ref, 'np_grad')
+    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                    dtype=np.float32, return_grad=True)
+    assert np.isfinite(rb).all() and np.isfinite(g).all()
+    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+
+
 @pytest.mark.parametrize("shape", [(8, 8), (9, 130), (130, 9), (97, 229), (49, 118), (51, 120), (233, 341), (600, 700)])
 @pytest.mark.parametrize("th", ["16", "24", "32", "48", "band"])
 def test_blobness_f64_tile_kernel_shapes_and_tilings(shape, th, monkeypatch):
