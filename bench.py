@@ -80,9 +80,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None):
+        """t_begin: start of the timed region (perf_counter).  The sampler is started before the warm-up (nvidia-smi
+        needs ~0.5 s to come up and the timed region of a multi-GPU run is a few tens of ms); samples taken inside the
+        timed region are used when there are any, otherwise the ones of warm-up + timed region (same load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -93,7 +96,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for t, ln in self.lines if t_begin is not None and t >= t_begin - 0.05]
+        window = "timed region" if inside else "warm-up + timed region"
+        for ln in (inside or [ln for _, ln in self.lines]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -106,7 +111,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def k1_dram_traffic(key):
@@ -332,11 +337,12 @@ def run_gpu(args):
         return e0.elapsed_time(e1)
 
     # ---- warm-up (all lanes), then the throughput pass: K steps of B concurrent runs
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         timed_step(lambda ln: ln.run_resident(), lanes)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    t_timed = time.perf_counter()
     launches0 = _lib.lib.aoslo_launch_count()
     step_ms = [timed_step(lambda ln: ln.run_resident(), lanes) for _ in range(args.steps)]
     # the sweep's only exchange: all-gather of the per-run metric records (tiny, latency only)
@@ -357,7 +363,7 @@ def run_gpu(args):
     g1.record()
     barrier()
     launches = _lib.lib.aoslo_launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_timed)
     total_ms = float(sum(step_ms)) + g0.elapsed_time(g1)
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
