@@ -73,6 +73,7 @@ SYMBOLS = {
     "aoslo_ctx_status": (_i, [_vp, _vp, _ip, _i]),
     "aoslo_ctx_capacity": (_i, [_vp]),
     "aoslo_ctx_set_blocking_sync": (_i, [_vp, _i]),
+    "aoslo_ctx_set_tuning": (_i, [_vp, C.c_char_p, _i]),
     "aoslo_prepare_inputs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _ip]),
     "aoslo_blobness": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_d), _ip, C.POINTER(_d), _i, _i, _i, _i, _vp, _vp]),
     "aoslo_grad_field": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -91,6 +92,7 @@ SYMBOLS = {
     "aoslo_iterate": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _ip]),
     "aoslo_run": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _i, C.POINTER(MetricsRecord), _i, _vp, _vp,
                        C.POINTER(RunSummary), C.POINTER(C.c_float)]),
+    "aoslo_read_particles": (_i, [_vp, _vp, _vp, _vp, _i]),
     "aoslo_kdtree_build_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i]),
     "aoslo_kdtree_num_nodes": (_i, [_i]),
 }

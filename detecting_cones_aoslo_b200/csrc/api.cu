@@ -14,7 +14,6 @@ namespace aoslo {
 static thread_local char g_last_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int set_cuda_error(cudaError_t e, const char* where) {
@@ -22,33 +21,6 @@ int set_cuda_error(cudaError_t e, const char* where) {
     cudaGetLastError();
     return AOSLO_ERR_CUDA;
 }
-
-// stage drivers defined in particles.cu (trailing d_n: optional device-resident particle count)
-int stage_knn(aoslo_ctx*, cudaStream_t, const double*, int, const double*, int, int, int, int32_t*, double*, bool,
-              const int* d_n);
-int stage_delete(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, const void*, int, int, int, double, int,
-                 double*, uint8_t*, uint8_t*, int*, int*, const int* d_n, int mode);
-int stage_force_move(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, int, int, double, double, double,
-                     const void*, int, int, int, double, double, int, double*, const int* d_n, bool links_ready);
-int stage_seed(aoslo_ctx*, cudaStream_t, const void*, int, int, int, int, int, double, double*, int, int*);
-int stage_lut(aoslo_ctx*, cudaStream_t, int, double, double, double, double*);
-int stage_gravity(aoslo_ctx*, cudaStream_t, const double*, int, int, int, double*, bool packed_ready);
-int stage_add(aoslo_ctx*, cudaStream_t, const double*, int, int, int, int, int, double, double*, uint8_t*, int,
-              const int*, int, int*);
-int stage_force(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, int, int, double, double, double, int,
-                double*, const int* d_n);
-int stage_move(aoslo_ctx*, cudaStream_t, double*, const uint8_t*, int, const void*, int, int, int, const double*,
-               double, double, int, const int* d_n);
-int stage_metrics(aoslo_ctx*, cudaStream_t, const double*, const uint8_t*, int, const double*, int, bool, bool,
-                  const void*, int, int, int, int, int, int, aoslo_metrics_record*, double*, double*, const int* d_n);
-int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t*, int, uint8_t, const int* d_n);
-int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int*, const int* d_n);
-int coop_blocks_for_delete(int num_sms);
-int stage_classify(aoslo_ctx*, cudaStream_t, const double*, int, const double*, const double*, int, int, int, int, int,
-                   double, uint8_t*, uint8_t*);
-int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t*, int, int, int, int, int, int, int, int, int, uint8_t*, int,
-                  const double*, int, double*, int*);
-int sqrt_inplace(cudaStream_t, double*, size_t);
 
 template <typename T>
 static int dmalloc(T** p, size_t count) {
@@ -205,6 +177,22 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         A(alloc_links(c->lk_p, H, W, cap, lshift));
     }
     A(dmalloc(&c->d_pos_tmp, (size_t)cap * 2));
+    A(dmalloc(&c->d_stable_tmp, cap));
+    A(dmalloc(&c->d_link_geom, 4));
+    A(dmalloc(&c->d_ctl, 1));
+    A(dmalloc(&c->d_params, 1));
+    if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_ctl, sizeof(RunCtl), cudaHostAllocDefault) != cudaSuccess)
+        st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_params, sizeof(RunParams), cudaHostAllocDefault) != cudaSuccess)
+        st = AOSLO_ERR_CUDA;
+    // environment knobs are read once here, never on the launch path
+    c->no_graph = getenv("AOSLO_NO_GRAPH") ? 1 : 0;
+    if (const char* e = getenv("AOSLO_K1_TMA")) c->tune.k1_tma = atoi(e);
+    if (const char* e = getenv("AOSLO_PAIR_TH")) c->tune.pair_th = atoi(e);
+    if (const char* e = getenv("AOSLO_PAIR_OCC")) c->tune.pair_occ = atoi(e);
+    if (const char* e = getenv("AOSLO_DTILE_TH")) c->tune.dtile_th = atoi(e);
+    if (const char* e = getenv("AOSLO_BLOBNESS_KERNEL"))
+        c->tune.k1_kernel = !strcmp(e, "tile") ? 1 : !strcmp(e, "band") ? 2 : !strcmp(e, "dtile") ? 3 : 0;
     A(dmalloc(&c->d_epoch, 1));
     A(dmalloc(&c->d_active, cap));
     A(dmalloc(&c->d_active_b, cap));
@@ -240,6 +228,8 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     if (st == AOSLO_OK && cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaStreamCreateWithFlags(&c->cap_stream2, cudaStreamNonBlocking) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaStreamCreateWithFlags(&c->cap_stream3, cudaStreamNonBlocking) != cudaSuccess) st = AOSLO_ERR_CUDA;
 #undef A
     if (st == AOSLO_OK && cudaMemset(c->d_status, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
@@ -265,8 +255,15 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (RunGraph& g : c->graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        if (g.graph) cudaGraphDestroy(g.graph);
+    }
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
+    if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
+    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_ctl); cudaFree(c->d_params);
+    cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
     cudaGetLastError();
     delete c;
@@ -274,6 +271,18 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
 }
 
 extern "C" int aoslo_ctx_capacity(aoslo_ctx* ctx) { return ctx ? ctx->cap : 0; }
+
+extern "C" int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return AOSLO_ERR_INVALID;
+    if (!strcmp(key, "k1_tma")) ctx->tune.k1_tma = value;
+    else if (!strcmp(key, "pair_th")) ctx->tune.pair_th = value;
+    else if (!strcmp(key, "pair_occ")) ctx->tune.pair_occ = value;
+    else if (!strcmp(key, "dtile_th")) ctx->tune.dtile_th = value;
+    else if (!strcmp(key, "k1_kernel")) ctx->tune.k1_kernel = value;
+    else if (!strcmp(key, "no_graph")) ctx->no_graph = value ? 1 : 0;
+    else return AOSLO_ERR_INVALID;
+    return AOSLO_OK;
+}
 
 extern "C" int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable) {
     if (!ctx) return AOSLO_ERR_INVALID;
@@ -423,6 +432,9 @@ extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* c
     const double e2 = pit ? cfg->lambda_dist_func : 0.0;
     const double* moved;
     int mode;
+    AOSLO_TRY(epoch_guard(ctx, s, 2u));              // the 20-bit touch epoch must not wrap (one resolve per call)
+    // a call that failed between the force step and the deletion must not leak its non-stable list
+    AOSLO_CUDA(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(int) * 4, s));
     if (cfg->tie_mode == AOSLO_TIE_CANONICAL) {
         AOSLO_TRY(stage_force_move(ctx, s, d_particles, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2, d_grad,
                                    field_dtype, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode,
@@ -447,27 +459,571 @@ extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* c
 // ---------------------------------------------------------------------------------------
 // whole run
 // ---------------------------------------------------------------------------------------
-// Control flow = reference pipeline_with_delitions.py:101-382.  The particle count lives in a
-// device scalar (double-buffered with the particle arrays); in the canonical tie mode the
-// host only synchronises where it needs a decision: the thinning fixpoint test, after every
-// resample (to refresh its upper bound of the count), for the early-stop test when that is
-// enabled, and once at the end for the records.  The sklearn-order tie mode needs the count
-// on the host for every kNN (host tree build) and synchronises per stage.
-extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
-                         int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records,
-                         int max_records, double* d_particles_out, uint8_t* d_stable_out,
-                         aoslo_run_summary* h_summary, float* h_stage_ms) {
-    if (!ctx || !cfg || !d_Rb || !d_grad || !d_gt || !h_summary) return AOSLO_ERR_INVALID;
-    if (cfg->H != ctx->H || cfg->W != ctx->W || n_gt < 1 || n_gt > ctx->gt_cap) return AOSLO_ERR_INVALID;
-    if (cfg->dist_n_neighbours < 1 || cfg->dist_n_neighbours + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
-    if (cfg->particle_call_window < 1 || cfg->reception_field_size < 1 || cfg->reception_field_size > 64)
-        return AOSLO_ERR_UNSUPPORTED;
-    if (cfg->fix_particles_frequency < 1 || cfg->metric_measure_freq < 1) return AOSLO_ERR_INVALID;
-    if (max_records > ctx->max_records) max_records = ctx->max_records;
-    cudaStream_t s = (cudaStream_t)stream;
+// Control flow = reference pipeline_with_delitions.py:101-382.
+//
+// Canonical tie order (run_canonical): the WHOLE run -- seeds, thinning to the fixpoint, LUT / gravity /
+// adding, the epoch loop, the final reads -- is ONE CUDA graph with no host decision inside.  The
+// particles always live in buffer 0 (the compaction of a step reads the moved copies); the count is a
+// device scalar; every decision the reference takes in Python is taken by a one-thread kernel:
+//   * thinning `while deleted: del_close_particles(thr=3)` (:115-120)  -> WHILE conditional graph node;
+//   * the epoch loop -> unrolled kernel nodes when the early stop is off; with the early stop (:381-382) a
+//     WHILE node whose body carries IF nodes for the resample (:256) and metrics (:320) branches;
+//   * all value parameters (thresholds, lambdas, energy parameters, frequencies, GT count) are read from a
+//     device-resident RunParams block, so one cached graph serves every configuration of a sweep -- only
+//     structural parameters (shapes, neighbour-count class, loop layout, buffer addresses) are baked in.
+// The host synchronises exactly once, at the end, to read the summary / records / status.
+//
+// sklearn tie order (run_sklearn): every kNN needs the host-built tree of the current points, so the run
+// stays a sequence of stage calls with the count on the host.
+namespace aoslo {
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void ctl_stamp(RunCtl* ctl, int bucket) {
+    const unsigned long long t = global_ns();
+    if (bucket >= 0) ctl->acc_ns[bucket] += t - ctl->t_last;
+    ctl->t_last = t;
+}
+
+__global__ void run_begin_kernel(RunCtl* ctl, int* status, int* counters) {
+    if (threadIdx.x != 0) return;
+    RunCtl z = {};
+    *ctl = z;
+    *status = 0;
+    counters[12] = 0; counters[13] = 0; counters[14] = 0; counters[15] = 0;
+    counters[4] = 0; counters[5] = 0;
+}
+
+__global__ void after_seed_kernel(RunCtl* ctl, const int* cnt, cudaGraphConditionalHandle h_thin, int use_handle) {
+    if (threadIdx.x != 0) return;
+    const int n = *cnt;
+    ctl->n_seeds = n;
+    ctl->n_after_thinning = n;
+    ctl->thin_cond = n >= 2 ? 1 : 0;
+    if (use_handle) cudaGraphSetConditional(h_thin, (unsigned)ctl->thin_cond);
+}
+
+// end of one thinning round: the survivors (buffer 1) become buffer 0; another round follows iff something
+// was deleted (reference :116-120)
+__global__ void __launch_bounds__(kThreads) thin_swap_kernel(const double2* __restrict__ pos1,
+                                                             const uint8_t* __restrict__ st1, const int* cnt1,
+                                                             double2* __restrict__ pos0, uint8_t* __restrict__ st0,
+                                                             int* cnt0, RunCtl* ctl, cudaGraphConditionalHandle h_thin,
+                                                             int use_handle) {
+    const int n1 = *cnt1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1; i += gridDim.x * blockDim.x) {
+        pos0[i] = pos1[i];
+        st0[i] = st1[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int n0 = *cnt0;            // no other thread of this kernel reads cnt0
+        *cnt0 = n1;
+        ctl->thin_rounds += 1;
+        ctl->n_after_thinning = n1;
+        ctl->thin_cond = (n1 != n0 && n1 >= 2) ? 1 : 0;
+        if (use_handle) cudaGraphSetConditional(h_thin, (unsigned)ctl->thin_cond);
+    }
+}
+
+__global__ void loop_begin_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, int* status,
+                                  cudaGraphConditionalHandle h_loop, int use_handle, int stamp) {
+    if (threadIdx.x != 0) return;
+    const int n = *cnt;
+    int go = rp->epoch_num > 0 ? 1 : 0;
+    if (n < rp->kk || n < 2) { atomicOr(status, AOSLO_DEV_KNN_SHORT); go = 0; }   // sklearn: n_neighbors > n_samples
+    ctl->it = 0;
+    ctl->loop_cond = go;
+    if (use_handle) cudaGraphSetConditional(h_loop, (unsigned)go);
+    if (stamp) ctl_stamp(ctl, -1);
+}
+
+// after the deletion of an iteration: the survivors' count becomes the current count, and the two branch
+// conditions of this iteration are fixed (resample :256, metrics :320)
+__global__ void iter_mid_kernel(RunCtl* ctl, const RunParams* rp, int* cnt0, const int* cnt1,
+                                cudaGraphConditionalHandle h_res, cudaGraphConditionalHandle h_met, int use_res,
+                                int use_met, int stamp) {
+    if (threadIdx.x != 0) return;
+    *cnt0 = *cnt1;
+    const int it = ctl->it;
+    const int do_res = (it % rp->fix_freq == 3) ? 1 : 0;
+    const int do_met = (it % rp->metric_freq == 0 && ctl->n_rec < rp->max_records) ? 1 : 0;
+    ctl->do_resample = do_res;
+    ctl->do_metrics = do_met;
+    if (use_res) cudaGraphSetConditional(h_res, (unsigned)do_res);
+    if (use_met) cudaGraphSetConditional(h_met, (unsigned)do_met);
+    if (stamp) ctl_stamp(ctl, 2);
+}
+
+__global__ void iter_end_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, int* status,
+                                cudaGraphConditionalHandle h_loop, int use_handle, int stamp) {
+    if (threadIdx.x != 0) return;
+    const int it = ctl->it + 1;
+    ctl->it = it;
+    const int n = *cnt;
+    int go = it < rp->epoch_num ? 1 : 0;
+    // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
+    if (rp->early_stop && (double)ctl->n_stable / (double)n > 0.997) go = 0;
+    if (go && (n < rp->kk || n < 2)) { atomicOr(status, AOSLO_DEV_KNN_SHORT); go = 0; }
+    ctl->loop_cond = go;
+    if (use_handle) cudaGraphSetConditional(h_loop, (unsigned)go);
+    if (stamp) ctl_stamp(ctl, 4);
+}
+
+__global__ void stamp_kernel(RunCtl* ctl, int bucket) {
+    if (threadIdx.x == 0) ctl_stamp(ctl, bucket);
+}
+
+__global__ void run_end_kernel(RunCtl* ctl, const int* cnt) {
+    if (threadIdx.x == 0) ctl->n_final = *cnt;
+}
+
+static thread_local int* tl_capture_counter = nullptr;   // kernel launches recorded into a graph body
+
+}  // namespace aoslo
+
+void aoslo::count_launch() {
+    if (tl_capture_counter) ++*tl_capture_counter;
+    else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+namespace {
+
+struct CondNode {
+    cudaGraphConditionalHandle handle = 0;
+    cudaGraph_t body = nullptr;
+};
+
+// WHILE / IF node after everything captured so far on `q`; the capture continues after the node.  The handle is
+// created by the caller BEFORE the kernel that sets it is recorded.
+int add_cond_node(cudaStream_t q, cudaGraphConditionalNodeType type, CondNode* node) {
+    cudaStreamCaptureStatus cs;
+    cudaGraph_t g = nullptr;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    AOSLO_CUDA(cudaStreamGetCaptureInfo(q, &cs, nullptr, &g, &deps, &ndeps));
+    if (cs != cudaStreamCaptureStatusActive) return AOSLO_ERR_INVALID;
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = node->handle;
+    p.conditional.type = type;
+    p.conditional.size = 1;
+    cudaGraphNode_t gn;
+    AOSLO_CUDA(cudaGraphAddNode(&gn, g, deps, ndeps, &p));
+    AOSLO_CUDA(cudaStreamUpdateCaptureDependencies(q, &gn, 1, cudaStreamSetCaptureDependencies));
+    node->body = p.conditional.phGraph_out[0];
+    return AOSLO_OK;
+}
+
+int new_cond_handle(cudaStream_t q, cudaGraphConditionalHandle* h) {
+    cudaStreamCaptureStatus cs;
+    cudaGraph_t g = nullptr;
+    AOSLO_CUDA(cudaStreamGetCaptureInfo(q, &cs, nullptr, &g, nullptr, nullptr));
+    if (cs != cudaStreamCaptureStatusActive) return AOSLO_ERR_INVALID;
+    AOSLO_CUDA(cudaGraphConditionalHandleCreate(h, g, 0, cudaGraphCondAssignDefault));
+    return AOSLO_OK;
+}
+
+struct RunKey {                      // everything baked into the nodes of a cached run graph
+    int H, W, bx, by, fdt, k_class, energy, step_mode, rfs, window;
+    int dynamic_loop, timing, epoch_num, fix_freq, metric_freq, max_rec, hint, has_records;
+    const void *Rb, *grad, *gt, *records;
+};
+
+struct RunPlan {
+    aoslo_ctx* ctx;
+    const aoslo_config* cfg;
+    const void* d_Rb;
+    const void* d_grad;
+    int fdt;
+    const double* d_gt;
+    int n_gt;
+    bool want_records;
+    int max_records;
+    bool timing;
+    bool dynamic_loop;               // WHILE / IF nodes (early stop) instead of the unrolled loop
+    int inner;                       // inner pixels: upper bound of the seed count
+    int hint;                        // launch-size hint of the in-loop compaction
+    int* cnt0;
+    int* cnt1;
+    // kernel launches per body, counted while capturing (gpu_launches bookkeeping)
+    int k_static = 0, k_thin = 0, k_iter = 0, k_res = 0, k_met = 0;
+};
+
+int enqueue_thin_round(RunPlan& P, cudaStream_t q, cudaGraphConditionalHandle h, int use_handle) {
+    aoslo_ctx* c = P.ctx;
+    const aoslo_config* cfg = P.cfg;
+    AOSLO_TRY(stage_delete(c, q, c->d_pos[0], c->d_stable[0], P.inner, P.d_Rb, P.fdt, cfg->H, cfg->W,
+                           cfg->thinning_threshold, AOSLO_TIE_CANONICAL, c->d_pos[1], c->d_stable[1], nullptr, P.cnt1,
+                           nullptr, P.cnt0, 0, &c->d_params->thin_thr, 0));
+    thin_swap_kernel<<<c->nb, kThreads, 0, q>>>((const double2*)c->d_pos[1], c->d_stable[1], P.cnt1,
+                                                (double2*)c->d_pos[0], c->d_stable[0], P.cnt0, c->d_ctl, h, use_handle);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int enqueue_resample(RunPlan& P, cudaStream_t q, const int* dn, int* dn_out, bool packed_ready) {
+    aoslo_ctx* c = P.ctx;
+    const aoslo_config* cfg = P.cfg;
+    const int bound = c->cap;
+    AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], bound, 1, dn));
+    AOSLO_TRY(build_cell_list(c, q, c->cl_p, c->d_pos[0], bound, dn));
+    AOSLO_TRY(stage_gravity(c, q, c->d_lut, cfg->reception_field_size, cfg->H, cfg->W, c->d_field, packed_ready));
+    // the spine kernel reads the base count before it writes the total, so both may be the same scalar
+    AOSLO_TRY(stage_add(c, q, c->d_field, cfg->H, cfg->W, cfg->bx, cfg->by, cfg->particle_call_window,
+                        cfg->particle_call_threshold, c->d_pos[0], c->d_stable[0], bound, dn, c->cap, dn_out,
+                        &c->d_params->add_thr, true));
+    return AOSLO_OK;
+}
+
+int enqueue_metrics(RunPlan& P, cudaStream_t q, const int* dn) {
+    aoslo_ctx* c = P.ctx;
+    const aoslo_config* cfg = P.cfg;
+    return stage_metrics(c, q, c->d_pos[0], c->d_stable[0], c->cap, P.d_gt, P.n_gt, true, false, P.d_Rb, P.fdt, cfg->H,
+                         cfg->W, cfg->bx, cfg->by, 0, c->d_records, c->d_dist_p2g, c->d_dist_g2p, dn,
+                         &c->d_params->n_gt, &c->d_ctl->n_rec, &c->d_ctl->it);
+}
+
+// force + move + deletion of one iteration (:185-253): particles in buffer 0 with count *dn; survivors back in
+// buffer 0 with count *dn_out
+int enqueue_step(RunPlan& P, cudaStream_t q, const int* dn, int* dn_out, bool links_ready) {
+    aoslo_ctx* c = P.ctx;
+    const aoslo_config* cfg = P.cfg;
+    const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
+    const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+    const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+    const double e2 = pit ? cfg->lambda_dist_func : 0.0;
+    AOSLO_TRY(stage_force_move(c, q, c->d_pos[0], c->d_stable[0], c->cap, cfg->dist_n_neighbours, cfg->dist_energy_type,
+                               e0, e1, e2, P.d_grad, P.fdt, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist,
+                               cfg->step_mode, c->d_pos_tmp, dn, links_ready, c->d_stable_tmp, c->d_params));
+    if (P.timing) {
+        stamp_kernel<<<1, 32, 0, q>>>(c->d_ctl, 0);       // force and move are one kernel: the move bucket stays 0
+        AOSLO_LAUNCH_CHECK();
+    }
+    AOSLO_TRY(stage_delete(c, q, c->d_pos_tmp, c->d_stable_tmp, c->cap, P.d_Rb, P.fdt, cfg->H, cfg->W,
+                           cfg->threshhold_dist_del, AOSLO_TIE_CANONICAL, c->d_pos[0], c->d_stable[0], nullptr, dn_out,
+                           nullptr, dn, 2, &c->d_params->del_thr, P.hint));
+    return AOSLO_OK;
+}
+
+// captures `fn` into the body graph of a conditional node; launches are counted into *counter
+template <class F>
+int capture_body(cudaStream_t q, cudaGraph_t body, int* counter, F fn) {
+    AOSLO_CUDA(cudaStreamBeginCaptureToGraph(q, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int* saved = tl_capture_counter;
+    tl_capture_counter = counter;
+    int st = fn();
+    tl_capture_counter = saved;
+    cudaError_t ce = cudaStreamEndCapture(q, nullptr);
+    if (st != AOSLO_OK) return st;
+    if (ce != cudaSuccess) return set_cuda_error(ce, "cudaStreamEndCapture(body)");
+    return AOSLO_OK;
+}
+
+// Enqueues the whole run on `q`.  graph = true: `q` is capturing and the loops become conditional nodes;
+// graph = false (AOSLO_NO_GRAPH debug path): the same kernels run eagerly and the host evaluates the loop
+// conditions from the control block (one synchronisation per decision).
+int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
+    aoslo_ctx* c = P.ctx;
+    const aoslo_config* cfg = P.cfg;
+    const int H = cfg->H, W = cfg->W;
+    RunCtl* ctl = c->d_ctl;
+    const RunParams* rp = c->d_params;
+    auto read_ctl = [&]() -> int {
+        AOSLO_CUDA(cudaMemcpyAsync(c->h_ctl, ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, q));
+        return stream_wait(c, q);
+    };
+    run_begin_kernel<<<1, 32, 0, q>>>(ctl, c->d_status, c->d_counters);
+    AOSLO_LAUNCH_CHECK();
+    // ---- seeds (:101), flags (:113)
+    AOSLO_TRY(stage_seed(c, q, P.d_Rb, P.fdt, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold, c->d_pos[0], c->cap,
+                         P.cnt0, &rp->seed_thr, true));
+    AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], P.inner, 0, P.cnt0));
+    // ---- thinning to the fixpoint (:115-120)
+    if (graph) {
+        CondNode thin;
+        AOSLO_TRY(new_cond_handle(q, &thin.handle));
+        after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, thin.handle, 1);
+        AOSLO_LAUNCH_CHECK();
+        AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &thin));
+        AOSLO_TRY(capture_body(c->cap_stream2, thin.body, &P.k_thin,
+                               [&]() { return enqueue_thin_round(P, c->cap_stream2, thin.handle, 1); }));
+    } else {
+        after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, 0, 0);
+        AOSLO_LAUNCH_CHECK();
+        for (;;) {
+            AOSLO_TRY(read_ctl());
+            if (!c->h_ctl->thin_cond) break;
+            AOSLO_TRY(enqueue_thin_round(P, q, 0, 0));
+        }
+    }
+    // ---- all stable, LUT, gravity field, adding (:130-152); GT cell list once per run
+    AOSLO_TRY(stage_lut(c, q, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
+                        cfg->lambda_dist_func, c->d_lut, rp));
+    AOSLO_TRY(enqueue_resample(P, q, P.cnt0, P.cnt0, false));
+    AOSLO_TRY(build_cell_list(c, q, c->cl_g, P.d_gt, P.n_gt, &rp->n_gt));
+    // ---- the epoch loop (:173-382)
+    if (!P.dynamic_loop && graph) {
+        // unrolled: the branches are static, the count alternates between two scalars, no control kernels
+        if (P.timing) {
+            stamp_kernel<<<1, 32, 0, q>>>(ctl, -1);
+            AOSLO_LAUNCH_CHECK();
+        }
+        int* cn[2] = {P.cnt0, P.cnt1};
+        int p = 0, n_rec = 0;
+        bool links_valid = false;
+        for (int it = 0; it < cfg->epoch_num; ++it) {
+            AOSLO_TRY(enqueue_step(P, q, cn[p], cn[p ^ 1], links_valid));
+            links_valid = false;
+            p ^= 1;
+            if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 2); AOSLO_LAUNCH_CHECK(); }
+            if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(enqueue_resample(P, q, cn[p], cn[p], true));
+            if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
+            if (it % cfg->metric_measure_freq == 0 && P.want_records && n_rec < P.max_records) {
+                // record slot / iteration number are static here
+                AOSLO_TRY(stage_metrics(c, q, c->d_pos[0], c->d_stable[0], c->cap, P.d_gt, P.n_gt, true, false, P.d_Rb,
+                                        P.fdt, H, W, cfg->bx, cfg->by, it, c->d_records + n_rec, c->d_dist_p2g,
+                                        c->d_dist_g2p, cn[p], &rp->n_gt, nullptr, nullptr));
+                links_valid = true;              // the metrics pass left links of buffer 0 behind
+                ++n_rec;
+            }
+            if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 4); AOSLO_LAUNCH_CHECK(); }
+        }
+        if (p != 0) AOSLO_CUDA(cudaMemcpyAsync(P.cnt0, P.cnt1, sizeof(int), cudaMemcpyDeviceToDevice, q));
+    } else {
+        auto step_and_mid = [&](cudaStream_t b, cudaGraphConditionalHandle h_res, cudaGraphConditionalHandle h_met,
+                                int use_res, int use_met) -> int {
+            AOSLO_TRY(enqueue_step(P, b, P.cnt0, P.cnt1, false));
+            iter_mid_kernel<<<1, 32, 0, b>>>(ctl, rp, P.cnt0, P.cnt1, h_res, h_met, use_res, use_met,
+                                             P.timing ? 1 : 0);
+            AOSLO_LAUNCH_CHECK();
+            return AOSLO_OK;
+        };
+        auto iter_tail = [&](cudaStream_t b, cudaGraphConditionalHandle h_loop, int use) -> int {
+            if (cfg->early_stop) AOSLO_TRY(stage_count_stable(c, b, c->d_stable[0], c->cap, &ctl->n_stable, P.cnt0));
+            iter_end_kernel<<<1, 32, 0, b>>>(ctl, rp, P.cnt0, c->d_status, h_loop, use, P.timing ? 1 : 0);
+            AOSLO_LAUNCH_CHECK();
+            return AOSLO_OK;
+        };
+        if (graph) {
+            CondNode loop;
+            AOSLO_TRY(new_cond_handle(q, &loop.handle));
+            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, c->d_status, loop.handle, 1, P.timing ? 1 : 0);
+            AOSLO_LAUNCH_CHECK();
+            AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &loop));
+            cudaStream_t b = c->cap_stream2;
+            AOSLO_TRY(capture_body(b, loop.body, &P.k_iter, [&]() -> int {
+                // the IF handles belong to the body graph and are set by iter_mid_kernel, upstream of both nodes
+                CondNode res, met;
+                AOSLO_TRY(new_cond_handle(b, &res.handle));
+                if (P.want_records) AOSLO_TRY(new_cond_handle(b, &met.handle));
+                AOSLO_TRY(step_and_mid(b, res.handle, met.handle, 1, P.want_records ? 1 : 0));
+                cudaStream_t b3 = c->cap_stream3;
+                AOSLO_TRY(add_cond_node(b, cudaGraphCondTypeIf, &res));
+                AOSLO_TRY(capture_body(b3, res.body, &P.k_res, [&]() -> int {
+                    AOSLO_TRY(enqueue_resample(P, b3, P.cnt0, P.cnt0, true));
+                    if (P.timing) { stamp_kernel<<<1, 32, 0, b3>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
+                    return AOSLO_OK;
+                }));
+                if (P.want_records) {
+                    AOSLO_TRY(add_cond_node(b, cudaGraphCondTypeIf, &met));
+                    AOSLO_TRY(capture_body(b3, met.body, &P.k_met, [&]() { return enqueue_metrics(P, b3, P.cnt0); }));
+                }
+                return iter_tail(b, loop.handle, 1);
+            }));
+        } else {
+            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, c->d_status, 0, 0, P.timing ? 1 : 0);
+            AOSLO_LAUNCH_CHECK();
+            for (;;) {
+                AOSLO_TRY(read_ctl());
+                if (!c->h_ctl->loop_cond) break;
+                AOSLO_TRY(step_and_mid(q, 0, 0, 0, 0));
+                AOSLO_TRY(read_ctl());
+                if (c->h_ctl->do_resample) {
+                    AOSLO_TRY(enqueue_resample(P, q, P.cnt0, P.cnt0, true));
+                    if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
+                }
+                if (c->h_ctl->do_metrics && P.want_records) AOSLO_TRY(enqueue_metrics(P, q, P.cnt0));
+                AOSLO_TRY(iter_tail(q, 0, 0));
+            }
+        }
+    }
+    // ---- final reads: stable count, control block, status, records -> pinned memory
+    AOSLO_TRY(stage_count_stable(c, q, c->d_stable[0], c->cap, &ctl->n_stable, P.cnt0));
+    run_end_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0);
+    AOSLO_LAUNCH_CHECK();
+    AOSLO_CUDA(cudaMemcpyAsync(c->h_ctl, ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, q));
+    AOSLO_CUDA(cudaMemcpyAsync(c->h_pinned + 2, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, q));
+    if (P.want_records)
+        AOSLO_CUDA(cudaMemcpyAsync(c->h_records, c->d_records, sizeof(aoslo_metrics_record) * P.max_records,
+                                   cudaMemcpyDeviceToHost, q));
+    return AOSLO_OK;
+}
+
+int k_class_of(int kk) { return kk <= 2 ? 2 : (kk <= 4 ? 4 : 8); }
+
+int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
+                  int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
+                  aoslo_run_summary* h_summary, float* h_stage_ms) {
+    const int H = cfg->H, W = cfg->W;
+    RunPlan P;
+    P.ctx = ctx; P.cfg = cfg; P.d_Rb = d_Rb; P.d_grad = d_grad; P.fdt = field_dtype; P.d_gt = d_gt; P.n_gt = n_gt;
+    P.want_records = h_records != nullptr && max_records > 0;
+    P.max_records = P.want_records ? max_records : 0;
+    P.timing = h_stage_ms != nullptr;
+    P.dynamic_loop = cfg->early_stop != 0 || ctx->no_graph;
+    P.inner = (H - 2 * cfg->by) * (W - 2 * cfg->bx);
+    if (P.inner < 1) return AOSLO_ERR_INVALID;
+    if (P.inner > ctx->cap) P.inner = ctx->cap;
+    if (ctx->loop_hint <= 0) {
+        int h = 1024;
+        while (h < P.inner / 16) h <<= 1;
+        ctx->loop_hint = h;
+    }
+    P.hint = ctx->loop_hint < ctx->cap ? ctx->loop_hint : ctx->cap;
+    P.cnt0 = ctx->d_counters + 4;
+    P.cnt1 = ctx->d_counters + 5;
+    // ---- value parameters -> device (stream ordered; the pinned staging copy is free again after the final sync)
+    {
+        const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
+        RunParams& r = *ctx->h_params;
+        memset(&r, 0, sizeof(r));
+        r.seed_thr = cfg->init_blob_threshold; r.thin_thr = cfg->thinning_threshold;
+        r.del_thr = cfg->threshhold_dist_del; r.add_thr = cfg->particle_call_threshold;
+        r.lut_mu = cfg->mu_dist_func; r.lut_sigma = cfg->sigma_dist_func; r.lut_lam = cfg->lambda_dist_func;
+        r.e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+        r.e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+        r.e2 = pit ? cfg->lambda_dist_func : 0.0;
+        r.lb = cfg->lambda_blob; r.ld = cfg->lambda_dist;
+        r.kk = cfg->dist_n_neighbours + 1;
+        r.fix_freq = cfg->fix_particles_frequency; r.metric_freq = cfg->metric_measure_freq;
+        r.epoch_num = cfg->epoch_num; r.early_stop = cfg->early_stop; r.max_records = P.max_records; r.n_gt = n_gt;
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(RunParams), cudaMemcpyHostToDevice, s));
+    }
+    AOSLO_TRY(epoch_guard(ctx, s, (unsigned)cfg->epoch_num + 1u));
+    ctx->epoch += (unsigned)cfg->epoch_num;          // upper estimate of the resolve calls of this run
+    if (ctx->no_graph) {
+        AOSLO_TRY(enqueue_run(P, s, false));
+    } else {
+        RunKey key;
+        memset(&key, 0, sizeof(key));
+        key.H = H; key.W = W; key.bx = cfg->bx; key.by = cfg->by; key.fdt = field_dtype;
+        key.k_class = k_class_of(cfg->dist_n_neighbours + 1); key.energy = cfg->dist_energy_type;
+        key.step_mode = cfg->step_mode; key.rfs = cfg->reception_field_size; key.window = cfg->particle_call_window;
+        key.dynamic_loop = P.dynamic_loop; key.timing = P.timing; key.hint = P.hint;
+        key.has_records = P.want_records;
+        if (!P.dynamic_loop) {
+            key.epoch_num = cfg->epoch_num; key.fix_freq = cfg->fix_particles_frequency;
+            key.metric_freq = cfg->metric_measure_freq; key.max_rec = P.max_records;
+        } else {
+            key.max_rec = P.max_records;             // size of the record read-back node
+        }
+        key.Rb = d_Rb; key.grad = d_grad; key.gt = d_gt; key.records = ctx->d_records;
+        RunGraph* hit = nullptr;
+        for (RunGraph& g : ctx->graphs)
+            if (g.exec && g.key.size() == sizeof(key) && memcmp(g.key.data(), &key, sizeof(key)) == 0) hit = &g;
+        if (!hit) {
+            const size_t kMaxGraphs = 8;
+            if (ctx->graphs.size() < kMaxGraphs) {
+                ctx->graphs.emplace_back();
+                hit = &ctx->graphs.back();
+            } else {
+                hit = &ctx->graphs[0];
+                for (RunGraph& g : ctx->graphs) if (g.stamp < hit->stamp) hit = &g;
+                if (hit->exec) cudaGraphExecDestroy(hit->exec);
+                if (hit->graph) cudaGraphDestroy(hit->graph);
+                *hit = RunGraph();
+            }
+            // record on the context's own streams (the caller's may be the legacy default stream, which cannot
+            // capture); nothing executes during capture
+            cudaStream_t q = ctx->cap_stream;
+            AOSLO_CUDA(cudaStreamBeginCapture(q, cudaStreamCaptureModeThreadLocal));
+            int* saved = tl_capture_counter;
+            tl_capture_counter = &P.k_static;
+            int st = enqueue_run(P, q, true);
+            tl_capture_counter = saved;
+            cudaGraph_t graph = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(q, &graph);
+            if (st != AOSLO_OK || ce != cudaSuccess) {
+                // a failed body capture may have left the helper streams capturing
+                cudaStreamEndCapture(ctx->cap_stream2, nullptr);
+                cudaStreamEndCapture(ctx->cap_stream3, nullptr);
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                hit->exec = nullptr;
+                if (st != AOSLO_OK) return st;
+                return set_cuda_error(ce, "cudaStreamEndCapture");
+            }
+            ce = cudaGraphInstantiate(&hit->exec, graph, 0);
+            if (ce != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                hit->exec = nullptr;
+                return set_cuda_error(ce, "cudaGraphInstantiate");
+            }
+            hit->graph = graph;                      // kept alive with its conditional handles
+            hit->key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
+            hit->static_kernels = P.k_static; hit->thin_kernels = P.k_thin; hit->iter_kernels = P.k_iter;
+            hit->resample_kernels = P.k_res; hit->metrics_kernels = P.k_met;
+        }
+        hit->stamp = ++ctx->graph_clock;
+        AOSLO_CUDA(cudaGraphLaunch(hit->exec, s));
+        P.k_static = hit->static_kernels; P.k_thin = hit->thin_kernels; P.k_iter = hit->iter_kernels;
+        P.k_res = hit->resample_kernels; P.k_met = hit->metrics_kernels;
+    }
+    // ---- the one synchronisation of the run
+    AOSLO_TRY(stream_wait(ctx, s));
+    const RunCtl& r = *ctx->h_ctl;
+    h_summary->status |= ctx->h_pinned[2];
+    h_summary->n_seeds = r.n_seeds;
+    h_summary->n_after_thinning = r.n_after_thinning;
+    h_summary->n_thinning_rounds = r.thin_rounds;
+    h_summary->n_stable = r.n_stable;
+    h_summary->n_particles = r.n_final;
+    int n_rec = 0, it_done = 0;
+    if (P.dynamic_loop) {
+        n_rec = r.n_rec;
+        it_done = r.it;
+    } else {
+        for (int it = 0; it < cfg->epoch_num; ++it)
+            if (it % cfg->metric_measure_freq == 0 && P.want_records && n_rec < P.max_records) ++n_rec;
+        it_done = cfg->epoch_num;
+    }
+    if (r.n_seeds < 2 || r.n_after_thinning < 2) h_summary->status |= AOSLO_DEV_KNN_SHORT;
+    h_summary->n_iterations = it_done;
+    h_summary->n_records = n_rec;
+    for (int i = 0; i < n_rec; ++i) h_records[i] = ctx->h_records[i];
+    if (h_stage_ms)
+        for (int i = 0; i < 5; ++i) h_stage_ms[i] = (float)((double)r.acc_ns[i] * 1e-6);
+    if (!ctx->no_graph) {
+        // kernels the graph executed: static nodes + the bodies as often as the control block says they ran
+        long long k = P.k_static + (long long)r.thin_rounds * P.k_thin;
+        if (P.dynamic_loop) {
+            int n_res = 0;
+            for (int it = 0; it < it_done; ++it) if (it % cfg->fix_particles_frequency == 3) ++n_res;
+            k += (long long)it_done * P.k_iter + (long long)n_res * P.k_res + (long long)n_rec * P.k_met;
+        }
+        count_launches((int)k);
+    }
+    // launch-size hint of the next run on this context (performance only): ~1.5 x the final count, power of two,
+    // changed only when it is off by a class so that similar runs keep sharing the cached graph
+    {
+        int want = 1024;
+        while (want < r.n_final + r.n_final / 2 && want < ctx->cap) want <<= 1;
+        if (want > ctx->loop_hint || want * 4 <= ctx->loop_hint) ctx->loop_hint = want;
+    }
+    ctx->last_n = r.n_final;
+    ctx->last_buf = 0;
+    return AOSLO_OK;
+}
+
+// sklearn tie order: stage calls with the count on the host (every kNN builds sklearn's tree on the host)
+int run_sklearn(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
+                int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
+                aoslo_run_summary* h_summary, float* h_stage_ms) {
     const int H = cfg->H, W = cfg->W, cap = ctx->cap;
-    const bool on_device = (cfg->tie_mode == AOSLO_TIE_CANONICAL);   // count stays on the device
-    memset(h_summary, 0, sizeof(*h_summary));
     AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), s));
     float acc_ms[5] = {0, 0, 0, 0, 0};
     // stage timing: CUDA events on the launch stream, resolved once at the end (no extra syncs)
@@ -486,7 +1042,6 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
         ++ev_used;
         return AOSLO_OK;
     };
-
     int cur = 0, n = 0;
     int* d_cnt[2] = {ctx->d_counters + 4, ctx->d_counters + 5};   // count of buffer 0 / 1
     AOSLO_TRY(epoch_guard(ctx, s, (unsigned)cfg->epoch_num + 1u));
@@ -519,175 +1074,74 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     AOSLO_TRY(stage_lut(ctx, s, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, ctx->d_lut));
     bool packed_ready = false;                       // rank-packed LUT: derived once per run
-    // resample; with `sync` the exact count comes back to the host (it bounds later launch sizes),
-    // without it `n` stays an upper-bound hint -- every kernel takes the real count from the device
-    cudaStream_t qs = s;                             // stream the loop is enqueued on (the capture stream while recording)
-    auto resample = [&](const int* d_n_in, bool sync) -> int {
-        AOSLO_TRY(stage_set_stable(ctx, qs, ctx->d_stable[cur], n, 1, d_n_in));
-        AOSLO_TRY(build_cell_list(ctx, qs, ctx->cl_p, ctx->d_pos[cur], n, d_n_in));
-        AOSLO_TRY(stage_gravity(ctx, qs, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
+    auto resample = [&]() -> int {
+        AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 1, nullptr));
+        AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, ctx->d_pos[cur], n, nullptr));
+        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
         packed_ready = true;
-        AOSLO_TRY(stage_add(ctx, qs, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
-                            cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, d_n_in, cap,
-                            ctx->d_counters + 6));
-        // the appended count lands in a scratch scalar, then becomes this buffer's count
-        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[cur], ctx->d_counters + 6, sizeof(int), cudaMemcpyDeviceToDevice, qs));
-        if (sync) {
-            AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
-            if (n > cap) return AOSLO_ERR_CAPACITY;
-        }
+        AOSLO_TRY(stage_add(ctx, s, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
+                            cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, nullptr, cap,
+                            d_cnt[cur]));
+        AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+        if (n > cap) return AOSLO_ERR_CAPACITY;
         return AOSLO_OK;
     };
-    AOSLO_TRY(resample(nullptr, true));
-    AOSLO_TRY(build_cell_list(ctx, qs, ctx->cl_g, d_gt, n_gt, nullptr));      // GT cell list once
+    AOSLO_TRY(resample());
+    AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));      // GT cell list once
 
     const int k = cfg->dist_n_neighbours;
     const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
+    const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
+    const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
+    const double e2 = pit ? cfg->lambda_dist_func : 0.0;
     int n_rec = 0, it_done = 0;
-    // The epoch loop.  In the canonical tie order without the early stop it contains no host decision:
-    // it is then captured once into a CUDA graph (cached in the context, keyed by everything baked into
-    // the nodes) and replayed -- one graph launch instead of ~350 kernel launches per run.
-    const bool graphable = on_device && !cfg->early_stop && !h_stage_ms && n >= k + 1 &&
-                           !getenv("AOSLO_NO_GRAPH");
-    if (graphable && cur != 0) {                     // the graph is recorded for buffer parity 0
-        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos[0], ctx->d_pos[1], sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, qs));
-        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_stable[0], ctx->d_stable[1], n, cudaMemcpyDeviceToDevice, qs));
-        AOSLO_CUDA(cudaMemcpyAsync(d_cnt[0], d_cnt[1], sizeof(int), cudaMemcpyDeviceToDevice, qs));
-        cur = 0;
-    }
-    auto enqueue_loop = [&](bool syncfree) -> int {
-        bool links_valid = false;                    // ctx->lk_p describes d_pos[cur]
-        if (!syncfree) AOSLO_TRY(mark(-1));
-        for (int it = 0; it < cfg->epoch_num; ++it) {
-            ++it_done;
-            if (!syncfree && n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
-            // `n` is exact in the synchronising mode and an upper-bound hint of the device count otherwise
-            const int* dn = on_device ? d_cnt[cur] : nullptr;
-            const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
-            const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
-            const double e2 = pit ? cfg->lambda_dist_func : 0.0;
-            const double* moved;
-            if (on_device) {
-                // non-stable list, warp-kNN on the linked cells + force + Jacobi move into d_pos_tmp
-                AOSLO_TRY(stage_force_move(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type,
-                                           e0, e1, e2, d_grad, field_dtype, H, W, cfg->lambda_blob, cfg->lambda_dist,
-                                           cfg->step_mode, ctx->d_pos_tmp, dn, links_valid));
-                links_valid = false;
-                moved = ctx->d_pos_tmp;
-                if (!syncfree) { AOSLO_TRY(mark(0)); AOSLO_TRY(mark(1)); }
-            } else {
-                AOSLO_TRY(stage_force(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0,
-                                      e1, e2, cfg->tie_mode, ctx->d_force, dn));
-                AOSLO_TRY(mark(0));
-                AOSLO_TRY(stage_move(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W,
-                                     ctx->d_force, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, dn));
-                AOSLO_TRY(mark(1));
-                moved = ctx->d_pos[cur];
-            }
-            AOSLO_TRY(stage_delete(ctx, qs, moved, ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
-                                   cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1],
-                                   ctx->d_stable[cur ^ 1], nullptr, d_cnt[cur ^ 1], nullptr, dn, on_device ? 2 : 1));
-            cur ^= 1;
-            if (!on_device) AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
-            dn = on_device ? d_cnt[cur] : nullptr;
-            if (!syncfree) AOSLO_TRY(mark(2));
-            if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample(dn, !syncfree));
-            if (!syncfree) AOSLO_TRY(mark(3));
-            if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) {
-                AOSLO_TRY(stage_metrics(ctx, qs, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
-                                        field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec,
-                                        ctx->d_dist_p2g, ctx->d_dist_g2p, dn));
-                links_valid = on_device;             // the metrics pass left links of d_pos[cur] behind
-                ++n_rec;
-            }
-            if (cfg->early_stop) {
-                int n_stable = 0;
-                AOSLO_TRY(stage_count_stable(ctx, qs, ctx->d_stable[cur], n, ctx->d_counters + 2, dn));
-                AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, qs));
-                AOSLO_TRY(read_int(ctx, qs, d_cnt[cur], &n));
-                n_stable = ctx->h_pinned[1];
-                h_summary->n_stable = n_stable;
-                // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
-                if ((double)n_stable / (double)n > 0.997) break;
-            }
-            if (!syncfree) AOSLO_TRY(mark(4));
+    AOSLO_TRY(mark(-1));
+    for (int it = 0; it < cfg->epoch_num; ++it) {
+        ++it_done;
+        if (n < k + 1) { h_summary->status |= AOSLO_DEV_KNN_SHORT; break; }
+        AOSLO_TRY(stage_force(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, k, cfg->dist_energy_type, e0, e1, e2,
+                              cfg->tie_mode, ctx->d_force, nullptr));
+        AOSLO_TRY(mark(0));
+        AOSLO_TRY(stage_move(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_grad, field_dtype, H, W, ctx->d_force,
+                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, nullptr));
+        AOSLO_TRY(mark(1));
+        AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_Rb, field_dtype, H, W,
+                               cfg->threshhold_dist_del, cfg->tie_mode, ctx->d_pos[cur ^ 1], ctx->d_stable[cur ^ 1],
+                               nullptr, d_cnt[cur ^ 1], nullptr, nullptr, 1));
+        cur ^= 1;
+        AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+        AOSLO_TRY(mark(2));
+        if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(resample());
+        AOSLO_TRY(mark(3));
+        if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) {
+            AOSLO_TRY(stage_metrics(ctx, s, ctx->d_pos[cur], ctx->d_stable[cur], n, d_gt, n_gt, true, false, d_Rb,
+                                    field_dtype, H, W, cfg->bx, cfg->by, it, ctx->d_records + n_rec, ctx->d_dist_p2g,
+                                    ctx->d_dist_g2p, nullptr));
+            ++n_rec;
         }
-        return AOSLO_OK;
-    };
-    if (!graphable) {
-        AOSLO_TRY(enqueue_loop(false));
-    } else {
-        // launch-size hint: next power of two above 1.25 n, so that runs of similar size share the graph
-        int hint = 1024;
-        while (hint < n + n / 4 && hint < cap) hint <<= 1;
-        if (hint > cap) hint = cap;
-        struct Key {
-            aoslo_config cfg; const void* Rb; const void* grad; const void* gt; int n_gt, fdt, hint, max_rec;
-            const void* recs;
-        } key;
-        memset(&key, 0, sizeof(key));
-        key.cfg = *cfg; key.Rb = d_Rb; key.grad = d_grad; key.gt = d_gt; key.n_gt = n_gt; key.fdt = field_dtype;
-        key.hint = hint; key.max_rec = max_records; key.recs = h_records ? (const void*)ctx->d_records : nullptr;
-        const bool hit = ctx->graph_exec && ctx->graph_key.size() == sizeof(key) &&
-                         memcmp(ctx->graph_key.data(), &key, sizeof(key)) == 0;
-        const int n_exact = n;
-        if (!hit) {
-            if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; }
-            n = hint;
-            // record on the context's own stream (the caller's may be the legacy default stream, which
-            // cannot capture); nothing executes during capture, the graph is launched on the caller's stream
-            qs = ctx->cap_stream;
-            AOSLO_CUDA(cudaStreamBeginCapture(qs, cudaStreamCaptureModeThreadLocal));
-            int st_loop = enqueue_loop(true);
-            cudaGraph_t graph = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(qs, &graph);
-            qs = s;
-            if (st_loop != AOSLO_OK) { if (graph) cudaGraphDestroy(graph); return st_loop; }
-            if (ce != cudaSuccess) return set_cuda_error(ce, "cudaStreamEndCapture");
-            size_t n_nodes = 0;
-            cudaGraphGetNodes(graph, nullptr, &n_nodes);
-            std::vector<cudaGraphNode_t> nodes(n_nodes);
-            cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
-            int kernels = 0;
-            for (size_t i = 0; i < n_nodes; ++i) {
-                cudaGraphNodeType t;
-                if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++kernels;
-            }
-            ce = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) { ctx->graph_exec = nullptr; return set_cuda_error(ce, "cudaGraphInstantiate"); }
-            ctx->graph_kernel_nodes = kernels;
-            ctx->graph_key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
-            // capture ran the bookkeeping of the loop once; replaying needs the same values
-        } else {
-            // bookkeeping the captured loop would have done
-            for (int it = 0; it < cfg->epoch_num; ++it)
-                if (it % cfg->metric_measure_freq == 0 && h_records && n_rec < max_records) ++n_rec;
-            it_done = cfg->epoch_num;
-            if (cfg->epoch_num & 1) cur ^= 1;
-            ctx->epoch += (unsigned)cfg->epoch_num;
+        if (cfg->early_stop) {
+            AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, nullptr));
+            int n_stable = 0;
+            AOSLO_TRY(read_int(ctx, s, ctx->d_counters + 2, &n_stable));
+            h_summary->n_stable = n_stable;
+            // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
+            if ((double)n_stable / (double)n > 0.997) { AOSLO_TRY(mark(4)); break; }
         }
-        n = n_exact;
-        AOSLO_CUDA(cudaGraphLaunch(ctx->graph_exec, s));
-        count_launches(ctx->graph_kernel_nodes);
+        AOSLO_TRY(mark(4));
     }
-    // ---- results: records, final particles, status -- one synchronisation
+    // ---- results: records, status -- one synchronisation
     if (n_rec)
         AOSLO_CUDA(cudaMemcpyAsync(ctx->h_records, ctx->d_records, sizeof(aoslo_metrics_record) * n_rec,
                                    cudaMemcpyDeviceToHost, s));
     if (!cfg->early_stop) {
-        AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, on_device ? d_cnt[cur] : nullptr));
+        AOSLO_TRY(stage_count_stable(ctx, s, ctx->d_stable[cur], n, ctx->d_counters + 2, nullptr));
         AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
     }
     AOSLO_CUDA(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));
-    AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
+    AOSLO_TRY(stream_wait(ctx, s));
     if (!cfg->early_stop) h_summary->n_stable = ctx->h_pinned[1];
     h_summary->status |= ctx->h_pinned[2];
     for (int i = 0; i < n_rec; ++i) h_records[i] = ctx->h_records[i];
-    if (d_particles_out)
-        AOSLO_CUDA(cudaMemcpyAsync(d_particles_out, ctx->d_pos[cur], sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
-    if (d_stable_out)
-        AOSLO_CUDA(cudaMemcpyAsync(d_stable_out, ctx->d_stable[cur], n, cudaMemcpyDeviceToDevice, s));
     h_summary->n_iterations = it_done;
     h_summary->n_particles = n;
     h_summary->n_records = n_rec;
@@ -700,5 +1154,66 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
         }
         for (int i = 0; i < 5; ++i) h_stage_ms[i] = acc_ms[i];
     }
+    ctx->last_n = n;
+    ctx->last_buf = cur;
+    return AOSLO_OK;
+}
+
+}  // namespace
+
+extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
+                         int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records,
+                         int max_records, double* d_particles_out, uint8_t* d_stable_out,
+                         aoslo_run_summary* h_summary, float* h_stage_ms) {
+    if (!ctx || !cfg || !d_Rb || !d_grad || !d_gt || !h_summary) return AOSLO_ERR_INVALID;
+    if (cfg->H != ctx->H || cfg->W != ctx->W || n_gt < 1 || n_gt > ctx->gt_cap) return AOSLO_ERR_INVALID;
+    if (cfg->dist_n_neighbours < 1 || cfg->dist_n_neighbours + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    if (cfg->particle_call_window < 1 || cfg->reception_field_size < 1 || cfg->reception_field_size > 64)
+        return AOSLO_ERR_UNSUPPORTED;
+    if (cfg->fix_particles_frequency < 1 || cfg->metric_measure_freq < 1 || cfg->epoch_num < 0) return AOSLO_ERR_INVALID;
+    if (cfg->dist_energy_type != AOSLO_ENERGY_PIT && cfg->dist_energy_type != AOSLO_ENERGY_EXP) return AOSLO_ERR_UNSUPPORTED;
+    if (max_records < 0) return AOSLO_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    AOSLO_CUDA(cudaSetDevice(ctx->device));
+    if (h_records && max_records > ctx->max_records) {
+        // grow the record buffers (wandb-style runs log every iteration); cached graphs refer to the old ones
+        AOSLO_CUDA(cudaStreamSynchronize(s));
+        for (RunGraph& g : ctx->graphs) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            if (g.graph) cudaGraphDestroy(g.graph);
+        }
+        ctx->graphs.clear();
+        cudaFree(ctx->d_records);
+        cudaFreeHost(ctx->h_records);
+        ctx->d_records = nullptr; ctx->h_records = nullptr;
+        ctx->max_records = 0;
+        AOSLO_CUDA(cudaMalloc((void**)&ctx->d_records, sizeof(aoslo_metrics_record) * (size_t)max_records));
+        AOSLO_CUDA(cudaHostAlloc((void**)&ctx->h_records, sizeof(aoslo_metrics_record) * (size_t)max_records,
+                                 cudaHostAllocDefault));
+        ctx->max_records = max_records;
+    }
+    memset(h_summary, 0, sizeof(*h_summary));
+    int st;
+    if (cfg->tie_mode == AOSLO_TIE_CANONICAL)
+        st = run_canonical(ctx, s, cfg, d_Rb, d_grad, field_dtype, d_gt, n_gt, h_records, max_records, h_summary,
+                           h_stage_ms);
+    else
+        st = run_sklearn(ctx, s, cfg, d_Rb, d_grad, field_dtype, d_gt, n_gt, h_records, max_records, h_summary,
+                         h_stage_ms);
+    if (st != AOSLO_OK) return st;
+    if (d_particles_out || d_stable_out)
+        return aoslo_read_particles(ctx, stream, d_particles_out, d_stable_out, h_summary->n_particles);
+    return AOSLO_OK;
+}
+
+extern "C" int aoslo_read_particles(aoslo_ctx* ctx, void* stream, double* d_particles_out, uint8_t* d_stable_out,
+                                    int n) {
+    if (!ctx || n < 0 || n > ctx->last_n) return AOSLO_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int b = ctx->last_buf;
+    if (d_particles_out && n)
+        AOSLO_CUDA(cudaMemcpyAsync(d_particles_out, ctx->d_pos[b], sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
+    if (d_stable_out && n)
+        AOSLO_CUDA(cudaMemcpyAsync(d_stable_out, ctx->d_stable[b], n, cudaMemcpyDeviceToDevice, s));
     return AOSLO_OK;
 }

@@ -84,11 +84,61 @@ struct CellLinks {
     int cap = 0;
 };
 
+// geom = {shift, gw, gh, ncell} lives in DEVICE memory: the cell edge is chosen from the point count, which the
+// run loop only knows on the device (link_clear_kernel writes it, every later kernel of the build reads it)
 struct LinkView {
-    int shift, gw, gh;
+    const int* geom;
     const int* head;
     const int* next;
     const double2* pos;
+};
+
+// ---- whole-run control block (device resident, mirrored to pinned memory once at the end of a run) ----
+// aoslo_run enqueues seeding, thinning (a WHILE conditional graph node), resampling and the epoch loop
+// (unrolled, or a WHILE node with IF nodes for the resample / metrics branches when the early stop is on)
+// as ONE CUDA graph; every decision the reference takes on the host is taken by a 1-thread kernel here.
+struct RunCtl {
+    int it;                  // iterations executed so far
+    int n_rec;               // metric records written
+    int n_seeds, n_after_thinning, thin_rounds;
+    int n_stable;            // stable flags counted last (early stop / summary)
+    int thin_cond;           // mirrors of the conditional-node values (the eager debug path reads them)
+    int loop_cond;
+    int do_resample, do_metrics;
+    int n_final;
+    int pad_;
+    unsigned long long t_last;       // %globaltimer of the last stage boundary
+    unsigned long long acc_ns[5];    // the reference's five time_spended buckets
+};
+
+// value parameters of a run, read by the kernels from device memory so that one cached graph serves every
+// configuration of a sweep (only structural parameters -- shapes, template classes, loop layout -- are baked)
+struct RunParams {
+    double seed_thr, thin_thr, del_thr, add_thr;
+    double lut_mu, lut_sigma, lut_lam;
+    double e0, e1, e2;       // energy parameters (pit: mu, sigma, lambda; exp: alpha, sigma, 0)
+    double lb, ld;           // lambda_blob, lambda_dist
+    int kk;                  // dist_n_neighbours + 1
+    int fix_freq, metric_freq, epoch_num, early_stop, max_records, n_gt, pad_;
+};
+
+// K1 implementation knobs: defaults from the environment ONCE at context creation (AOSLO_K1_TMA, AOSLO_PAIR_TH,
+// AOSLO_PAIR_OCC, AOSLO_DTILE_TH, AOSLO_BLOBNESS_KERNEL = tile | band | dtile), changed with aoslo_ctx_set_tuning;
+// nothing on the launch path calls getenv
+struct K1Tuning {
+    int k1_tma = 1;          // 0: cp.async staging, plain stores; 1: TMA tensor loads; 2: TMA tensor stores too
+    int pair_th = 0;         // tile height of the f32 pair kernel (0 = chosen per image)
+    int pair_occ = 0;        // CTAs per SM of the f32 pair kernel (0 = by tile height)
+    int dtile_th = 0;        // tile height of the f64 tile kernel (0 = 32)
+    int k1_kernel = 0;       // 0 auto, 1 generic tile kernel, 2 band kernel, 3 f64 tile kernel
+};
+
+struct RunGraph {            // one cached instantiation
+    std::vector<unsigned char> key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int static_kernels = 0, thin_kernels = 0, iter_kernels = 0, resample_kernels = 0, metrics_kernels = 0;
+    unsigned long long stamp = 0;    // LRU
 };
 
 // sklearn-order KD tree mirrored on the device (built on the host, kdtree_host.cpp)
@@ -131,11 +181,23 @@ struct aoslo_ctx {
     cudaEvent_t ev_block = nullptr;
     unsigned int epoch = 1;           // host-side upper estimate of *d_epoch
     unsigned int* d_epoch = nullptr;  // device call counter of the in-loop deletion (stamps `touch`)
-    // cached CUDA graph of the epoch loop (canonical tie order, no early stop)
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaStream_t cap_stream = nullptr;   // recording stream of the capture
-    std::vector<unsigned char> graph_key;
-    int graph_kernel_nodes = 0;
+    // cached CUDA graphs of the whole run (canonical tie order), keyed by the structural parameters
+    std::vector<aoslo::RunGraph> graphs;
+    unsigned long long graph_clock = 0;
+    cudaStream_t cap_stream = nullptr;   // recording streams of the capture (top level, WHILE body, IF body)
+    cudaStream_t cap_stream2 = nullptr;
+    cudaStream_t cap_stream3 = nullptr;
+    aoslo::RunCtl* d_ctl = nullptr;
+    aoslo::RunCtl* h_ctl = nullptr;      // pinned
+    aoslo::RunParams* d_params = nullptr;
+    aoslo::RunParams* h_params = nullptr;   // pinned staging of the per-run upload
+    int* d_link_geom = nullptr;          // [4] shift, gw, gh, ncell of lk_p
+    uint8_t* d_stable_tmp = nullptr;     // [cap] flags of the moved particles (input of the in-loop compaction)
+    int loop_hint = 0;                   // launch-size hint of the in-loop compaction (performance only)
+    aoslo::K1Tuning tune;
+    int last_n = 0, last_buf = 0;        // where the final particles of the last run live (aoslo_read_particles)
+    int no_graph = 0;                    // AOSLO_NO_GRAPH read once at context creation (eager debug path)
+    int coop_cap_blocks = 0;
     int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
     double* d_knn_d2 = nullptr;
     int* d_block_sums = nullptr;      // [kMaxScanBlocks + 1]
@@ -226,9 +288,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_count_kernel(Op op, int m_h
 }
 
 // one block: exclusive scan of the block sums; writes total (+ base) to d_total
+// `clamp` > 0: the stored total never exceeds it (an over-full append raises AOSLO_DEV_CAPACITY in `status`
+// and later kernels iterate over at most `clamp` rows -- the buffers' capacity)
 __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
                                                                   const int* d_base, int base_host,
-                                                                  int* d_total_added);
+                                                                  int* d_total_added, int clamp, int* status);
 
 template <class Op>
 __global__ void __launch_bounds__(kScanThreads) scan_emit_kernel(Op op, int m_host, const int* d_m,
@@ -256,11 +320,12 @@ int scan_blocks_for(int m_capacity);
 // `base` (offset added to every prefix handed to emit) comes from *d_base if non-null.
 template <class Op>
 int ordered_scan(aoslo_ctx* ctx, cudaStream_t s, Op op, int m_capacity, int m_host, const int* d_m,
-                 int* d_total, const int* d_base, int base_host, int* d_total_added) {
+                 int* d_total, const int* d_base, int base_host, int* d_total_added, int clamp = 0) {
     int nb = scan_blocks_for(m_capacity);
     scan_count_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
     AOSLO_LAUNCH_CHECK();
-    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(ctx->d_block_sums, nb, d_total, d_base, base_host, d_total_added);
+    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(ctx->d_block_sums, nb, d_total, d_base, base_host, d_total_added,
+                                                 clamp, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
     scan_emit_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
     AOSLO_LAUNCH_CHECK();
@@ -281,9 +346,51 @@ int kd_reserve(aoslo_ctx* ctx);
 int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead);
 int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr);
+                const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr,
+                uint8_t* prep_stable_out = nullptr);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
                 int n_query, int k, int32_t* d_idx, double* d_d2);
+
+// stage drivers (particles.cu).  Trailing d_n: optional device-resident particle count (n is then only a
+// launch-size bound); d_thr / rp: device-resident value parameters of the graph path (override the host values)
+int stage_knn(aoslo_ctx*, cudaStream_t, const double* d_points, int n_points, const double* d_query, int n_query,
+              int k, int tie_mode, int32_t* d_idx, double* d_d2, bool tree_is_particles, const int* d_n = nullptr);
+int stage_delete(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d_stable, int n, const void* d_Rb,
+                 int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
+                 uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode,
+                 const double* d_thr = nullptr, int scan_hint = 0);
+int stage_force_move(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d_stable, int n, int k,
+                     int energy_type, double p0, double p1, double p2, const void* d_grad, int field_dtype, int H,
+                     int W, double lb, double ld, int step_mode, double* d_pos_out, const int* d_n, bool links_ready,
+                     uint8_t* d_stable_copy = nullptr, const RunParams* rp = nullptr);
+int stage_seed(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int H, int W, int bx, int by, double thr,
+               double* d_pos, int cap, int* d_n_out, const double* d_thr = nullptr, bool clamp_count = false);
+int stage_lut(aoslo_ctx*, cudaStream_t, int rfs, double mu, double sigma, double lam, double* d_lut,
+              const RunParams* rp = nullptr);
+int stage_gravity(aoslo_ctx*, cudaStream_t, const double* d_lut, int rfs, int H, int W, double* d_field,
+                  bool packed_ready);
+int stage_add(aoslo_ctx*, cudaStream_t, const double* d_field, int H, int W, int bx, int by, int window, double thr,
+              double* d_pos, uint8_t* d_stable, int n_host, const int* d_n, int cap, int* d_n_out,
+              const double* d_thr = nullptr, bool clamp_count = false);
+int stage_force(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d_stable, int n, int k, int energy_type,
+                double p0, double p1, double p2, int tie_mode, double* d_force, const int* d_n);
+int stage_move(aoslo_ctx*, cudaStream_t, double* d_pos, const uint8_t* d_stable, int n, const void* d_grad,
+               int field_dtype, int H, int W, const double* d_force, double lb, double ld, int step_mode,
+               const int* d_n);
+int stage_metrics(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d_stable, int n, const double* d_gt,
+                  int n_gt, bool gt_list_ready, bool p_list_ready, const void* d_Rb, int field_dtype, int H, int W,
+                  int bx, int by, int iteration, aoslo_metrics_record* d_rec, double* d_p2g, double* d_g2p,
+                  const int* d_n, const int* d_n_gt = nullptr, int* d_rec_idx = nullptr,
+                  const int* d_iteration = nullptr);
+int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t* d_stable, int n, uint8_t v, const int* d_n);
+int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t* d_stable, int n, int* d_out, const int* d_n);
+int coop_blocks_for_delete(int num_sms);
+int stage_classify(aoslo_ctx*, cudaStream_t, const double* d_g2p, int n_gt, const double* d_p2g, const double* d_pos,
+                   int n, int bx, int by, int W, int H, double thr, uint8_t* gt_is_tp, uint8_t* particle_is_fp);
+int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t* d_raw, int H0, int W0, int pitch0, int x_min, int x_max,
+                  int y_min, int y_max, int bx, int by, uint8_t* d_img_out, int out_pitch, const double* d_gt_raw,
+                  int n_gt_raw, double* d_gt_out, int* d_n_gt_out);
+int sqrt_inplace(cudaStream_t, double* a, size_t n);
 
 }  // namespace aoslo

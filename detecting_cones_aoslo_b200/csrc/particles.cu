@@ -29,7 +29,7 @@ namespace aoslo {
 // =======================================================================================
 __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
                                                                   const int* d_base, int base_host,
-                                                                  int* d_total_added) {
+                                                                  int* d_total_added, int clamp, int* status) {
     __shared__ int sw[33];
     int base = d_base ? *d_base : base_host;
     int v = (threadIdx.x < nblocks) ? block_sums[threadIdx.x] : 0;
@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sum
     int excl = block_excl_scan(v, sw, total);
     if (threadIdx.x < nblocks) block_sums[threadIdx.x] = base + excl;
     if (threadIdx.x == 0) {
-        if (d_total) *d_total = base + total;
+        int t = base + total;
+        if (clamp > 0 && t > clamp) {             // the emit phase skipped the rows beyond the capacity
+            t = clamp;
+            if (status) atomicOr(status, AOSLO_DEV_CAPACITY);
+        }
+        if (d_total) *d_total = t;
         if (d_total_added) *d_total_added = total;
     }
 }
@@ -197,21 +202,50 @@ __device__ __forceinline__ void knn_cells_query(const CellView& cl, double qx, d
 // =======================================================================================
 // scan-free linked cells: build (memset + 1 kernel) and the same exact ring search
 // =======================================================================================
-// PREP additionally does ns_prepare_kernel's work in the same pass (copy to the move buffer, clear the
+// Cell edge from the point density: about two points per cell, 2..16 px.  Dense seed sets (thinning: every
+// other pixel) get 2-4 px cells, the steady state (one particle per ~34 px^2) 8 px cells.  Evaluated on the
+// device from the device-resident count (the run loop never brings it to the host); AOSLO_LINK_SHIFT pins it.
+__host__ __device__ inline int link_shift_for(int n, int H, int W, int min_shift, int fixed_shift) {
+    int shift = fixed_shift;
+    if (shift <= 0) {
+        const double area = 2.0 * (double)H * (double)W / (double)(n > 0 ? n : 1);
+        shift = 1;
+        while (shift < 4 && (double)(1 << (shift + 1)) * (double)(1 << (shift + 1)) <= area * 1.5) ++shift;
+    }
+    if (shift < min_shift) shift = min_shift;
+    return shift;
+}
+
+// first kernel of a build: fixes the geometry (every thread derives it from the count, thread 0 publishes it for
+// the kernels that follow) and empties the cell heads
+__global__ void __launch_bounds__(kThreads) link_clear_kernel(int n_host, const int* d_n, int H, int W, int min_shift,
+                                                              int fixed_shift, int* geom, int* head) {
+    const int n = d_n ? *d_n : n_host;
+    const int shift = link_shift_for(n, H, W, min_shift, fixed_shift);
+    const int gw = (W + (1 << shift) - 1) >> shift, gh = (H + (1 << shift) - 1) >> shift;
+    const int ncell = gw * gh;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { geom[0] = shift; geom[1] = gw; geom[2] = gh; geom[3] = ncell; }
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) head[c] = -1;
+}
+
+// PREP additionally does ns_prepare_kernel's work in the same pass (copy to the move buffers, clear the
 // deletion flags, collect the non-stable list)
 template <bool PREP>
 __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restrict__ pos, int n_host,
-                                                        const int* d_n, int shift, int gw, int gh, int W, int H,
+                                                        const int* d_n, const int* __restrict__ geom, int W, int H,
                                                         int* head, int* next, int* status,
                                                         const uint8_t* __restrict__ stable, double2* pos_out,
-                                                        uint8_t* del, int* ns_list, int* n_ns) {
+                                                        uint8_t* stable_out, uint8_t* del, int* ns_list, int* n_ns) {
     int n = d_n ? *d_n : n_host;
+    const int shift = geom[0], gw = geom[1], gh = geom[2];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double2 p = pos[i];
         if (PREP) {
+            const uint8_t st = stable[i];
             pos_out[i] = p;
+            if (stable_out) stable_out[i] = st;
             del[i] = 0;
-            if (!stable[i]) ns_list[atomicAdd(n_ns, 1)] = i;
+            if (!st) ns_list[atomicAdd(n_ns, 1)] = i;
         }
         bool bad = false;
         int cx = cell_coord(p.x, shift, gw, bad);
@@ -222,38 +256,27 @@ __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restric
     }
 }
 
+// n_host is the count, or (with d_n) only its launch-size upper bound
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                const uint8_t* prep_stable, double* prep_pos_out) {
-    // cell edge from the point density (n_host is the count or its launch-size hint): about two points
-    // per cell, 2..16 px.  Dense seed sets (thinning: every other pixel) get 2-4 px cells, the steady
-    // state (one particle per ~34 px^2) 8 px cells.  AOSLO_LINK_SHIFT pins it.
-    int shift = lk.fixed_shift;
-    if (shift <= 0) {
-        const double area = 2.0 * (double)ctx->H * (double)ctx->W / (double)(n_host > 0 ? n_host : 1);
-        shift = 1;
-        while (shift < 4 && (double)(1 << (shift + 1)) * (double)(1 << (shift + 1)) <= area * 1.5) ++shift;
-    }
-    if (shift < lk.min_shift) shift = lk.min_shift;
-    lk.shift = shift;
-    lk.gw = (ctx->W + (1 << shift) - 1) >> shift;
-    lk.gh = (ctx->H + (1 << shift) - 1) >> shift;
-    lk.ncell = lk.gw * lk.gh;
-    AOSLO_CUDA(cudaMemsetAsync(lk.head, 0xff, sizeof(int) * lk.ncell, s));
+                const uint8_t* prep_stable, double* prep_pos_out, uint8_t* prep_stable_out) {
+    link_clear_kernel<<<ctx->nb, kThreads, 0, s>>>(n_host, d_n, ctx->H, ctx->W, lk.min_shift, lk.fixed_shift,
+                                                   ctx->d_link_geom, lk.head);
+    AOSLO_LAUNCH_CHECK();
     if (prep_stable)
-        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh,
-                                                       ctx->W, ctx->H, lk.head, lk.next, ctx->d_status, prep_stable,
-                                                       (double2*)prep_pos_out, ctx->d_del, ctx->d_ns_list,
-                                                       ctx->d_counters + 13);
+        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->d_link_geom, ctx->W,
+                                                       ctx->H, lk.head, lk.next, ctx->d_status, prep_stable,
+                                                       (double2*)prep_pos_out, prep_stable_out, ctx->d_del,
+                                                       ctx->d_ns_list, ctx->d_counters + 13);
     else
-        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, lk.shift, lk.gw, lk.gh,
-                                                        ctx->W, ctx->H, lk.head, lk.next, ctx->d_status, nullptr,
+        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->d_link_geom, ctx->W,
+                                                        ctx->H, lk.head, lk.next, ctx->d_status, nullptr, nullptr,
                                                         nullptr, nullptr, nullptr, nullptr);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
 
-inline LinkView link_view(const CellLinks& lk, const double* d_pos) {
-    return LinkView{lk.shift, lk.gw, lk.gh, lk.head, lk.next, (const double2*)d_pos};
+inline LinkView link_view(aoslo_ctx* ctx, const CellLinks& lk, const double* d_pos) {
+    return LinkView{ctx->d_link_geom, lk.head, lk.next, (const double2*)d_pos};
 }
 
 template <int K>
@@ -268,28 +291,29 @@ __device__ __forceinline__ void knn_links_cell(const LinkView& lv, int cell, dou
 template <int K>
 __device__ __forceinline__ void knn_links_query(const LinkView& lv, double qx, double qy, TopK<K>& top) {
     top.init();
-    const int c = 1 << lv.shift;
-    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> lv.shift) : 0;
-    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> lv.shift) : 0;
-    cx = min(cx, lv.gw - 1);
-    cy = min(cy, lv.gh - 1);
-    const int rmax = max(lv.gw, lv.gh);
+    const int shift = lv.geom[0], gw = lv.geom[1], gh = lv.geom[2];
+    const int c = 1 << shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
+    cx = min(cx, gw - 1);
+    cy = min(cy, gh - 1);
+    const int rmax = max(gw, gh);
     for (int r = 0; r <= rmax; ++r) {
         const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
-        for (int y = max(ylo, 0); y <= min(yhi, lv.gh - 1); ++y) {
+        for (int y = max(ylo, 0); y <= min(yhi, gh - 1); ++y) {
             if (y == ylo || y == yhi) {
-                for (int x = max(xlo, 0); x <= min(xhi, lv.gw - 1); ++x)
-                    knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, top);
+                for (int x = max(xlo, 0); x <= min(xhi, gw - 1); ++x)
+                    knn_links_cell<K>(lv, y * gw + x, qx, qy, top);
             } else {
-                if (xlo >= 0) knn_links_cell<K>(lv, y * lv.gw + xlo, qx, qy, top);
-                if (xhi < lv.gw) knn_links_cell<K>(lv, y * lv.gw + xhi, qx, qy, top);
+                if (xlo >= 0) knn_links_cell<K>(lv, y * gw + xlo, qx, qy, top);
+                if (xhi < gw) knn_links_cell<K>(lv, y * gw + xhi, qx, qy, top);
             }
         }
         double bound = INFINITY;
         if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
         if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
-        if (xhi < lv.gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
-        if (yhi < lv.gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (xhi < gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
         if (bound == INFINITY) break;
         if (bound > 0.0 && top.d2[K - 1] < bound * bound) break;
     }
@@ -367,19 +391,20 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
     TopK<K> mine;
     mine.init();
     out.init();
-    const int c = 1 << lv.shift;
-    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> lv.shift) : 0;
-    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> lv.shift) : 0;
-    cx = min(cx, lv.gw - 1);
-    cy = min(cy, lv.gh - 1);
-    const int rmax = max(lv.gw, lv.gh);
+    const int shift = lv.geom[0], gw = lv.geom[1], gh = lv.geom[2];
+    const int c = 1 << shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
+    cx = min(cx, gw - 1);
+    cy = min(cy, gh - 1);
+    const int rmax = max(gw, gh);
     // rings 0 and 1 (the 3x3 block) are visited together -- lane j takes cell j -- so the common case costs
     // one round of dependent loads and one merge; further rings follow one at a time
     for (int r = 1; r <= rmax; ++r) {
         if (r == 1) {
             if (lane < 9) {
                 const int x = cx + (lane % 3) - 1, y = cy + (lane / 3) - 1;
-                if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, qx, qy, mine);
             }
         } else {
             const int ncells = 8 * r;
@@ -390,7 +415,7 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
                 else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
                 else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
                 const int x = cx + dx, y = cy + dy;
-                if (x >= 0 && x < lv.gw && y >= 0 && y < lv.gh) knn_links_cell<K>(lv, y * lv.gw + x, qx, qy, mine);
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, qx, qy, mine);
             }
         }
         warp_merge_topk<K>(mine, out);
@@ -398,8 +423,8 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
         double bound = INFINITY;
         if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
         if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
-        if (xhi < lv.gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
-        if (yhi < lv.gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (xhi < gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
         if (bound == INFINITY) break;
         if (bound > 0.0 && out.d2[K - 1] < bound * bound) break;
     }
@@ -559,12 +584,14 @@ struct SeedOp {
     const T* Rb;
     int W, bx, by, wi;
     double thr;
+    const double* d_thr;        // device-resident threshold of the graph path (overrides thr)
     double2* out;
     int cap;
     int* status;
     __device__ int value(int m) const {
         int y = by + m / wi, x = bx + m % wi;
-        return ((double)Rb[(size_t)y * fpitch(W) + x] > thr) ? 1 : 0;
+        const double t = d_thr ? *d_thr : thr;
+        return ((double)Rb[(size_t)y * fpitch(W) + x] > t) ? 1 : 0;
     }
     __device__ void emit(int m, int v, int dst) const {
         if (!v) return;
@@ -592,6 +619,7 @@ struct DeleteParams {
     const int32_t* knn_idx;     // [n][2]
     const double* knn_d2;       // [n][2]
     double thr;
+    const double* d_thr;        // overrides thr (graph path)
     int W, H;
     unsigned long long* touch;
     uint8_t* del;
@@ -617,12 +645,13 @@ __global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p
     const int n = p.d_n ? *p.d_n : p.n_host;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthr = gridDim.x * blockDim.x;
+    const double thr = p.d_thr ? *p.d_thr : p.thr;
     __shared__ int s_pending;
 
     for (int i = tid; i < n; i += nthr) {
         int from = p.knn_idx[2 * i], to = p.knn_idx[2 * i + 1];
         double dist = sqrt(p.knn_d2[2 * i + 1]);
-        bool active = (to >= 0) && (from >= 0) && !p.stable[from] && (dist < p.thr);
+        bool active = (to >= 0) && (from >= 0) && !p.stable[from] && (dist < thr);
         p.rowstate[i] = active ? 1 : 0;
         p.del[i] = 0;
         p.touch[i] = 0ull;
@@ -672,11 +701,12 @@ __global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p
 // (rows whose `from` is not stable and whose neighbour is closer than the threshold)
 __global__ void __launch_bounds__(kThreads) knn2_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
                                                              int n_host, const int* d_n, double thr,
-                                                             int32_t* knn_idx, double* knn_d2, uint8_t* del,
-                                                             int* active, int* n_active, int* status,
+                                                             const double* d_thr, int32_t* knn_idx, double* knn_d2,
+                                                             uint8_t* del, int* active, int* n_active, int* status,
                                                              const int* gate) {
     if (gate && *gate == 0) return;            // fallback of the non-stable-list path: nothing coincided
     int n = d_n ? *d_n : n_host;
+    if (d_thr) thr = *d_thr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double2 p = lv.pos[i];
         TopK<2> top;
@@ -832,9 +862,10 @@ __device__ __forceinline__ double energy_pit2(double dist, double mu, double sig
     return (dist <= mu) ? (e - nrm + 0.48) : (e + nrm - 0.48);
 }
 
-__global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, double* lut) {
+__global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, double* lut, const RunParams* rp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rfs * rfs) return;
+    if (rp) { mu = rp->lut_mu; sigma = rp->lut_sigma; lam = rp->lut_lam; }
     int y = i / rfs, x = i - y * rfs;
     double dx = (double)(x - rfs / 2), dy = (double)(y - rfs / 2);
     lut[i] = energy_pit2(sqrt(dx * dx + dy * dy), mu, sigma, lam);
@@ -940,9 +971,10 @@ __global__ void __launch_bounds__(kGravCols) gravity_field_kernel(CellView cl, c
 // =======================================================================================
 __global__ void __launch_bounds__(kThreads) window_argmin_kernel(const double* __restrict__ field, int H, int W,
                                                                 int bx, int by, int step, double thr, int nwx,
-                                                                int nwy, int32_t* cand) {
+                                                                int nwy, int32_t* cand, const double* d_thr) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nwx * nwy) return;
+    if (d_thr) thr = *d_thr;
     int wy = w / nwx, wx = w - wy * nwx;
     int px = bx + wx * step, py = by + wy * step;
     int x1 = min(px + step, W), y1 = min(py + step, H);
@@ -1084,12 +1116,15 @@ __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint
 __global__ void __launch_bounds__(kThreads) ns_prepare_kernel(const double2* __restrict__ pos,
                                                               const uint8_t* __restrict__ stable, int n_host,
                                                               const int* d_n, double2* __restrict__ pos_out,
+                                                              uint8_t* __restrict__ stable_out,
                                                               uint8_t* __restrict__ del, int* ns_list, int* n_ns) {
     int n = d_n ? *d_n : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t st = stable[i];
         pos_out[i] = pos[i];
+        if (stable_out) stable_out[i] = st;
         del[i] = 0;
-        if (!stable[i]) ns_list[atomicAdd(n_ns, 1)] = i;
+        if (!st) ns_list[atomicAdd(n_ns, 1)] = i;
     }
 }
 
@@ -1097,10 +1132,11 @@ template <int K, typename T>
 __global__ void __launch_bounds__(kThreads) ns_force_move_kernel(
     LinkView lv, const int* __restrict__ ns_list, const int* __restrict__ n_ns, int kk, int energy_type, double p0,
     double p1, double p2, const T* __restrict__ grad, int H, int W, double lb, double ld, int step_mode,
-    double2* __restrict__ pos_out, int* status) {
+    double2* __restrict__ pos_out, int* status, const RunParams* rp) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = *n_ns;
+    if (rp) { kk = rp->kk; p0 = rp->e0; p1 = rp->e1; p2 = rp->e2; lb = rp->lb; ld = rp->ld; }
     for (int q = warp; q < total; q += nwarps) {
         const int i = ns_list[q];
         double2 p = lv.pos[i];
@@ -1147,9 +1183,10 @@ __global__ void __launch_bounds__(kThreads) ns_force_move_kernel(
 __global__ void __launch_bounds__(kThreads) ns_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
                                                            const int* __restrict__ ns_list,
                                                            const int* __restrict__ n_ns, double thr,
-                                                           int32_t* knn_idx, double* knn_d2, int* active,
-                                                           int* n_active, int* fallback) {
+                                                           const double* d_thr, int32_t* knn_idx, double* knn_d2,
+                                                           int* active, int* n_active, int* fallback) {
     const int lane = threadIdx.x & 31;
+    if (d_thr) thr = *d_thr;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = *n_ns;
     for (int q = warp; q < total; q += nwarps) {
@@ -1229,8 +1266,11 @@ __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
     CellView cl_g, LinkView lk_p, const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host,
     const int* d_n, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W, int bx, int by,
     double* d_p2g, double* d_g2p, int* icount /*[9]: 8 counts + block ticket*/, MetricsPartial* partials,
-    int iteration, aoslo_metrics_record* rec, int* status) {
+    int iteration, aoslo_metrics_record* rec, int* status, const int* d_n_gt, int* d_rec_idx, const int* d_iteration) {
+    // graph path: GT count, record slot and iteration number are device scalars (d_rec_idx is advanced by the
+    // thread that writes the record)
     const int n = d_n ? *d_n : n_host;
+    if (d_n_gt) n_gt = *d_n_gt;
     const int total = n + n_gt;
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tp1 tp2 fn1 fn2 fp1 fp2 nin nst
     Moments mp, mg;
@@ -1330,6 +1370,8 @@ __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
         }
     }
     if (threadIdx.x != 0) return;
+    if (d_rec_idx) { const int slot = *d_rec_idx; rec += slot; *d_rec_idx = slot + 1; }
+    if (d_iteration) iteration = *d_iteration;
     rec->iteration = iteration;
     rec->n_particles = n;
     rec->n_stable = __ldcg(&icount[7]);
@@ -1411,7 +1453,7 @@ __global__ void __launch_bounds__(kThreads) count_stable_kernel(const uint8_t* _
 // sklearn-order path needs the count on the host to build the tree)
 int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
               int n_query, int k, int tie_mode, int32_t* d_idx, double* d_d2, bool tree_is_particles,
-              const int* d_n = nullptr) {
+              const int* d_n) {
     if (tie_mode == AOSLO_TIE_SKLEARN) {
         if (d_n) return AOSLO_ERR_INVALID;
         return knn_sklearn(ctx, s, d_points, n_points, d_query, n_query, k, d_idx, d_d2);
@@ -1419,7 +1461,7 @@ int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_poin
     (void)tree_is_particles;
     if (n_points > ctx->lk_p.cap) return AOSLO_ERR_CAPACITY;
     AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_points, n_points, d_n));
-    return knn_links(ctx, s, link_view(ctx->lk_p, d_points), d_query, n_query, d_n, k, d_idx, d_d2);
+    return knn_links(ctx, s, link_view(ctx, ctx->lk_p, d_points), d_query, n_query, d_n, k, d_idx, d_d2);
 }
 
 // The 20-bit epoch field of the touch keys must never wrap inside a run: called at the start of a run
@@ -1438,7 +1480,8 @@ int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead) {
 template <typename T>
 int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                    const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
-                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode) {
+                   uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode,
+                   const double* d_thr, int scan_hint) {
     // mode 0: cooperative all-rows resolve; 1: compact active list + one block; 2: as 1, rows taken from
     // the non-stable list left by stage_force_move (canonical run loop)
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
@@ -1453,17 +1496,17 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
     if (small) {
         if (use_ns) {
             AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
-            LinkView lv = link_view(ctx->lk_p, d_pos);
-            ns_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, ctx->d_ns_list, n_ns, thr, ctx->d_knn_idx,
+            LinkView lv = link_view(ctx, ctx->lk_p, d_pos);
+            ns_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, ctx->d_ns_list, n_ns, thr, d_thr, ctx->d_knn_idx,
                                                         ctx->d_knn_d2, ctx->d_active, n_active, fallback);
             AOSLO_LAUNCH_CHECK();
-            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, n, d_n, thr, ctx->d_knn_idx, ctx->d_knn_d2,
-                                                          ctx->d_del, ctx->d_active_b, n_active_b, ctx->d_status,
-                                                          fallback);
+            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, n, d_n, thr, d_thr, ctx->d_knn_idx,
+                                                          ctx->d_knn_d2, ctx->d_del, ctx->d_active_b, n_active_b,
+                                                          ctx->d_status, fallback);
             AOSLO_LAUNCH_CHECK();
         } else if (tie_mode == AOSLO_TIE_CANONICAL) {
             AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
-            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx->lk_p, d_pos), d_stable, n, d_n, thr,
+            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx, ctx->lk_p, d_pos), d_stable, n, d_n, thr, d_thr,
                                                           ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_del, ctx->d_active,
                                                           n_active, ctx->d_status, nullptr);
             AOSLO_LAUNCH_CHECK();
@@ -1475,7 +1518,8 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         }
         // the resolving block also prepares the compaction offsets, so only the emit phase of the
         // ordered scan has to be launched afterwards
-        const int nb_scan = scan_blocks_for(n);
+        // the number of compaction blocks is a launch-size choice only (any count is correct for any n)
+        const int nb_scan = scan_blocks_for(scan_hint > 0 ? scan_hint : n);
         delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
             (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active,
             use_ns ? ctx->d_active_b : nullptr, use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr,
@@ -1492,7 +1536,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
         DeleteParams p;
         p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
-        p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.W = W; p.H = H;
+        p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.d_thr = d_thr; p.W = W; p.H = H;
         p.touch = ctx->d_touch; p.del = ctx->d_del; p.rowstate = ctx->d_rowstate;
         p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
         void* args[] = {&p, (void*)&d_Rb};
@@ -1510,12 +1554,12 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
 int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                  const void* d_Rb, int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out,
                  uint8_t* d_stable_out, uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n,
-                 int mode) {
+                 int mode, const double* d_thr, int scan_hint) {
     if (field_dtype == AOSLO_F32)
         return stage_delete_t<float>(ctx, s, d_pos, d_stable, n, (const float*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode);
+                                     d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode, d_thr, scan_hint);
     return stage_delete_t<double>(ctx, s, d_pos, d_stable, n, (const double*)d_Rb, H, W, thr, tie_mode, d_pos_out,
-                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode);
+                                  d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode, d_thr, scan_hint);
 }
 
 // force + move of the run loop (canonical tie order): copy positions + collect the non-stable list,
@@ -1524,24 +1568,24 @@ int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint
 int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
                      int energy_type, double p0, double p1, double p2, const void* d_grad, int field_dtype, int H,
                      int W, double lb, double ld, int step_mode, double* d_pos_out, const int* d_n,
-                     bool links_ready) {
+                     bool links_ready, uint8_t* d_stable_copy, const RunParams* rp) {
     if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
-    int* n_ns = ctx->d_counters + 13;
+    int* n_ns = ctx->d_counters + 13;          // zero here: reset by the resolve kernel / by the callers
     if (!links_ready) {
         // one pass: link the particles and do ns_prepare's work (copy, clear flags, non-stable list)
-        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, d_stable, d_pos_out));
+        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, d_stable, d_pos_out, d_stable_copy));
     } else {
         ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
-                                                       ctx->d_del, ctx->d_ns_list, n_ns);
+                                                       d_stable_copy, ctx->d_del, ctx->d_ns_list, n_ns);
         AOSLO_LAUNCH_CHECK();
     }
-    LinkView lv = link_view(ctx->lk_p, d_pos);
+    LinkView lv = link_view(ctx, ctx->lk_p, d_pos);
     const int kk = k + 1;
 #define AOSLO_FM(KT, TT)                                                                                          \
     ns_force_move_kernel<KT, TT><<<ctx->nb, kThreads, 0, s>>>(lv, ctx->d_ns_list, n_ns, kk, energy_type, p0, p1, p2, \
                                                               (const TT*)d_grad, H, W, lb, ld, step_mode,          \
-                                                              (double2*)d_pos_out, ctx->d_status)
+                                                              (double2*)d_pos_out, ctx->d_status, rp)
     if (field_dtype == AOSLO_F32) {
         if (kk <= 2) AOSLO_FM(2, float); else if (kk <= 4) AOSLO_FM(4, float); else AOSLO_FM(8, float);
     } else {
@@ -1552,22 +1596,25 @@ int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const 
     return AOSLO_OK;
 }
 
+// clamp_count: the stored count never exceeds cap (graph path); otherwise the caller compares it with cap
 int stage_seed(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
-               double thr, double* d_pos, int cap, int* d_n_out) {
+               double thr, double* d_pos, int cap, int* d_n_out, const double* d_thr, bool clamp_count) {
     int wi = W - 2 * bx, hi = H - 2 * by;
     if (wi <= 0 || hi <= 0) return AOSLO_ERR_INVALID;
     int m = wi * hi;
+    const int clamp = clamp_count ? cap : 0;
     if (field_dtype == AOSLO_F32) {
-        SeedOp<float> op{(const float*)d_Rb, W, bx, by, wi, thr, (double2*)d_pos, cap, ctx->d_status};
-        return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr);
+        SeedOp<float> op{(const float*)d_Rb, W, bx, by, wi, thr, d_thr, (double2*)d_pos, cap, ctx->d_status};
+        return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr, clamp);
     }
-    SeedOp<double> op{(const double*)d_Rb, W, bx, by, wi, thr, (double2*)d_pos, cap, ctx->d_status};
-    return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr);
+    SeedOp<double> op{(const double*)d_Rb, W, bx, by, wi, thr, d_thr, (double2*)d_pos, cap, ctx->d_status};
+    return ordered_scan(ctx, s, op, m, m, nullptr, d_n_out, nullptr, 0, nullptr, clamp);
 }
 
-int stage_lut(aoslo_ctx*, cudaStream_t s, int rfs, double mu, double sigma, double lam, double* d_lut) {
+int stage_lut(aoslo_ctx*, cudaStream_t s, int rfs, double mu, double sigma, double lam, double* d_lut,
+              const RunParams* rp) {
     if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
-    dist_lut_kernel<<<(rfs * rfs + 255) / 256, 256, 0, s>>>(rfs, mu, sigma, lam, d_lut);
+    dist_lut_kernel<<<(rfs * rfs + 255) / 256, 256, 0, s>>>(rfs, mu, sigma, lam, d_lut, rp);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
@@ -1592,16 +1639,17 @@ int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, 
 }
 
 int stage_add(aoslo_ctx* ctx, cudaStream_t s, const double* d_field, int H, int W, int bx, int by, int window,
-              double thr, double* d_pos, uint8_t* d_stable, int n_host, const int* d_n, int cap, int* d_n_out) {
+              double thr, double* d_pos, uint8_t* d_stable, int n_host, const int* d_n, int cap, int* d_n_out,
+              const double* d_thr, bool clamp_count) {
     if (window < 1) return AOSLO_ERR_INVALID;
     int nwx = (W - 2 * bx + window - 1) / window, nwy = (H - 2 * by + window - 1) / window;
     if (nwx <= 0 || nwy <= 0) return AOSLO_ERR_INVALID;
     int nw = nwx * nwy;
     window_argmin_kernel<<<(nw + kThreads - 1) / kThreads, kThreads, 0, s>>>(d_field, H, W, bx, by, window, thr,
-                                                                           nwx, nwy, ctx->d_win);
+                                                                           nwx, nwy, ctx->d_win, d_thr);
     AOSLO_LAUNCH_CHECK();
     AppendOp op{ctx->d_win, W, (double2*)d_pos, d_stable, cap, ctx->d_status};
-    return ordered_scan(ctx, s, op, nw, nw, nullptr, d_n_out, d_n, n_host, nullptr);
+    return ordered_scan(ctx, s, op, nw, nw, nullptr, d_n_out, d_n, n_host, nullptr, clamp_count ? cap : 0);
 }
 
 int stage_force(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
@@ -1634,10 +1682,11 @@ int stage_move(aoslo_ctx* ctx, cudaStream_t s, double* d_pos, const uint8_t* d_s
 int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n,
                   const double* d_gt, int n_gt, bool gt_list_ready, bool p_list_ready, const void* d_Rb,
                   int field_dtype, int H, int W, int bx, int by, int iteration, aoslo_metrics_record* d_rec,
-                  double* d_p2g, double* d_g2p, const int* d_n) {
+                  double* d_p2g, double* d_g2p, const int* d_n, const int* d_n_gt, int* d_rec_idx,
+                  const int* d_iteration) {
     if (n > ctx->cap || n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
     if (n < 1 || n_gt < 1) return AOSLO_ERR_INVALID;
-    if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, nullptr));
+    if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, d_n_gt));
     if (!p_list_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
     // one pass: particle -> nearest GT ("gt_to_particles", :322) and GT -> nearest particle
     // ("particles_to_gt", :323), counts, moments and blob energy
@@ -1646,14 +1695,14 @@ int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uin
     MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
     if (field_dtype == AOSLO_F32)
         metrics_pass_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
-            view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
+            view_of(ctx->cl_g), link_view(ctx, ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
             (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, iteration,
-            d_rec, ctx->d_status);
+            d_rec, ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
     else
         metrics_pass_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
-            view_of(ctx->cl_g), link_view(ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
+            view_of(ctx->cl_g), link_view(ctx, ctx->lk_p, d_pos), (const double2*)d_pos, d_stable, n, d_n,
             (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, d_p2g, d_g2p, icount, partials, iteration,
-            d_rec, ctx->d_status);
+            d_rec, ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }

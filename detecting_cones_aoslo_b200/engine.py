@@ -46,10 +46,17 @@ class Engine:
         self._n_out = C.c_int(0)
         self._fields = {}
         self._in_bufs = None
+        self._raw_bufs = None
 
     def set_blocking_sync(self, enable=True):
         """Host waits sleep instead of spinning: for many concurrent lanes (one host thread each)."""
         check(lib.aoslo_ctx_set_blocking_sync(self._h, 1 if enable else 0), "aoslo_ctx_set_blocking_sync")
+
+    def set_tuning(self, **knobs):
+        """Implementation knobs of the library (k1_tma, pair_th, pair_occ, dtile_th, k1_kernel, no_graph);
+        results never depend on them."""
+        for k, v in knobs.items():
+            check(lib.aoslo_ctx_set_tuning(self._h, k.encode(), int(v)), "aoslo_ctx_set_tuning(%s)" % k)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -87,19 +94,30 @@ class Engine:
         pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array; gt_minus1: (n,2) float64 host
         array ALREADY shifted by -1 (the in-place side effect stays on the host).  Returns the padded
         image view (pitch multiple of 16) and the cropped / shifted GT, both on the device."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 2:
+            # the kernels take the raw bytes; the reference's skimage path would rescale other dtypes
+            # (img_as_float), which is not implemented -- refuse instead of reinterpreting the buffer
+            raise TypeError("img must be a 2-D uint8 array (got %s, ndim %d)" % (img.dtype, img.ndim))
         img = np.ascontiguousarray(img)
         H0, W0 = img.shape
         assert (0 <= region['x_min']) and (0 <= region['y_min'])                       # image_transformation.py:7
         assert (W0 > region['x_max']) and (H0 > region['y_max'])                       # image_transformation.py:8
-        d_raw = torch.as_tensor(img).to(self.device, non_blocking=True)
         g = np.ascontiguousarray(gt_minus1, dtype=np.float64).reshape(-1, 2)
-        d_gt_raw = torch.as_tensor(g).to(self.device, non_blocking=True)
+        if g.shape[0] > self.gt_cap:
+            raise MemoryError("GT capacity of the context exceeded")
+        # context-owned device staging (stable addresses, no allocation per call); pageable host arrays go
+        # through cudaMemcpyAsync's own staging, pinned ones (torch pin_memory) are true async copies
+        if self._raw_bufs is None or self._raw_bufs[0].numel() < img.size:
+            self._raw_bufs = (self.empty((img.size,), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
+        d_raw = self._raw_bufs[0][: img.size].view(H0, W0)
+        d_raw.copy_(torch.from_numpy(img), non_blocking=True)
+        d_gt_raw = self._raw_bufs[1][: g.shape[0]]
+        d_gt_raw.copy_(torch.from_numpy(g), non_blocking=True)
         pitch = (self.W + 15) // 16 * 16
         if self._in_bufs is None:          # context-owned: stable addresses (CUDA-graph replay in aoslo_run)
             self._in_bufs = (self.empty((self.H, pitch), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
         buf, d_gt = self._in_bufs
-        if g.shape[0] > self.gt_cap:
-            raise MemoryError("GT capacity of the context exceeded")
         check(lib.aoslo_prepare_inputs(self._h, self._stream(), self._p(d_raw), H0, W0, W0,
                                        int(region['x_min']), int(region['x_max']), int(region['y_min']),
                                        int(region['y_max']), int(boundary['x']), int(boundary['y']),
@@ -356,10 +374,14 @@ class Engine:
         recs = (_lib.MetricsRecord * max_records)()
         summ = _lib.RunSummary()
         ms = (C.c_float * 5)() if collect_times else None
-        pos = self.empty((self.cap, 2), torch.float64)
-        st = self.empty((self.cap,), torch.uint8)
         check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._pf(Rb), self._pf(grad), self._fdt(Rb),
-                            self._p(gt), gt.shape[0], recs, max_records, self._p(pos), self._p(st), C.byref(summ), ms),
+                            self._p(gt), gt.shape[0], recs, max_records, None, None, C.byref(summ), ms),
               "aoslo_run")
+        # the final particles are copied out AFTER the run, sized by its result (no capacity-sized output)
         n = summ.n_particles
-        return summ, [recs[i] for i in range(summ.n_records)], pos[:n], st[:n], (list(ms) if ms is not None else [0.0] * 5)
+        pos = self.empty((n, 2), torch.float64)
+        st = self.empty((n,), torch.uint8)
+        if n:
+            check(lib.aoslo_read_particles(self._h, self._stream(), self._p(pos), self._p(st), n),
+                  "aoslo_read_particles")
+        return summ, [recs[i] for i in range(summ.n_records)], pos, st, (list(ms) if ms is not None else [0.0] * 5)

@@ -4,10 +4,10 @@
         -> (result, time_spended)
 
 Same signature, config keys, result / time_spended keys, in-place GT mutation and exceptions
-as the reference.  Crop + mirror padding stay on the host (thin geometry); everything after
-that -- blobness field, gradient, seeding, thinning, gravity-field resampling, kNN pit force,
-move, deletion, metrics -- runs in hand-written sm_100a kernels, device resident, through
-libaoslo_b200's C ABI.  There is no CPU fallback.
+as the reference.  Only the GT "-1" shift (a side effect on the caller's array) happens on the host;
+np.round, crop and mirror padding, the blobness field, gradient, seeding, thinning, gravity-field
+resampling, kNN pit force, move, deletion and metrics run in hand-written sm_100a kernels, device
+resident, through libaoslo_b200's C ABI.  There is no CPU fallback.
 
 Extension keys (optional, absent == reference behaviour):
     tie_mode          'sklearn' (default; neighbour ties ordered like the reference's KD tree)
@@ -16,9 +16,8 @@ Extension keys (optional, absent == reference behaviour):
     blobness_scales   [1.0] (default) -- multi-scale extension
     early_stop        True (default; reference :381-382) | False (run all epoch_num iterations)
     engine_mode       'fused' (default: one aoslo_run call) | 'staged' (stage calls from Python)
-    collect_stage_times  True (default: the five `time_spended` buckets are measured) | False (zeros; lets
-                      aoslo_run replay its epoch loop from a cached CUDA graph when tie_mode='canonical' and
-                      early_stop=False)
+    collect_stage_times  True (default: the five `time_spended` buckets are measured) | False (zeros; saves
+                      the five one-thread time-stamp kernels per iteration of the canonical run graph)
 VERBOSE (matplotlib figures), write_gif and save_best_result_visualisation are visualisation
 side effects outside the accelerated path and are ignored.
 """

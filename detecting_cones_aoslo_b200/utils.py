@@ -9,6 +9,8 @@ to the device and its results back (`find_blobs` keeps everything device residen
 Extension: functions that search neighbours take `tie_mode` ('sklearn' = the reference's
 KD-tree tie order, the default; 'canonical' = (distance, index) order, the cell-list path).
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -17,21 +19,24 @@ from .engine import Engine
 
 DEFAULT_TIE_MODE = 'sklearn'
 _ENGINES = {}
+_ENGINES_LOCK = threading.Lock()
 
 
 def get_engine(H, W, n_particles=0, n_gt=0):
-    """Context cache keyed by the padded image shape (capacity = every pixel a particle)."""
+    """Context cache keyed by (device, thread, padded image shape); capacity = every pixel a particle.
+    A context is single-stream state, so concurrent threads get their own; an engine that is too small is
+    replaced in the cache but never closed here (another caller may still hold it -- it is released when the
+    last reference goes away)."""
     if not torch.cuda.is_available():
         raise RuntimeError("detecting_cones_aoslo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     dev = torch.cuda.current_device()
-    key = (dev, int(H), int(W))
-    eng = _ENGINES.get(key)
+    key = (dev, threading.get_ident(), int(H), int(W))
     need_p, need_g = max(int(H) * int(W), int(n_particles)), max(65536, int(n_gt))
-    if eng is None or eng.cap < need_p or eng.gt_cap < need_g:
-        if eng is not None:
-            eng.close()
-        eng = Engine(H, W, particle_capacity=need_p, gt_capacity=need_g, device=dev)
-        _ENGINES[key] = eng
+    with _ENGINES_LOCK:
+        eng = _ENGINES.get(key)
+        if eng is None or eng.cap < need_p or eng.gt_cap < need_g:
+            eng = Engine(H, W, particle_capacity=need_p, gt_capacity=need_g, device=dev)
+            _ENGINES[key] = eng
     return eng
 
 

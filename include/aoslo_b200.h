@@ -130,6 +130,10 @@ int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int particle_cap
 int aoslo_ctx_destroy(aoslo_ctx* ctx);
 int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear);
 int aoslo_ctx_capacity(aoslo_ctx* ctx);
+/* implementation knobs (defaults come from the environment once, at aoslo_ctx_create): "k1_tma" 0|1|2,
+ * "pair_th", "pair_occ", "dtile_th" (0 = automatic), "k1_kernel" 0 auto | 1 generic tile | 2 band | 3 f64 tile,
+ * "no_graph" 1 = run aoslo_run's canonical path eagerly (debugging / profiling).  Results do not depend on them. */
+int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value);
 /* 1: host-side waits of this context sleep on a blocking-sync event instead of spinning (use when many
  * contexts run concurrently, one host thread each); 0 (default): lowest-latency spinning sync */
 int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable);
@@ -227,12 +231,22 @@ int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const v
 
 /* ---- L5 whole run: pipeline_with_delitions.find_blobs (:12-403) after crop/pad.
  * Seeds, thins, resamples and runs the epoch loop with every stage on the device; returns the
- * per-evaluation metric records, the final particles and a summary.  Stage timings (ms, CUDA
- * events) in h_stage_ms[5]: dist_energy_calc, moving_particles, deleting_particles,
- * fix_resample, metrics_logging (the reference's `time_spended` keys, :165-171). */
+ * per-evaluation metric records, the final particles and a summary.  Stage timings (ms) in
+ * h_stage_ms[5] (may be NULL): dist_energy_calc, moving_particles, deleting_particles, fix_resample,
+ * metrics_logging (the reference's `time_spended` keys, :165-171).
+ * AOSLO_TIE_CANONICAL: the whole run is one cached CUDA graph (conditional WHILE / IF nodes for the thinning
+ * fixpoint, the early stop and the resample / metrics branches); the host synchronises once, at the end.
+ * All value parameters of `cfg` are uploaded per call, so runs that differ only in values (a sweep) share the
+ * graph; d_Rb, d_grad, d_gt must be stable addresses for the graph to be reused.
+ * AOSLO_TIE_SKLEARN: stage calls with one host round trip per kNN (host-built tree). */
 int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
               int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
               double* d_particles_out, uint8_t* d_stable_out, aoslo_run_summary* h_summary, float* h_stage_ms);
+
+/* final particles / stable flags of the last aoslo_run on this context (the first n rows, n <= summary.n_particles),
+ * copied device -> device on `stream`: lets the caller size its output after the run instead of passing
+ * capacity-sized buffers to aoslo_run (whose d_particles_out / d_stable_out may be NULL). */
+int aoslo_read_particles(aoslo_ctx* ctx, void* stream, double* d_particles_out, uint8_t* d_stable_out, int n);
 
 /* ---- host helper used by the sklearn-order kNN: builds sklearn's KDTree(leaf_size=1)
  * idx_array / node table on the HOST (std::nth_element, sklearn/neighbors/_partition_nodes.pyx). */

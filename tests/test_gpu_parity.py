@@ -4,10 +4,13 @@ oracle (oracle/aoslo_oracle.py) and the committed traces of the executed referen
 Tolerances (stated per assertion):
   * integer / index / decision outputs (seeds, kNN indices, deletion masks, particle
     positions in discrete mode, TP/FP/FN and the ratios derived from them): bit exact;
-  * f64 fields: 5e-14 absolute (CUDA's exp is 1 ulp, R_b ~ 5); f32 fields: 1e-4 of max|ref|
-    (BASELINE.json north_star tolerance);
+  * f64 fields: 5e-14 absolute (CUDA's exp is 1 ulp, R_b ~ 5); f32 fields: F32_TOL = 2e-5 ABSOLUTE on R_b
+    (values ~5, f32 ulp 4.8e-7) and on its gradient -- ~10x the measured f32 error (1.2e-6 / 1.5e-6)
+    and 25x tighter than BASELINE.json's north_star tolerance (1e-4 relative = 5e-4), which is asserted as well;
   * f64 forces: 1e-13 absolute; Chamfer sums: 1e-12 relative (different summation order).
 """
+import contextlib
+
 import numpy as np
 import pytest
 import torch
@@ -20,6 +23,30 @@ from trace_compare import compare_traces
 pytestmark = pytest.mark.gpu
 
 gpu_utils = pytest.importorskip("detecting_cones_aoslo_b200.utils")
+
+F32_TOL = 2e-5          # absolute, R_b and gradient (see the module docstring)
+K1_DEFAULTS = dict(k1_tma=1, pair_th=0, pair_occ=0, dtile_th=0, k1_kernel=0)
+K1_KERNELS = {"tile": 1, "band": 2, "dtile": 3}
+
+
+@contextlib.contextmanager
+def k1_tuning(shape, **knobs):
+    """Implementation knobs of the blobness kernels on the cached engine of `shape` (aoslo_ctx_set_tuning);
+    restored afterwards.  Results must not depend on them."""
+    eng = gpu_utils.get_engine(*shape)
+    eng.set_tuning(**knobs)
+    try:
+        yield eng
+    finally:
+        eng.set_tuning(**K1_DEFAULTS)
+
+
+def assert_f32_fields(rb, g, ref, gref):
+    assert np.isfinite(rb).all() and np.isfinite(g).all()
+    assert np.abs(rb - ref).max() <= F32_TOL, np.abs(rb - ref).max()
+    assert np.abs(g - gref).max() <= F32_TOL, np.abs(g - gref).max()
+    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()            # north_star: 1e-4 relative in fp32
+    assert np.abs(g - gref).max() <= 1e-4 * np.abs(gref).max()
 
 
 def _padded(cfg):
@@ -52,8 +79,9 @@ def test_blobness_f32_within_north_star_tolerance(zoo_field):
     cfg, img, gt, Rb, grad = zoo_field
     rb, g = gpu_utils.calc_blobness(img, cfg, dtype=np.float32, return_grad=True)
     assert rb.dtype == np.float32
-    assert np.abs(rb - Rb).max() <= 1e-4 * np.abs(Rb).max()
-    assert np.abs(g - grad).max() <= 1e-4 * np.abs(grad).max()
+    assert_f32_fields(rb, g, Rb, grad)
+    print("f32 field error on the shipped image: R_b %.3g, grad %.3g (abs)" % (np.abs(rb - Rb).max(),
+                                                                              np.abs(g - grad).max()))
 
 
 @pytest.mark.parametrize("shape", [(37, 53), (64, 64), (2, 2), (33, 2), (130, 97)])
@@ -69,72 +97,65 @@ def test_blobness_ragged_shapes(shape):
 
 @pytest.mark.parametrize("shape", [(37, 53), (64, 64), (2, 2), (33, 2), (130, 97), (300, 113), (17, 260), (70, 225)])
 def test_blobness_f32_fast_path_ragged_shapes(shape):
-    """The f32 column-marching kernel (strip / chunk seams, one-sided edges) against the f64 oracle."""
+    """The f32 path on ragged shapes (pair kernel, or the band kernel below 8 rows / columns) against the f64 oracle."""
     rng = np.random.default_rng(shape[0] * 7 + shape[1])
     img = rng.integers(0, 256, size=shape, dtype=np.uint8)
     ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
     gref = orc.calc_grad_field(ref, 'np_grad')
     rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
                                     dtype=np.float32, return_grad=True)
-    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()
-    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+    assert_f32_fields(rb, g, ref, gref)
 
 
 @pytest.mark.parametrize("shape", [(8, 8), (9, 130), (130, 9), (97, 229), (100, 229), (48, 117), (49, 118), (50, 119),
                                    (51, 120), (233, 341), (64, 224), (72, 225), (600, 700)])
 @pytest.mark.parametrize("variant", ["auto", "16:3", "20:3", "24:2", "28:2", "36:2"])
-def test_blobness_f32_pair_kernel_shapes_and_tilings(shape, variant, monkeypatch):
+def test_blobness_f32_pair_kernel_shapes_and_tilings(shape, variant):
     """The f32 pair kernel (two tiles per CTA, ghost-value borders, zero-filled staging) at every tile height /
     residency it is built for, on shapes that put the image border at every position of a tile pair (tile B
     partly or wholly outside, the right border inside the halo columns, one to seven tile columns)."""
+    knobs = {}
     if variant != "auto":
         th, occ = variant.split(":")
-        monkeypatch.setenv("AOSLO_PAIR_TH", th)
-        monkeypatch.setenv("AOSLO_PAIR_OCC", occ)
+        knobs = dict(pair_th=int(th), pair_occ=int(occ))
     rng = np.random.default_rng(shape[0] * 7919 + shape[1])
     img = rng.integers(0, 256, size=shape, dtype=np.uint8)
     ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
     gref = orc.calc_grad_field(ref, 'np_grad')
-    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
-                                    dtype=np.float32, return_grad=True)
-    assert np.isfinite(rb).all() and np.isfinite(g).all()
-    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()            # north_star: 1e-4 relative in fp32
-    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+    with k1_tuning(shape, **knobs):
+        rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                        dtype=np.float32, return_grad=True)
+    assert_f32_fields(rb, g, ref, gref)
 
 
 @pytest.mark.parametrize("shape", [(8, 8), (97, 229), (51, 120), (233, 341), (600, 700)])
 @pytest.mark.parametrize("tma", ["0", "2"])
 @pytest.mark.parametrize("th", ["24", "36"])
-def test_blobness_f32_pair_kernel_staging_and_store_variants(shape, tma, th, monkeypatch):
-    """AOSLO_K1_TMA = 0 (cp.async staging, plain stores) and 2 (TMA tensor loads AND stores, clipped at the image
+def test_blobness_f32_pair_kernel_staging_and_store_variants(shape, tma, th):
+    """k1_tma = 0 (cp.async staging, plain stores) and 2 (TMA tensor loads AND stores, clipped at the image
     border); the default (TMA loads, plain stores) is what every other f32 test runs."""
-    monkeypatch.setenv("AOSLO_K1_TMA", tma)
-    monkeypatch.setenv("AOSLO_PAIR_TH", th)
     rng = np.random.default_rng(shape[0] * 31 + shape[1])
     img = rng.integers(0, 256, size=shape, dtype=np.uint8)
     ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
     gref = orc.calc_grad_field(ref, 'np_grad')
-    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
-                                    dtype=np.float32, return_grad=True)
-    assert np.isfinite(rb).all() and np.isfinite(g).all()
-    assert np.abs(rb - ref).max() <= 1e-4 * np.abs(ref).max()
-    assert np.abs(g - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1.0)
+    with k1_tuning(shape, k1_tma=int(tma), pair_th=int(th)):
+        rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                        dtype=np.float32, return_grad=True)
+    assert_f32_fields(rb, g, ref, gref)
 
 
 @pytest.mark.parametrize("shape", [(8, 8), (9, 130), (130, 9), (97, 229), (49, 118), (51, 120), (233, 341), (600, 700)])
 @pytest.mark.parametrize("th", ["16", "24", "32", "48", "band"])
-def test_blobness_f64_tile_kernel_shapes_and_tilings(shape, th, monkeypatch):
+def test_blobness_f64_tile_kernel_shapes_and_tilings(shape, th):
     """The f64 tile kernel at every tile height, and the band kernel it replaced, against the oracle (5e-14:
     CUDA's exp is 1 ulp) with identical seed decisions."""
-    if th == "band":
-        monkeypatch.setenv("AOSLO_BLOBNESS_KERNEL", "band")
-    else:
-        monkeypatch.setenv("AOSLO_BLOBNESS_KERNEL", "dtile")
-        monkeypatch.setenv("AOSLO_DTILE_TH", th)
+    knobs = dict(k1_kernel=K1_KERNELS["band"]) if th == "band" else dict(k1_kernel=K1_KERNELS["dtile"], dtile_th=int(th))
     rng = np.random.default_rng(shape[0] * 104729 + shape[1])
     img = rng.integers(0, 256, size=shape, dtype=np.uint8)
     ref = orc.blobness_from_eigs(orc.hessian_eigs(img, 1.0), 'custom')
-    rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'}, return_grad=True)
+    with k1_tuning(shape, **knobs):
+        rb, g = gpu_utils.calc_blobness(img, {'blobness_formula': 'custom', 'gradient_type': 'np_grad'},
+                                        return_grad=True)
     assert np.abs(rb - ref).max() <= 5e-14
     assert np.abs(g - orc.calc_grad_field(ref, 'np_grad')).max() <= 5e-14
     assert np.array_equal(rb > 5.0, ref > 5.0)
@@ -167,7 +188,7 @@ def test_blobness_multiscale_extension(zoo_field):
     rb = gpu_utils.calc_blobness(img, cfg, scales=scales)
     assert np.abs(rb - ref).max() <= 1e-12
     rb32 = gpu_utils.calc_blobness(img, cfg, scales=scales, dtype=np.float32)
-    assert np.abs(rb32 - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(rb32 - ref).max() <= F32_TOL
 
 
 def test_errors_match_reference():
@@ -433,7 +454,13 @@ def test_find_blobs_mutates_gt_like_reference_and_f32_mode():
     np.testing.assert_array_equal(g, gt - 1.0)             # GT shifted by -1 in place (utils.py:16)
     cfg32 = configs.variant(configs.zoo_config(), field_dtype='f32', tie_mode='canonical')
     res, _ = find_blobs(cfg32, gt.copy(), img, None, False, False)
-    assert abs(res["dice_coeff_2"] - 0.9343) < 0.01         # f32 fields: statistically equivalent F1
+    # f32 fields flip a handful of the run's discrete decisions (2 pixels sit within 1e-6 of the seed threshold,
+    # SURVEY 0-4): not a parity mode; the particle count and F1 stay within 0.5 % / 0.003 of the f64 run
+    ref, _ = find_blobs(configs.variant(configs.zoo_config(), tie_mode='canonical'), gt.copy(), img, None, False, False)
+    assert abs(res["_summary"]["n_particles"] - ref["_summary"]["n_particles"]) <= 0.005 * ref["_summary"]["n_particles"]
+    assert abs(res["dice_coeff_2"] - ref["dice_coeff_2"]) < 0.003
+    with pytest.raises(TypeError):                          # non-uint8 images are refused, not reinterpreted
+        find_blobs(configs.main_config(), gt.copy(), img.astype(np.uint16), None, False, False)
 
 
 # ----------------------------------------------------------------------------------- more whole-run branches
@@ -622,34 +649,97 @@ def test_batch_of_frames_and_sweep_trials():
         np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
 
 
-def test_graph_replay_equals_eager_loop():
-    """aoslo_run replays the epoch loop from a cached CUDA graph when nothing in it needs the host
-    (canonical order, early stop off, stage timing off): same particles / records as the eager loop, on the
-    capture run, on replays, after a config change (re-capture) and for another frame of the same shape."""
+def _same_run(a, b):
+    np.testing.assert_array_equal(a["_final_particles"].cpu().numpy(), b["_final_particles"].cpu().numpy())
+    np.testing.assert_array_equal(a["_final_stable"].cpu().numpy(), b["_final_stable"].cpu().numpy())
+    assert a["_summary"] == b["_summary"]
+    for key in ("dice_coeff_1", "dice_coeff_2", "best_lsa_mean", "best_blobEn_mean"):
+        assert a[key] == b[key]
+
+
+@pytest.mark.parametrize("early_stop", [False, True])
+def test_run_graph_equals_eager_path(early_stop):
+    """aoslo_run in the canonical tie order is ONE cached CUDA graph (WHILE node for the thinning fixpoint;
+    unrolled epoch loop, or WHILE + IF nodes with the early stop).  It must give the same particles / records /
+    summary as the same kernels run eagerly with the loop conditions evaluated on the host (no_graph): on the
+    capture run, on replays, with and without the time-stamp kernels, after a VALUE change of the configuration
+    (same graph, new device parameters), after a STRUCTURAL change (another graph) and for another frame."""
+    from detecting_cones_aoslo_b200.engine import Engine
     from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
     from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    from detecting_cones_aoslo_b200 import _lib
     frames = [synth_aoslo(512, 512, 5.8, seed=s) for s in (5, 6)]
+    H = W = 511 + 30
+    eng_g = Engine(H, W)
+    eng_e = Engine(H, W)
+    eng_e.set_tuning(no_graph=1)
 
-    def run(img, gt, **over):
-        cfg = synth_config(512, 512, 5.8, boundary=15, epoch_num=9, early_stop=False, tie_mode='canonical', **over)
-        res, ts = find_blobs(cfg, gt.copy(), img, None, False, False)
+    def run(eng, img, gt, **over):
+        cfg = synth_config(512, 512, 5.8, boundary=15, epoch_num=9, early_stop=early_stop, tie_mode='canonical', **over)
+        res, ts = find_blobs(cfg, gt.copy(), img, None, False, False, engine=eng)
         return res, ts
 
     for img, gt in frames:
-        eager, ts_e = run(img, gt, collect_stage_times=True)
+        eager, ts_e = run(eng_e, img, gt, collect_stage_times=True)
         assert sum(ts_e.values()) > 0
-        for _ in range(3):                                   # capture, then two replays
-            g, ts_g = run(img, gt, collect_stage_times=False)
-            np.testing.assert_array_equal(g["_final_particles"].cpu().numpy(), eager["_final_particles"].cpu().numpy())
-            np.testing.assert_array_equal(g["_final_stable"].cpu().numpy(), eager["_final_stable"].cpu().numpy())
-            assert g["_summary"] == eager["_summary"]
-            for key in ("dice_coeff_1", "dice_coeff_2", "best_lsa_mean", "best_blobEn_mean"):
-                assert g[key] == eager[key]
-        # another configuration on the same context: the cached graph must not be reused
-        e2, _ = run(img, gt, collect_stage_times=True, threshhold_dist_del=4.2, lambda_dist=0.3)
-        g2, _ = run(img, gt, collect_stage_times=False, threshhold_dist_del=4.2, lambda_dist=0.3)
-        np.testing.assert_array_equal(g2["_final_particles"].cpu().numpy(), e2["_final_particles"].cpu().numpy())
-        assert g2["dice_coeff_2"] == e2["dice_coeff_2"]
+        assert eager["_summary"]["n_iterations"] == 9 or early_stop
+        for times in (False, True, False):                   # capture, another graph (time stamps), replay
+            l0 = _lib.lib.aoslo_launch_count()
+            g, ts_g = run(eng_g, img, gt, collect_stage_times=times)
+            assert _lib.lib.aoslo_launch_count() - l0 > 50   # the executed graph nodes are counted
+            _same_run(g, eager)
+            assert (sum(ts_g.values()) > 0) == times
+        # value parameters only: the cached graph is reused with new device parameters
+        e2, _ = run(eng_e, img, gt, threshhold_dist_del=4.2, lambda_dist=0.3, init_blob_threshold=4.99,
+                    particle_call_threshold=0.2, mu_dist_func=5.7)
+        g2, _ = run(eng_g, img, gt, collect_stage_times=False, threshhold_dist_del=4.2, lambda_dist=0.3,
+                    init_blob_threshold=4.99, particle_call_threshold=0.2, mu_dist_func=5.7)
+        _same_run(g2, e2)
+        assert g2["_summary"] != eager["_summary"]
+        # structural parameters: neighbour count class, window, frequencies
+        over = dict(dist_n_neighbours=5, particle_call_window=6, fix_particles_frequency=5, metric_measure_freq=2)
+        e3, _ = run(eng_e, img, gt, **over)
+        g3, _ = run(eng_g, img, gt, collect_stage_times=False, **over)
+        _same_run(g3, e3)
+    eng_g.close()
+    eng_e.close()
+
+
+def test_run_capacity_overflow_is_reported_not_corrupting():
+    """A context with too small a particle capacity: the device count is clamped where it is produced, the run
+    reports MemoryError, and nothing is written past the buffers (a later run on a proper context still agrees
+    with the oracle; CUDA reports no sticky error)."""
+    from detecting_cones_aoslo_b200.engine import Engine
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    cfg = configs.variant(configs.zoo_config(), tie_mode='canonical')
+    H = 515 + 34
+    W = 518 + 34
+    # (a) capacity below the seed count (31 876); (b) 1 301 seeds at threshold 5.08 fit, the third resample of the
+    # loop (3 124 particles, oracle trajectory 1 316 -> 2 272 -> 3 124) overflows the append
+    for cap, thr in ((1000, 5.0), (3000, 5.08)):
+        small = Engine(H, W, particle_capacity=cap)
+        for early_stop in (True, False):
+            c = configs.variant(cfg, init_blob_threshold=thr, early_stop=early_stop, collect_stage_times=False)
+            with pytest.raises(MemoryError):
+                find_blobs(c, gt.copy(), img, None, False, False, engine=small)
+        small.close()
+    torch.cuda.synchronize()
+    ref, _ = orc.find_blobs(dict(cfg), gt.copy(), img, None, False, False, tie_mode='canonical')
+    res, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
+
+
+def test_calc_distances_wrapper_matches_reference_layout():
+    """utils.calc_distances (reference utils.py:26-40): kNN self-query, column 0 dropped, vec[i, j] = p_i - p_nbr."""
+    rng = np.random.default_rng(11)
+    p = _lattice(rng, 700, 60)
+    for tie_mode in ("canonical", "sklearn"):
+        for k in (1, 3):
+            idx_ref, vec_ref = orc.calc_distances(p, p, k, tie_mode=tie_mode)
+            idx, vec = gpu_utils.calc_distances(p, p, k, tie_mode=tie_mode)
+            np.testing.assert_array_equal(idx, idx_ref)
+            np.testing.assert_array_equal(vec, vec_ref)
 
 
 def test_classification_sets_match_visualize_all(zoo_field):
