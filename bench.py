@@ -12,15 +12,17 @@ per-run metric records at the end of the timed region.  The single-run latency i
 
 value     runs/s with the frame and GT already resident in HBM (timed: aoslo_blobness + aoslo_run)
 e2e       runs/s through the reference-facing entry point find_blobs(cur_config, GT_data, img, ...)
-          with HOST NumPy buffers: crop/pad on the host, host->device copies and the device->host
-          read of the metric records are inside the timed region
-roofline  the fused blobness kernel (K1), the HBM-designed kernel of the path, in the f32 form north_star states the
-          field tolerance for (13 B/px), timed with CUDA events around 32 back-to-back launches over 8 distinct
-          frames (> L2), against MEASURED_PEAKS.json; roofline_f64_in_step is the f64 parity form the timed step
-          runs, timed inside the single-lane latency pass
+          with HOST (pinned) NumPy buffers: host->device copies of the raw frame and GT, crop/pad on the device
+          and the device->host read of the metric records are inside the timed region
+roofline  the fused blobness kernel (K1) in the f64 form the timed step launches (25 B/px), CUDA events around the
+          kernel inside the timed single-lane step, against MEASURED_PEAKS.json; roofline_f32 is the f32 form
+          north_star states the field tolerance for (13 B/px), timed around 32 back-to-back launches over 8
+          distinct frames (> L2)
+faithful  the drop-in's default mode (sklearn KD-tree tie order, early stop on), end to end
 cpu_baseline / --impl reference
           the CPU oracle (port of the reference's NumPy/SciPy/scikit-learn pipeline; the reference
-          is Python and cannot travel to the GPU box) on a bounded sample of the same workload
+          is Python and cannot travel to the GPU box) on the SAME full 2048^2 frame, configuration, tie order
+          and iteration count: 1 process (cpu_baseline) resp. one process per core, <= 16 (--impl reference)
 """
 import argparse
 import json
@@ -39,7 +41,8 @@ SIZE = 2048
 PITCH = 5.8
 EPOCHS = 30
 BOUNDARY = 15
-SAMPLE = 1024           # edge of the CPU baseline's bounded sample (a crop of the same frame)
+TIE_MODE = 'canonical'  # both arms: (distance, index) neighbour order; the as-is reference order ('sklearn') is
+EARLY_STOP = False      # reported beside it as `faithful`; all M iterations run in both arms
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -52,8 +55,8 @@ def workload_name():
 def make_workload(rank, size=SIZE):
     from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
     img, gt = synth_aoslo(size, size, PITCH, seed=2022 + rank)
-    cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS, early_stop=False,
-                       tie_mode='canonical', field_dtype='f64', collect_stage_times=False)
+    cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS, early_stop=EARLY_STOP,
+                       tie_mode=TIE_MODE, field_dtype='f64', collect_stage_times=False)
     return img, gt, cfg
 
 
@@ -134,46 +137,79 @@ def measured_hbm_peak():
 
 
 # --------------------------------------------------------------------------------------- CPU arm
-def cpu_sample_run(size=SAMPLE, epochs=EPOCHS):
-    """One oracle run on the bounded sample: the top-left size x size crop of rank 0's frame."""
+def cpu_full_run(seed_index=0, tie_mode=TIE_MODE, early_stop=EARLY_STOP):
+    """One oracle run (NumPy / SciPy / scikit-learn port of the reference's find_blobs, closed-form pit energy) on
+    the SAME 2048^2 frame, configuration, tie order and iteration count as the GPU arm."""
     from oracle import aoslo_oracle as orc
-    from detecting_cones_aoslo_b200.synth import synth_config
-    img, gt, _ = make_workload(0)
-    img = np.ascontiguousarray(img[:size, :size])
-    gt = gt[(gt[:, 0] < size) & (gt[:, 1] < size)].copy()
-    cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=epochs)
+    img, gt, cfg = make_workload(seed_index)
+    ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode', 'field_dtype', 'collect_stage_times')}
     t = time.perf_counter()
-    res, _ = orc.find_blobs(cfg, gt, img, None, False, False, tie_mode='sklearn', early_stop=False)
-    return time.perf_counter() - t, res
+    res, ts = orc.find_blobs(ocfg, gt, img, None, False, False, tie_mode=tie_mode, early_stop=early_stop)
+    return time.perf_counter() - t, res, ts
 
 
-def _cpu_worker(_):
+def _cpu_worker(i):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    return cpu_sample_run()[0]
+    return cpu_full_run(0)[0]
 
 
-def cpu_baseline(processes=1):
-    """runs/s of the CPU oracle, scaled from the sample by pixel count ((SIZE/SAMPLE)^2 samples per run)."""
-    scale = (SIZE / SAMPLE) ** 2
+def cpu_side_rows():
+    """The two extra CPU rows SURVEY 8d asks for: the blobness stage alone (MPix/s next to `blobness_mpix_s`) and the
+    reference AS SHIPPED, whose pit energy builds two scipy.stats frozen distributions per call (utils.py:82-87): the
+    per-call cost is measured on 2 000 calls and multiplied by the number of calls the run makes."""
+    from oracle import aoslo_oracle as orc
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs
+    import scipy.stats
+    img, gt, cfg = make_workload(0)
+    pimg, _ = prepare_inputs(cfg, gt.copy(), img)
+    best = 1e9
+    for _ in range(2):
+        t = time.perf_counter()
+        rb = orc.calc_blobness(pimg, 'custom')
+        orc.calc_grad_field(rb, 'np_grad')
+        best = min(best, time.perf_counter() - t)
+    d = np.linspace(0.5, 12.0, 2000)
+    t = time.perf_counter()
+    for x in d:                                          # energy_pit_func2 as the reference ships it
+        ef = scipy.stats.expon(cfg['lambda_dist_func'])
+        nf = scipy.stats.norm(cfg['mu_dist_func'], cfg['sigma_dist_func'])
+        _ = ef.pdf(x) - nf.pdf(x) + 0.48 if x <= cfg['mu_dist_func'] else ef.pdf(x) + nf.pdf(x) - 0.48
+    per_call = (time.perf_counter() - t) / d.size
+    return {"blobness_mpix_s": pimg.size / best / 1e6, "blobness_seconds": best,
+            "as_shipped_energy_call_us": per_call * 1e6}
+
+
+def cpu_baseline(processes=1, side_rows=False):
+    """runs/s of the CPU oracle on the full frame: `processes` concurrent single-threaded runs."""
     if processes <= 1:
-        dt = cpu_sample_run()[0]
-        runs_per_s = 1.0 / (dt * scale)
+        dt, res, ts = cpu_full_run(0)
+        runs_per_s = 1.0 / dt
+        n_calls = res.get('n_energy_calls')
     else:
         import multiprocessing as mp
         ctx = mp.get_context("spawn")
         t = time.perf_counter()
         with ctx.Pool(processes) as pool:
             pool.map(_cpu_worker, range(processes))
-        wall = time.perf_counter() - t
-        dt = wall
-        runs_per_s = processes / (wall * scale)
-    return {"value": runs_per_s, "unit": "runs/s", "cores": processes, "kind": "port",
-            "sample": "CPU oracle (NumPy/SciPy/scikit-learn port of the reference, sklearn KD-tree kNN) on the "
-                      "%dx%d top-left crop of the %dx%d frame, same config, M=%d; %.1f s per sample%s, runs/s = "
-                      "1 / (t * %d) by pixel count" % (SAMPLE, SAMPLE, SIZE, SIZE, EPOCHS, dt,
-                                                      " wall for %d concurrent processes" % processes
-                                                      if processes > 1 else "", int(scale)),
-            "seconds_per_sample": dt}
+        dt = time.perf_counter() - t
+        runs_per_s = processes / dt
+        n_calls = None
+    out = {"value": runs_per_s, "unit": "runs/s", "cores": processes, "kind": "port",
+           "sample": "CPU oracle (NumPy/SciPy/scikit-learn port of the reference's find_blobs, closed-form pit "
+                     "energy, %s tie order) on the full %dx%d frame of the GPU arm, same config, M=%d (early stop "
+                     "off): 1 whole run per process, %d concurrent process(es), %.1f s wall"
+                     % (TIE_MODE, SIZE, SIZE, EPOCHS, processes, dt),
+           "seconds_per_sample": dt}
+    if side_rows:
+        rows = cpu_side_rows()
+        out["blobness_mpix_s"] = rows["blobness_mpix_s"]
+        if n_calls:
+            shipped_s = dt + n_calls * rows["as_shipped_energy_call_us"] * 1e-6
+            out["as_shipped"] = {"value": 1.0 / shipped_s, "unit": "runs/s",
+                                 "how": "closed-form run time + %d energy_pit_func2 calls x %.0f us (two scipy.stats "
+                                        "frozen distributions per call, utils.py:82-87; measured on 2000 calls)"
+                                        % (n_calls, rows["as_shipped_energy_call_us"])}
+    return out
 
 
 def run_reference(args):
@@ -183,9 +219,7 @@ def run_reference(args):
     procs = max(1, min(os.cpu_count() or 1, 16))
     t0 = time.perf_counter()
     vals = []
-    for _ in range(max(1, args.warmup) if args.warmup < 1 else 0):
-        pass
-    steps = max(1, min(args.steps, 2))          # each step is a bounded CPU sample; keep the arm to minutes
+    steps = max(1, min(args.steps, 2))          # each step = `procs` whole 2048^2 CPU runs (~2 min); keep the arm to minutes
     base = None
     for _ in range(steps):
         base = cpu_baseline(processes=procs)
@@ -257,12 +291,13 @@ class Lane:
         self.last = (summ, recs, ms)
         return summ
 
-    def run_e2e(self):
-        """the reference-facing call with HOST buffers (crop/pad, H2D, run, D2H of the records)."""
+    def run_e2e(self, **over):
+        """the reference-facing call with HOST buffers (H2D of the raw frame + GT, device crop/pad, run, D2H of the
+        records)."""
         from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
         with self.torch.cuda.stream(self.stream):
             np.copyto(self.gt_scratch, self.gt)
-            res, _ = find_blobs(dict(self.cfg), self.gt_scratch, self.img, None, False, False, engine=self.eng)
+            res, _ = find_blobs(dict(self.cfg, **over), self.gt_scratch, self.img, None, False, False, engine=self.eng)
         return res
 
 
@@ -459,7 +494,41 @@ def run_gpu(args):
         if i >= 2:
             two_ms.append(a.elapsed_time(b) / (NB * REP))
     k1_f32_two_ms = float(np.mean(two_ms))
-    del s_img, s_rb, s_g
+    # the f64 form (the kernel the timed step runs), same protocol: 32 back-to-back launches over 8 distinct frames
+    d_rb = [eng.field(H, W, torch.float64) for _ in range(NB)]
+    d_g = [eng.field(H, W, torch.float64, 2) for _ in range(NB)]
+    f64_ms = []
+    for i in range(2 + 3):
+        evict_l2()
+        torch.cuda._sleep(6000000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(REP):
+            for j in range(NB):
+                eng.blobness(s_img[j], 'custom', 'np_grad', (1.0,), torch.float64, out=(d_rb[j], d_g[j]))
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            f64_ms.append(a.elapsed_time(b) / (NB * REP))
+    k1_f64_stream_ms = float(np.mean(f64_ms))
+    del s_img, s_rb, s_g, d_rb, d_g
+
+    # ---- the as-is reference semantics: sklearn KD-tree tie order (host-built trees, one round trip per kNN) and
+    # the early stop on -- the drop-in's default mode, the one the golden traces of the executed reference pin
+    faithful = None
+    if not args.no_faithful:
+        fo = dict(tie_mode='sklearn', early_stop=True)
+        lane0.run_e2e(**fo)
+        f_lat = [timed_step(lambda ln: ln.run_e2e(**fo), [lane0]) for _ in range(2)]
+        f_all = [timed_step(lambda ln: ln.run_e2e(**fo), lanes) for _ in range(2)]
+        fres = lane0.run_e2e(**fo)
+        faithful = {"mode": "tie_mode='sklearn' (the reference's KD-tree neighbour order), early stop on: find_blobs' "
+                            "default; end to end with host buffers",
+                    "latency_ms_single_run": float(np.mean(f_lat)),
+                    "value": B / (float(np.mean(f_all)) / 1e3), "unit": "runs/s (this rank, %d lanes)" % B,
+                    "iterations": int(fres["_summary"]["n_iterations"]),
+                    "n_particles_final": int(fres["_summary"]["n_particles"]),
+                    "dice_2": float(fres["dice_coeff_2"])}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -484,29 +553,30 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": int(lane0.h2d * B),
                     "d2h_bytes_per_step": int(d2h * B), "latency_ms_single_run": float(np.mean(e2e_lat))},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "blobness_pair_kernel (K1 f32: fused Gaussian / Hessian / eigenvalues / blobness / "
-                                   "gradient, 13 B/px)",
-                         "bound": "hbm", "achieved": bytes_f32 / (k1_f32_stream_ms / 1e3) / 1e9, "peak": peak,
-                         "unit": "GB/s", "frac": bytes_f32 / (k1_f32_stream_ms / 1e3) / 1e9 / peak,
-                         "traffic": k1_dram_traffic("f32"), "peak_source": peak_src,
-                         "traffic_note": "ncu dram bytes of one launch (profiles/r01_k1_ncu.md); below the algorithmic "
-                                         "bytes because most of the output is still in the 126 MB L2 at kernel end",
-                         "algorithmic_bytes_per_launch": bytes_f32, "ms_per_launch": k1_f32_stream_ms,
-                         "ms_single_launch_l2_flushed": k1_f32_ms,
-                         "ms_per_frame_two_streams": k1_f32_two_ms,
-                         "frac_two_streams": bytes_f32 / (k1_f32_two_ms / 1e3) / 1e9 / peak,
-                         "frac_single_launch": bytes_f32 / (k1_f32_ms / 1e3) / 1e9 / peak,
-                         "timed": "CUDA events on the launch stream around 32 back-to-back launches over 8 distinct "
-                                  "frames (working set 450 MB > L2), GPU parked while the host enqueues",
-                         "measured_limiter": "L1 data pipe (shared-memory wavefronts ~1 per pixel), not HBM: "
-                                             "profiles/r01_k1_ncu.md"},
-            "roofline_f64_in_step": {
-                "kernel": "blobness_dtile_kernel (K1 f64, the parity mode the timed step runs: 25 B/px)",
+            "roofline": {
+                "kernel": "blobness_dtile_kernel (K1 f64: fused Gaussian / Hessian / eigenvalues / blobness / gradient; "
+                          "the kernel the timed step launches; 25 B/px = 1 B u8 in + 8 B R_b + 16 B grad out)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": k1_dram_traffic("f64"), "algorithmic_bytes_per_launch": bytes_f64, "ms_per_launch": k1_ms,
+                "traffic": k1_dram_traffic("f64"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_f64, "ms_per_launch": k1_ms,
                 "share_of_step": k1_ms / latency_ms,
-                "timed": "CUDA events on the launch stream inside the single-lane latency pass",
-                "measured_limiter": "FP64 pipe (software exp / div / sqrt per pixel), see profiles/r01_k1_ncu.md"},
+                "timed": "CUDA events on the launch stream around the kernel INSIDE the timed single-lane step",
+                "ms_per_launch_back_to_back": k1_f64_stream_ms,
+                "frac_back_to_back": bytes_f64 / (k1_f64_stream_ms / 1e3) / 1e9 / peak,
+                "measured_limiter": "FP64 pipe (exp / division / square root in FP64 per pixel), see profiles/"},
+            "roofline_f32": {
+                "kernel": "blobness_pair_kernel (K1 in f32 storage, the form north_star states the field tolerance "
+                          "for: 13 B/px); NOT in the timed step (f32 fields flip discrete decisions of the run)",
+                "bound": "hbm", "achieved": bytes_f32 / (k1_f32_stream_ms / 1e3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": bytes_f32 / (k1_f32_stream_ms / 1e3) / 1e9 / peak,
+                "traffic": k1_dram_traffic("f32"),
+                "algorithmic_bytes_per_launch": bytes_f32, "ms_per_launch": k1_f32_stream_ms,
+                "ms_single_launch_l2_flushed": k1_f32_ms,
+                "ms_per_frame_two_streams": k1_f32_two_ms,
+                "frac_two_streams": bytes_f32 / (k1_f32_two_ms / 1e3) / 1e9 / peak,
+                "frac_single_launch": bytes_f32 / (k1_f32_ms / 1e3) / 1e9 / peak,
+                "timed": "CUDA events on the launch stream around 32 back-to-back launches over 8 distinct "
+                         "frames (working set 450 MB > L2), GPU parked while the host enqueues"},
             "blobness_mpix_s": {"f32": H * W / (k1_f32_stream_ms / 1e3) / 1e6, "f64": H * W / (k1_ms / 1e3) / 1e6,
                                 "f32_single_launch": H * W / (k1_f32_ms / 1e3) / 1e6,
                                 "f32_ms": k1_f32_stream_ms, "f32_single_launch_ms": k1_f32_ms},
@@ -514,8 +584,10 @@ def run_gpu(args):
                                              'fix_resample', 'metrics_logging'], [float(x) for x in stage_ms])),
             "last_run": {"dice_1": float(gathered[0][0][3]), "dice_2": float(gathered[0][0][4])},
         }
+        if faithful is not None:
+            line["faithful"] = faithful
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(processes=1)
+            line["cpu_baseline"] = cpu_baseline(processes=1, side_rows=True)
         print(json.dumps(line))
     pool.shutdown()
     if world > 1:
@@ -532,6 +604,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="frames run concurrently per step (lanes per GPU); 0 = min(8, host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-faithful", action="store_true", help="skip the sklearn-order / early-stop leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

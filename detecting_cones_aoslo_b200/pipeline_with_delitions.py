@@ -202,6 +202,7 @@ def _run_fused(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_id
                         rec.n_gt, rec.n_particles, rec.n_stable)
     result['_final_particles'] = pos
     result['_final_stable'] = st
+    result['_records'] = recs
     result['_summary'] = {k: getattr(summ, k) for k, _ in summ._fields_}
     return {k: ms[i] / 1e3 for i, k in enumerate(TIME_KEYS)}
 

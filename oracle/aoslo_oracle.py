@@ -425,6 +425,7 @@ def find_blobs(cur_config, GT_data, img, img_colorful=None, VERBOSE=False, USE_W
         trace.add('grad', R_b=R_b, grad=blobness_grad)
 
     particles = initialize_high_prop_location(R_b, cur_config['init_blob_threshold'], img.shape, cur_config)
+    result['n_seeds'] = int(particles.shape[0])            # oracle-only diagnostics
     if trace is not None:
         trace.add('seeds', particles=np.array(particles))
     stable = [0] * particles.shape[0]
@@ -469,6 +470,9 @@ def find_blobs(cur_config, GT_data, img, img_colorful=None, VERBOSE=False, USE_W
             if trace is not None:
                 trace.add('force_exp', particles=np.array(particles), force=force, modules=modules)
         elif cur_config['dist_energy_type'] == 'pit':
+            # oracle-only diagnostics: energy_pit_func2 calls the reference's Python loop makes here (utils.py:117-127)
+            result['n_energy_calls'] = result.get('n_energy_calls', int(cur_config['reception_field_size']) ** 2) + \
+                (len(stable) - int(np.sum(stable))) * int(cur_config['dist_n_neighbours'])
             force, modules = calc_dist_energy_pit_optim(
                 particles, stable, cur_config['dist_n_neighbours'], cur_config['mu_dist_func'],
                 cur_config['sigma_dist_func'], cur_config['lambda_dist_func'], tie_mode)
@@ -509,6 +513,7 @@ def find_blobs(cur_config, GT_data, img, img_colorful=None, VERBOSE=False, USE_W
                 result['best_lsa_mean'] = lsa_mean
             if result['best_blobEn_mean'] < np.mean(blob_energy):
                 result['best_blobEn_mean'] = np.mean(blob_energy)
+            result['last_metrics'] = {t: dict(v) for t, v in pm.items()}      # oracle-only diagnostics
             if trace is not None:                          # reference call order (:325, :329, :349)
                 trace.add('blob_energy', energy=np.array(blob_energy))
                 trace.add('acc', particles=np.array(particles), gt=np.array(GT_data),

@@ -622,6 +622,39 @@ def test_full_size_run_properties(size):
                        'metrics_logging'}
 
 
+@pytest.mark.slow
+@pytest.mark.parametrize("size,tie_mode,epochs,early_stop", [
+    (1024, "canonical", 12, False), (1024, "sklearn", 30, True),
+    (2048, "canonical", 8, False), (2048, "sklearn", 8, True),
+])
+def test_benchmark_size_run_matches_oracle(size, tie_mode, epochs, early_stop):
+    """The BENCHMARK frame (bench.py: synthetic lattice, pitch 5.8, seed 2022, boundary 15, config_zoo values) at
+    1024^2 and at the full 2048^2, against the CPU oracle in both tie orders: identical final particles and
+    stable flags, identical iteration count, bit-exact TP / FP / FN / dice at both radii.  (~145 k particles
+    and 695 k seeds at 2048^2; the oracle needs 20-60 s per case.)"""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = synth_aoslo(size, size, 5.8, seed=2022)
+    cfg = synth_config(size, size, 5.8, boundary=15, epoch_num=epochs, early_stop=early_stop, tie_mode=tie_mode,
+                       collect_stage_times=False)
+    ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode', 'collect_stage_times')}
+    ref, _ = orc.find_blobs(ocfg, gt.copy(), img, None, False, False, tie_mode=tie_mode, early_stop=early_stop)
+    res, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
+    np.testing.assert_array_equal(res["_final_stable"].cpu().numpy(), ref["final_stable"])
+    assert res["_summary"]["n_iterations"] == ref["n_iterations"]
+    assert res["_summary"]["n_seeds"] == ref["n_seeds"]
+    for key in ("dice_coeff_1", "dice_coeff_2"):
+        assert res[key] == ref[key]
+    np.testing.assert_allclose(res["best_lsa_mean"], ref["best_lsa_mean"], rtol=1e-12)
+    np.testing.assert_allclose(res["best_blobEn_mean"], ref["best_blobEn_mean"], rtol=1e-13)
+    # the last metrics evaluation, count by count
+    last = ref['last_metrics']
+    rec = res["_records"][-1]
+    for j, t in enumerate(("1", "2")):
+        assert (rec.tp[j], rec.fp[j], rec.fn[j]) == (last[t]['TP'], last[t]['FP'], last[t]['FN'])
+
+
 def test_batch_of_frames_and_sweep_trials():
     """configs 4/5 in miniature: a batch of 512^2 frames and sweep trials on one image through the
     sharded runner (1 rank), each record equal to the oracle's result for that unit."""
