@@ -37,26 +37,50 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SIZE = 2048
-PITCH = 5.8
-EPOCHS = 30
 BOUNDARY = 15
 TIE_MODE = 'canonical'  # both arms: (distance, index) neighbour order; the as-is reference order ('sklearn') is
 EARLY_STOP = False      # reported beside it as `faithful`; all M iterations run in both arms
 FALLBACK_HBM_GBS = 6650.0
 
+# BASELINE.json configs.  `default` is the one the metric is quoted on ("detection runs/s, full pipeline, 2048^2
+# img"); cfg2 / cfg3 are configs[1] / [2]; `batch` / `sweep` (configs[3] / [4]) run through sweep.UnitRunner.
+WORKLOADS = {
+    'default': dict(size=2048, pitch=5.8, epochs=30, scales=(1.0,), lanes=8,
+                    metric="detection runs/s (full pipeline, 2048^2 image)"),
+    'cfg2': dict(size=1024, pitch=11.0, epochs=100, scales=(1.0, 1.5, 2.0, 2.5, 3.0), lanes=8,
+                 metric="detection runs/s (cfg2: 1024^2, 5 blobness scales, M=100)"),
+    'cfg3': dict(size=4096, pitch=11.4, epochs=30, scales=(1.0,), lanes=2,
+                 metric="detection runs/s (cfg3: 4096^2 montage)"),
+    'batch': dict(size=512, pitch=5.8, epochs=30, scales=(1.0,), lanes=8, units=256,
+                  metric="frames/s (cfg4: batch of 256 synthetic 512^2 frames, sharded by image)"),
+    'sweep': dict(size=2048, pitch=5.8, epochs=30, scales=(1.0,), lanes=8, units=1024,
+                  metric="trials/s (cfg5: 1024 sweep trials of the sweep_config_new.yaml space on one 2048^2 image)"),
+}
+WL = WORKLOADS['default']
+SIZE, PITCH, EPOCHS = WL['size'], WL['pitch'], WL['epochs']
+
+
+def select_workload(name):
+    global WL, SIZE, PITCH, EPOCHS
+    WL = WORKLOADS[name]
+    SIZE, PITCH, EPOCHS = WL['size'], WL['pitch'], WL['epochs']
+
 
 def workload_name():
+    sc = "" if len(WL['scales']) == 1 else ", blobness scales %s" % (list(WL['scales']),)
     return ("synthetic %dx%d AOSLO-like cone lattice (pitch %.1f px, seed 2022+rank), config_zoo, boundary %d, "
-            "k=3, M=%d iterations (early stop off), f64 fields, canonical tie order"
-            % (SIZE, SIZE, PITCH, BOUNDARY, EPOCHS))
+            "k=3, M=%d iterations (early stop off), f64 fields, canonical tie order%s"
+            % (SIZE, SIZE, PITCH, BOUNDARY, EPOCHS, sc))
 
 
-def make_workload(rank, size=SIZE):
+def make_workload(rank, size=None):
     from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    size = size or SIZE
     img, gt = synth_aoslo(size, size, PITCH, seed=2022 + rank)
     cfg = synth_config(size, size, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS, early_stop=EARLY_STOP,
                        tie_mode=TIE_MODE, field_dtype='f64', collect_stage_times=False)
+    if len(WL['scales']) > 1:
+        cfg['blobness_scales'] = tuple(WL['scales'])
     return img, gt, cfg
 
 
@@ -142,9 +166,11 @@ def cpu_full_run(seed_index=0, tie_mode=TIE_MODE, early_stop=EARLY_STOP):
     the SAME 2048^2 frame, configuration, tie order and iteration count as the GPU arm."""
     from oracle import aoslo_oracle as orc
     img, gt, cfg = make_workload(seed_index)
-    ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode', 'field_dtype', 'collect_stage_times')}
+    ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode', 'field_dtype', 'collect_stage_times',
+                                                      'blobness_scales')}
     t = time.perf_counter()
-    res, ts = orc.find_blobs(ocfg, gt, img, None, False, False, tie_mode=tie_mode, early_stop=early_stop)
+    res, ts = orc.find_blobs(ocfg, gt, img, None, False, False, tie_mode=tie_mode, early_stop=early_stop,
+                             scales=tuple(WL['scales']))
     return time.perf_counter() - t, res, ts
 
 
@@ -226,7 +252,7 @@ def run_reference(args):
         vals.append(base["value"])
     v = float(np.mean(vals))
     line = {
-        "impl": "reference", "metric": "detection runs/s (full pipeline, 2048^2 image)", "value": v,
+        "impl": "reference", "metric": WL['metric'], "value": v,
         "unit": "runs/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
         "ms_per_step": base["seconds_per_sample"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
@@ -280,8 +306,8 @@ class Lane:
             if time_k1:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self.eng.blobness(self.d_img, self.cfg['blobness_formula'], self.cfg['gradient_type'], (1.0,),
-                              torch.float64, out=(self.Rb, self.grad))
+            self.eng.blobness(self.d_img, self.cfg['blobness_formula'], self.cfg['gradient_type'],
+                              tuple(WL['scales']), torch.float64, out=(self.Rb, self.grad))
             if time_k1:
                 e1.record()
                 self.k1_events.append((e0, e1))
@@ -316,7 +342,7 @@ def run_gpu(args):
     # lanes per GPU: every lane has a host thread that enqueues one run (a CUDA graph + ~90 eager launches)
     # and waits for the device.  8 lanes saturate one B200 (1/2/4/8 lanes: 295/450/600/690 runs/s) and were
     # also the best setting on the 8-GPU / 32-core box (4388 runs/s vs 3826 with 4 lanes per GPU).
-    B = args.batch if args.batch > 0 else max(1, min(8, cores))
+    B = args.batch if args.batch > 0 else max(1, min(WL['lanes'], cores))
     # host wait policy: spin unless the lane threads of all ranks oversubscribe the cores, then yield
     # (measured on the 8-GPU / 32-core box before the CUDA-graph loop: 2938 runs/s with yield vs 2639 with spin)
     policy = os.environ.get("AOSLO_BENCH_WAIT_POLICY", "2" if world * B * 2 > cores else "")
@@ -536,7 +562,7 @@ def run_gpu(args):
         bytes_f32 = 13.0 * H * W                       # 1 B u8 in + 4 B R_b + 8 B grad out per pixel
         ach = bytes_f64 / (k1_ms / 1e3) / 1e9
         line = {
-            "metric": "detection runs/s (full pipeline, 2048^2 image)", "value": value, "unit": "runs/s",
+            "metric": WL['metric'], "value": value, "unit": "runs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(), "batch": B,
@@ -554,7 +580,9 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(d2h * B), "latency_ms_single_run": float(np.mean(e2e_lat))},
             "gpu_launches": int(launches),
             "roofline": {
-                "kernel": "blobness_dtile_kernel (K1 f64: fused Gaussian / Hessian / eigenvalues / blobness / gradient; "
+                "kernel": ("blobness_dtile_kernel" if len(WL['scales']) == 1 else "blobness_kernel (generic tile kernel, "
+                           "%d scales)" % len(WL['scales'])) +
+                          " (K1 f64: fused Gaussian / Hessian / eigenvalues / blobness / gradient; "
                           "the kernel the timed step launches; 25 B/px = 1 B u8 in + 8 B R_b + 16 B grad out)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": k1_dram_traffic("f64"), "peak_source": peak_src,
@@ -595,6 +623,112 @@ def run_gpu(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------- cfg4 / cfg5
+def run_units(args):
+    """BASELINE.json configs[3] / [4] through the product's sharded runner (sweep.UnitRunner): units are
+    partitioned over the ranks, run on `lanes` concurrent contexts per GPU, and the per-unit records are all-gathered
+    once.  One step = the whole job (host frames -> records), timed wall clock between barriers on every rank
+    (device work is bracketed by the final synchronisation of each unit); value = units / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    from detecting_cones_aoslo_b200 import _lib, configs, sweep
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is defined for the run workloads "
+                              "(default / cfg2 / cfg3); cfg4 / cfg5 are multiples of them"}))
+        return 0
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_units = args.units or WL['units']
+    lanes = args.batch if args.batch > 0 else max(1, min(WL['lanes'], os.cpu_count() or 1))
+    runner = sweep.UnitRunner(device=local, lanes=lanes)
+    mine = list(sweep.shard_units(n_units, rank, world))
+    if args.workload == "batch":
+        frames_all = None
+        frames = []
+        for i in mine:
+            im, g = synth_aoslo(SIZE, SIZE, PITCH, seed=2022 + i)
+            frames.append((i, im, g, synth_config(SIZE, SIZE, PITCH, boundary=BOUNDARY, epoch_num=EPOCHS,
+                                                  tie_mode=TIE_MODE, collect_stage_times=False)))
+        h2d = sum(f[1].nbytes + f[2].nbytes for f in frames)
+
+        def job():
+            return runner.run_frames(frames)
+    else:
+        img, gt, _ = make_workload(0)
+        base = synth_config(SIZE, SIZE, PITCH, boundary=BOUNDARY, tie_mode=TIE_MODE, collect_stage_times=False)
+        trials = []
+        for i in mine:
+            c = sweep.sample_trial(base, i)
+            c['region'] = dict(base['region'])             # the synthetic frame, not the shipped crop
+            c['tie_mode'] = TIE_MODE
+            c['collect_stage_times'] = False
+            trials.append((i, c))
+        h2d = img.nbytes + gt.nbytes
+
+        def job():
+            return runner.run_trials(img, gt, trials)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(1, min(args.warmup, 2))):
+        job()                                               # contexts, graphs, allocator warm
+    steps = max(1, min(args.steps, 3))
+    barrier()
+    t_timed = time.perf_counter()
+    l0 = _lib.lib.aoslo_launch_count()
+    rows = None
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rows = job()
+        table = sweep.gather_records(rows, n_units, device=dev)       # the one exchange: all-gather of the records
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    launches = _lib.lib.aoslo_launch_count() - l0
+    barrier()
+    clocks = sampler.stop(t_timed)
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt.item())
+    if rank == 0:
+        ok = int((table[:, 1] == 0).sum())
+        d2 = table[:, sweep.RECORD_FIELDS.index('dice_coeff_2')]
+        value = n_units * steps / dt
+        line = {"metric": WL['metric'], "value": value, "unit": "units/s", "n_gpus": world, "steps": steps,
+                "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: %d units of %s" % (args.workload, n_units, workload_name()),
+                           "lanes_per_rank": lanes, "units_ok": ok, "units_failed": int(n_units - ok),
+                           "early_stop": "on (reference behaviour)",
+                           "l2": "inputs larger than L2 (every unit streams its own 2048^2 / 512^2 fields)",
+                           "field": "computed once per rank and shared by its trials" if args.workload == "sweep"
+                                    else "computed per frame"},
+                "clocks": clocks,
+                "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(len(mine) * 12 * 88),
+                        "note": "the job IS end to end: host frames / configs in, record table out"},
+                "gpu_launches": int(launches),
+                "dice_2": {"min": float(np.nanmin(d2)), "median": float(np.nanmedian(d2)), "max": float(np.nanmax(d2))}}
+        print(json.dumps(line))
+    runner.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -605,7 +739,14 @@ def main():
                     help="frames run concurrently per step (lanes per GPU); 0 = min(8, host cores)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-faithful", action="store_true", help="skip the sklearn-order / early-stop leg")
+    ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS),
+                    help="default = the configuration BASELINE.json's metric is quoted on; cfg2 / cfg3 / batch / sweep "
+                         "= its other configs")
+    ap.add_argument("--units", type=int, default=0, help="batch / sweep: number of frames / trials (0 = the config's)")
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload in ("batch", "sweep"):
+        return run_units(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

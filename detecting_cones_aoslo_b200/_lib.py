@@ -93,6 +93,9 @@ SYMBOLS = {
     "aoslo_run": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _i, C.POINTER(MetricsRecord), _i, _vp, _vp,
                        C.POINTER(RunSummary), C.POINTER(C.c_float)]),
     "aoslo_read_particles": (_i, [_vp, _vp, _vp, _vp, _i]),
+    "aoslo_tiff_info": (_i, [C.c_char_p, _ip, _ip, _ip, _ip]),
+    "aoslo_tiff_read_gray8": (_i, [C.c_char_p, _vp, _i]),
+    "aoslo_csv_read_points": (_i, [C.c_char_p, _i, _vp, _i, _ip]),
     "aoslo_kdtree_build_host": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i]),
     "aoslo_kdtree_num_nodes": (_i, [_i]),
 }

@@ -25,6 +25,7 @@ UNITS = [
     ("hungarian.cu", ["-fmad=false"]),
     ("api.cu", []),
     ("kdtree_host.cpp", []),
+    ("io_host.cpp", []),
 ]
 
 

@@ -87,6 +87,7 @@ static int alloc_links(CellLinks& lk, int H, int W, int cap, int fixed_shift) {
     lk.ncell = lk.gw * lk.gh;                       // the finest grid: head[] is sized for it
     lk.cap = cap;
     AOSLO_TRY(dmalloc(&lk.head, lk.ncell));
+    AOSLO_CUDA(cudaMemset(lk.head, 0, sizeof(unsigned long long) * lk.ncell));     // tag 0 is never a valid build
     AOSLO_TRY(dmalloc(&lk.next, cap));
     return AOSLO_OK;
 }
@@ -178,7 +179,11 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     }
     A(dmalloc(&c->d_pos_tmp, (size_t)cap * 2));
     A(dmalloc(&c->d_stable_tmp, cap));
-    A(dmalloc(&c->d_link_geom, 4));
+    A(dmalloc(&c->d_link_geom, 8));
+    A(dmalloc(&c->d_link_epoch, 1));
+    A(dmalloc(&c->d_link_epoch_ticket, 1));
+    if (st == AOSLO_OK && cudaMemset(c->d_link_epoch, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaMemset(c->d_link_epoch_ticket, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_ctl, 1));
     A(dmalloc(&c->d_params, 1));
     if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_ctl, sizeof(RunCtl), cudaHostAllocDefault) != cudaSuccess)
@@ -262,7 +267,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
     if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
-    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_ctl); cudaFree(c->d_params);
+    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket); cudaFree(c->d_ctl); cudaFree(c->d_params);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
     cudaGetLastError();
@@ -926,7 +931,7 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
         for (RunGraph& g : ctx->graphs)
             if (g.exec && g.key.size() == sizeof(key) && memcmp(g.key.data(), &key, sizeof(key)) == 0) hit = &g;
         if (!hit) {
-            const size_t kMaxGraphs = 8;
+            const size_t kMaxGraphs = 24;          // a sweep cycles through (neighbour class) x (window) combinations
             if (ctx->graphs.size() < kMaxGraphs) {
                 ctx->graphs.emplace_back();
                 hit = &ctx->graphs.back();

@@ -79,19 +79,22 @@ struct CellLinks {
     int min_shift = 1;           // head[] is allocated for this finest grid
     int shift = 3;
     int gw = 0, gh = 0, ncell = 0;
-    int* head = nullptr;         // [ncell]  -1 = empty
+    unsigned long long* head = nullptr;   // [ncell] (tag << 32) | first index; stale tags = empty
     int* next = nullptr;         // [cap]
     int cap = 0;
 };
 
-// geom = {shift, gw, gh, ncell} lives in DEVICE memory: the cell edge is chosen from the point count, which the
-// run loop only knows on the device (link_clear_kernel writes it, every later kernel of the build reads it)
+// geom = {shift, gw, gh, ncell, tag} lives in DEVICE memory: the cell edge is chosen from the point count, which the
+// run loop only knows on the device (the last block of link_kernel publishes it, every later kernel reads it);
+// head words are (tag << 32) | index, valid only with the tag of the current build (no clearing pass)
 struct LinkView {
     const int* geom;
-    const int* head;
+    const unsigned long long* head;
     const int* next;
     const double2* pos;
 };
+constexpr int kLinkBiasDense = 6;     // link_shift_for bias: thinning rounds (dense seed sets)
+constexpr int kLinkBiasSteady = 3;    // steady state of the loop / metrics
 
 // ---- whole-run control block (device resident, mirrored to pinned memory once at the end of a run) ----
 // aoslo_run enqueues seeding, thinning (a WHILE conditional graph node), resampling and the epoch loop
@@ -191,7 +194,9 @@ struct aoslo_ctx {
     aoslo::RunCtl* h_ctl = nullptr;      // pinned
     aoslo::RunParams* d_params = nullptr;
     aoslo::RunParams* h_params = nullptr;   // pinned staging of the per-run upload
-    int* d_link_geom = nullptr;          // [4] shift, gw, gh, ncell of lk_p
+    int* d_link_geom = nullptr;          // [8] shift, gw, gh, ncell, tag of lk_p
+    unsigned int* d_link_epoch = nullptr;   // build counter = tag of the last build
+    int* d_link_epoch_ticket = nullptr;
     uint8_t* d_stable_tmp = nullptr;     // [cap] flags of the moved particles (input of the in-loop compaction)
     int loop_hint = 0;                   // launch-size hint of the in-loop compaction (performance only)
     aoslo::K1Tuning tune;
@@ -346,7 +351,7 @@ int kd_reserve(aoslo_ctx* ctx);
 int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead);
 int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr,
+                int bias_x4, const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr,
                 uint8_t* prep_stable_out = nullptr);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,

@@ -202,42 +202,38 @@ __device__ __forceinline__ void knn_cells_query(const CellView& cl, double qx, d
 // =======================================================================================
 // scan-free linked cells: build (memset + 1 kernel) and the same exact ring search
 // =======================================================================================
-// Cell edge from the point density: about two points per cell, 2..16 px.  Dense seed sets (thinning: every
-// other pixel) get 2-4 px cells, the steady state (one particle per ~34 px^2) 8 px cells.  Evaluated on the
-// device from the device-resident count (the run loop never brings it to the host); AOSLO_LINK_SHIFT pins it.
-__host__ __device__ inline int link_shift_for(int n, int H, int W, int min_shift, int fixed_shift) {
+// Cell edge from the point density, evaluated on the device from the device-resident count (the run loop never
+// brings it to the host).  bias_x4 / 4 scales the target cell area: 6 (about two points per cell, 2..16 px) for
+// the dense seed sets of the thinning rounds, 3 (about one point per two cells: 4 px cells at one particle per
+// ~30 px^2) for the steady state, where the queries' nearest neighbours are close and small cells mean fewer
+// candidates (measured: metrics pass 38 us with 4 px cells, 45 us with 8 px).  AOSLO_LINK_SHIFT pins it.
+__host__ __device__ inline int link_shift_for(int n, int H, int W, int min_shift, int fixed_shift, int bias_x4) {
     int shift = fixed_shift;
     if (shift <= 0) {
         const double area = 2.0 * (double)H * (double)W / (double)(n > 0 ? n : 1);
         shift = 1;
-        while (shift < 4 && (double)(1 << (shift + 1)) * (double)(1 << (shift + 1)) <= area * 1.5) ++shift;
+        while (shift < 4 && (double)(1 << (shift + 1)) * (double)(1 << (shift + 1)) <= area * 0.25 * (double)bias_x4) ++shift;
     }
     if (shift < min_shift) shift = min_shift;
     return shift;
 }
 
-// first kernel of a build: fixes the geometry (every thread derives it from the count, thread 0 publishes it for
-// the kernels that follow) and empties the cell heads
-__global__ void __launch_bounds__(kThreads) link_clear_kernel(int n_host, const int* d_n, int H, int W, int min_shift,
-                                                              int fixed_shift, int* geom, int* head) {
-    const int n = d_n ? *d_n : n_host;
-    const int shift = link_shift_for(n, H, W, min_shift, fixed_shift);
-    const int gw = (W + (1 << shift) - 1) >> shift, gh = (H + (1 << shift) - 1) >> shift;
-    const int ncell = gw * gh;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { geom[0] = shift; geom[1] = gw; geom[2] = gh; geom[3] = ncell; }
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) head[c] = -1;
-}
-
+// Build of the linked cells in ONE kernel, without clearing the heads: a head word is (tag << 32) | index and only
+// words carrying the tag of the current build are valid.  The tag is a device counter: every thread reads it at
+// kernel start, the LAST block to finish (ticket) publishes tag + geometry for the kernels that follow.
 // PREP additionally does ns_prepare_kernel's work in the same pass (copy to the move buffers, clear the
-// deletion flags, collect the non-stable list)
+// deletion flags, collect the non-stable list).
 template <bool PREP>
 __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restrict__ pos, int n_host,
-                                                        const int* d_n, const int* __restrict__ geom, int W, int H,
-                                                        int* head, int* next, int* status,
+                                                        const int* d_n, int W, int H, int min_shift, int fixed_shift,
+                                                        int bias_x4, int* geom, unsigned int* epoch, int* ticket,
+                                                        unsigned long long* head, int* next, int* status,
                                                         const uint8_t* __restrict__ stable, double2* pos_out,
                                                         uint8_t* stable_out, uint8_t* del, int* ns_list, int* n_ns) {
-    int n = d_n ? *d_n : n_host;
-    const int shift = geom[0], gw = geom[1], gh = geom[2];
+    const int n = d_n ? *d_n : n_host;
+    const int shift = link_shift_for(n, H, W, min_shift, fixed_shift, bias_x4);
+    const int gw = (W + (1 << shift) - 1) >> shift, gh = (H + (1 << shift) - 1) >> shift;
+    const unsigned int tag = *epoch + 1u;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double2 p = pos[i];
         if (PREP) {
@@ -252,25 +248,35 @@ __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restric
         int cy = cell_coord(p.y, shift, gh, bad);
         if (p.x != p.x || p.y != p.y) atomicOr(status, AOSLO_DEV_NAN);
         else if (bad || p.x >= (double)W || p.y >= (double)H) atomicOr(status, AOSLO_DEV_ESCAPED);
-        next[i] = atomicExch(&head[cy * gw + cx], i);
+        const unsigned long long old =
+            atomicExch(&head[cy * gw + cx], ((unsigned long long)tag << 32) | (unsigned long long)(unsigned int)i);
+        next[i] = ((unsigned int)(old >> 32) == tag) ? (int)(unsigned int)old : -1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {      // every block has read the old epoch by now
+            geom[0] = shift; geom[1] = gw; geom[2] = gh; geom[3] = gw * gh; geom[4] = (int)tag;
+            *epoch = tag;
+            *ticket = 0;
+        }
     }
 }
 
 // n_host is the count, or (with d_n) only its launch-size upper bound
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                const uint8_t* prep_stable, double* prep_pos_out, uint8_t* prep_stable_out) {
-    link_clear_kernel<<<ctx->nb, kThreads, 0, s>>>(n_host, d_n, ctx->H, ctx->W, lk.min_shift, lk.fixed_shift,
-                                                   ctx->d_link_geom, lk.head);
-    AOSLO_LAUNCH_CHECK();
+                int bias_x4, const uint8_t* prep_stable, double* prep_pos_out, uint8_t* prep_stable_out) {
     if (prep_stable)
-        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->d_link_geom, ctx->W,
-                                                       ctx->H, lk.head, lk.next, ctx->d_status, prep_stable,
-                                                       (double2*)prep_pos_out, prep_stable_out, ctx->d_del,
+        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->W, ctx->H, lk.min_shift,
+                                                       lk.fixed_shift, bias_x4, ctx->d_link_geom, ctx->d_link_epoch,
+                                                       ctx->d_link_epoch_ticket, lk.head, lk.next, ctx->d_status,
+                                                       prep_stable, (double2*)prep_pos_out, prep_stable_out, ctx->d_del,
                                                        ctx->d_ns_list, ctx->d_counters + 13);
     else
-        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->d_link_geom, ctx->W,
-                                                        ctx->H, lk.head, lk.next, ctx->d_status, nullptr, nullptr,
-                                                        nullptr, nullptr, nullptr, nullptr);
+        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->W, ctx->H, lk.min_shift,
+                                                        lk.fixed_shift, bias_x4, ctx->d_link_geom, ctx->d_link_epoch,
+                                                        ctx->d_link_epoch_ticket, lk.head, lk.next, ctx->d_status, nullptr,
+                                                        nullptr, nullptr, nullptr, nullptr, nullptr);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
@@ -279,19 +285,30 @@ inline LinkView link_view(aoslo_ctx* ctx, const CellLinks& lk, const double* d_p
     return LinkView{ctx->d_link_geom, lk.head, lk.next, (const double2*)d_pos};
 }
 
+__device__ __forceinline__ int link_first(const LinkView& lv, int cell, unsigned int tag) {
+    const unsigned long long h = lv.head[cell];
+    return ((unsigned int)(h >> 32) == tag) ? (int)(unsigned int)h : -1;
+}
+
 template <int K>
-__device__ __forceinline__ void knn_links_cell(const LinkView& lv, int cell, double qx, double qy, TopK<K>& top) {
-    for (int p = lv.head[cell]; p >= 0; p = lv.next[p]) {
+__device__ __forceinline__ void knn_links_cell(const LinkView& lv, int cell, unsigned int tag, double qx, double qy,
+                                               TopK<K>& top) {
+    for (int p = link_first(lv, cell, tag); p >= 0; p = lv.next[p]) {
         double2 t = lv.pos[p];
         double dx = qx - t.x, dy = qy - t.y;
         top.push(dx * dx + dy * dy, p);
     }
 }
 
+// Thread-per-query ring search.  (A variant that walked the nine chains of the 3 x 3 block in lock step -- nine
+// independent loads per step -- was measured: 80 instead of 32-64 registers, a third fewer resident threads, metrics
+// pass 45 -> 56 us, thinning kNN unchanged: these kernels are bound by the number of resident queries, not by the
+// length of one query's chain.)
 template <int K>
 __device__ __forceinline__ void knn_links_query(const LinkView& lv, double qx, double qy, TopK<K>& top) {
     top.init();
     const int shift = lv.geom[0], gw = lv.geom[1], gh = lv.geom[2];
+    const unsigned int tag = (unsigned int)lv.geom[4];
     const int c = 1 << shift;
     int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
     int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
@@ -303,10 +320,10 @@ __device__ __forceinline__ void knn_links_query(const LinkView& lv, double qx, d
         for (int y = max(ylo, 0); y <= min(yhi, gh - 1); ++y) {
             if (y == ylo || y == yhi) {
                 for (int x = max(xlo, 0); x <= min(xhi, gw - 1); ++x)
-                    knn_links_cell<K>(lv, y * gw + x, qx, qy, top);
+                    knn_links_cell<K>(lv, y * gw + x, tag, qx, qy, top);
             } else {
-                if (xlo >= 0) knn_links_cell<K>(lv, y * gw + xlo, qx, qy, top);
-                if (xhi < gw) knn_links_cell<K>(lv, y * gw + xhi, qx, qy, top);
+                if (xlo >= 0) knn_links_cell<K>(lv, y * gw + xlo, tag, qx, qy, top);
+                if (xhi < gw) knn_links_cell<K>(lv, y * gw + xhi, tag, qx, qy, top);
             }
         }
         double bound = INFINITY;
@@ -392,6 +409,7 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
     mine.init();
     out.init();
     const int shift = lv.geom[0], gw = lv.geom[1], gh = lv.geom[2];
+    const unsigned int tag = (unsigned int)lv.geom[4];
     const int c = 1 << shift;
     int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
     int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
@@ -404,7 +422,7 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
         if (r == 1) {
             if (lane < 9) {
                 const int x = cx + (lane % 3) - 1, y = cy + (lane / 3) - 1;
-                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, qx, qy, mine);
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, tag, qx, qy, mine);
             }
         } else {
             const int ncells = 8 * r;
@@ -415,7 +433,7 @@ __device__ __forceinline__ void knn_links_query_warp(const LinkView& lv, double 
                 else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
                 else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
                 const int x = cx + dx, y = cy + dy;
-                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, qx, qy, mine);
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_links_cell<K>(lv, y * gw + x, tag, qx, qy, mine);
             }
         }
         warp_merge_topk<K>(mine, out);
@@ -1460,7 +1478,7 @@ int stage_knn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_poin
     }
     (void)tree_is_particles;
     if (n_points > ctx->lk_p.cap) return AOSLO_ERR_CAPACITY;
-    AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_points, n_points, d_n));
+    AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_points, n_points, d_n, kLinkBiasDense));
     return knn_links(ctx, s, link_view(ctx, ctx->lk_p, d_points), d_query, n_query, d_n, k, d_idx, d_d2);
 }
 
@@ -1495,7 +1513,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
     const bool use_ns = (mode == 2) && tie_mode == AOSLO_TIE_CANONICAL;
     if (small) {
         if (use_ns) {
-            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
             LinkView lv = link_view(ctx, ctx->lk_p, d_pos);
             ns_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, ctx->d_ns_list, n_ns, thr, d_thr, ctx->d_knn_idx,
                                                         ctx->d_knn_d2, ctx->d_active, n_active, fallback);
@@ -1505,7 +1523,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                                                           ctx->d_status, fallback);
             AOSLO_LAUNCH_CHECK();
         } else if (tie_mode == AOSLO_TIE_CANONICAL) {
-            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
             knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx, ctx->lk_p, d_pos), d_stable, n, d_n, thr, d_thr,
                                                           ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_del, ctx->d_active,
                                                           n_active, ctx->d_status, nullptr);
@@ -1574,7 +1592,7 @@ int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const 
     int* n_ns = ctx->d_counters + 13;          // zero here: reset by the resolve kernel / by the callers
     if (!links_ready) {
         // one pass: link the particles and do ns_prepare's work (copy, clear flags, non-stable list)
-        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, d_stable, d_pos_out, d_stable_copy));
+        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady, d_stable, d_pos_out, d_stable_copy));
     } else {
         ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
                                                        d_stable_copy, ctx->d_del, ctx->d_ns_list, n_ns);
@@ -1687,7 +1705,7 @@ int stage_metrics(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uin
     if (n > ctx->cap || n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
     if (n < 1 || n_gt < 1) return AOSLO_ERR_INVALID;
     if (!gt_list_ready) AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_g, d_gt, n_gt, d_n_gt));
-    if (!p_list_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n));
+    if (!p_list_ready) AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
     // one pass: particle -> nearest GT ("gt_to_particles", :322) and GT -> nearest particle
     // ("particles_to_gt", :323), counts, moments and blob energy
     int* icount = ctx->d_counters + 16;

@@ -94,12 +94,19 @@ class Engine:
         pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array; gt_minus1: (n,2) float64 host
         array ALREADY shifted by -1 (the in-place side effect stays on the host).  Returns the padded
         image view (pitch multiple of 16) and the cropped / shifted GT, both on the device."""
-        img = np.asarray(img)
-        if img.dtype != np.uint8 or img.ndim != 2:
+        on_device = isinstance(img, torch.Tensor)
+        if not on_device:
+            img = np.asarray(img)
+        if img.dtype not in (np.uint8, torch.uint8) or img.ndim != 2:
             # the kernels take the raw bytes; the reference's skimage path would rescale other dtypes
             # (img_as_float), which is not implemented -- refuse instead of reinterpreting the buffer
             raise TypeError("img must be a 2-D uint8 array (got %s, ndim %d)" % (img.dtype, img.ndim))
-        img = np.ascontiguousarray(img)
+        if on_device:
+            if not img.is_cuda or img.device != self.device:
+                raise ValueError("a tensor image must live on the engine's device (dataio.PinnedBatch)")
+            img = img.contiguous()
+        else:
+            img = np.ascontiguousarray(img)
         H0, W0 = img.shape
         assert (0 <= region['x_min']) and (0 <= region['y_min'])                       # image_transformation.py:7
         assert (W0 > region['x_max']) and (H0 > region['y_max'])                       # image_transformation.py:8
@@ -108,10 +115,13 @@ class Engine:
             raise MemoryError("GT capacity of the context exceeded")
         # context-owned device staging (stable addresses, no allocation per call); pageable host arrays go
         # through cudaMemcpyAsync's own staging, pinned ones (torch pin_memory) are true async copies
-        if self._raw_bufs is None or self._raw_bufs[0].numel() < img.size:
-            self._raw_bufs = (self.empty((img.size,), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
-        d_raw = self._raw_bufs[0][: img.size].view(H0, W0)
-        d_raw.copy_(torch.from_numpy(img), non_blocking=True)
+        if self._raw_bufs is None or self._raw_bufs[0].numel() < H0 * W0:
+            self._raw_bufs = (self.empty((H0 * W0,), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
+        if on_device:
+            d_raw = img                                    # already uploaded (batched pinned upload)
+        else:
+            d_raw = self._raw_bufs[0][: H0 * W0].view(H0, W0)
+            d_raw.copy_(torch.from_numpy(img), non_blocking=True)
         d_gt_raw = self._raw_bufs[1][: g.shape[0]]
         d_gt_raw.copy_(torch.from_numpy(g), non_blocking=True)
         pitch = (self.W + 15) // 16 * 16

@@ -133,7 +133,8 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     np.random.seed(cur_config['random_seed'])          # reference :24 (no RNG is consumed afterwards)
 
     region, boundary = cur_config['region'], cur_config['boundary_size']
-    img = np.asarray(img)
+    if not isinstance(img, torch.Tensor):                  # a device uint8 tensor (dataio.PinnedBatch) is taken as is
+        img = np.asarray(img)
     assert (0 <= region['x_min']) and (0 <= region['y_min'])                            # crop_image asserts
     assert (img.shape[1] > region['x_max']) and (img.shape[0] > region['y_max'])
     H = (region['y_max'] - region['y_min']) + 2 * int(boundary['y'])
@@ -168,6 +169,31 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
                                    trace)
     result['time_spended'] = time.time() - t0
     return result, time_spended
+
+
+def run_on_field(eng, cur_config, Rb, grad, d_gt, USE_WANDB=False, experiment_idx=0, log_fn=None):
+    """The part of find_blobs after the field computation (reference :95-403) on an existing blobness field:
+    what a sweep calls per trial, the field being shared by every trial of an image (sweep.UnitRunner).
+    `Rb` / `grad` / `d_gt` are device tensors (Engine.blobness / Engine.prepare_inputs, possibly of another
+    Engine of the same shape).  Returns the `result` dict of find_blobs."""
+    result = {
+        'best_lsa_mean': +np.inf,
+        'best_blobEn_mean': -np.inf,
+        'dice_coeff_1': -np.inf,
+        'dice_coeff_2': -np.inf,
+        'cur_config': cur_config,
+        'time_spended': 0,
+    }
+    t0 = time.time()
+    if cur_config['blobness_formula'] not in ('simple_div', 'custom', 'div_corrected'):
+        raise NotImplementedError
+    eng.status(clear=True)
+    if cur_config['metric_algo'] == 'hangarian' or _get(cur_config, 'engine_mode', 'fused') == 'staged':
+        _run_staged(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn, None)
+    else:
+        _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn)
+    result['time_spended'] = time.time() - t0
+    return result
 
 
 def _log_record(log_fn, it, pm, lsa_sum, lsa_mean, lsa_var, blob_sum, blob_mean, n_gt, n, n_stable):

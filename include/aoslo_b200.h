@@ -248,6 +248,16 @@ int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void*
  * capacity-sized buffers to aoslo_run (whose d_particles_out / d_stable_out may be NULL). */
 int aoslo_read_particles(aoslo_ctx* ctx, void* stream, double* d_particles_out, uint8_t* d_stable_out, int n);
 
+/* ---- host-side input readers (replace cv2.imread(path, -1) / pd.read_csv(path).to_numpy() of the reference's
+ * drivers, pipeline_with_delitions.py:443-446, main_with_delitions.py:153-155); they decode into caller buffers
+ * (pinned host memory in the batched loader).  TIFF subset: baseline 8-bit grayscale strips, uncompressed or
+ * PackBits, either byte order; anything else returns AOSLO_ERR_UNSUPPORTED. */
+int aoslo_tiff_info(const char* path, int* h_H, int* h_W, int* h_bits, int* h_samples);
+int aoslo_tiff_read_gray8(const char* path, uint8_t* h_out, int out_pitch_bytes);
+/* "x,y" per line.  skip_first_row = 1: the reference's pd.read_csv default, which consumes line 1 of the header-less
+ * annotation file as column names.  *h_n_out = points in the file (AOSLO_ERR_CAPACITY if more than `capacity`). */
+int aoslo_csv_read_points(const char* path, int skip_first_row, double* h_xy_out, int capacity, int* h_n_out);
+
 /* ---- host helper used by the sklearn-order kNN: builds sklearn's KDTree(leaf_size=1)
  * idx_array / node table on the HOST (std::nth_element, sklearn/neighbors/_partition_nodes.pyx). */
 int aoslo_kdtree_build_host(const double* h_points, int n, int32_t* h_idx_array, int32_t* h_node_start,

@@ -682,6 +682,98 @@ def test_batch_of_frames_and_sweep_trials():
         np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
 
 
+def test_sweep_runner_lanes_shared_field_and_failures(tmp_path):
+    """sweep.UnitRunner: trials of the sweep space on one image with the field computed once and 3 concurrent lanes
+    (own context + stream each) give the same record table as 1 lane and as separate find_blobs calls; a unit that
+    raises (float window, like 10 of the 11 windows of sweep_config_new.yaml in the reference) gets status -1 and
+    does not stop the others; a batch of frames through the same runner equals find_blobs per frame."""
+    from detecting_cones_aoslo_b200 import sweep
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    img, gt = load_dataset()
+    base = configs.zoo_config()
+    n = 7
+    t3 = sweep.run_sweep_on_image(img, gt, base, n, lanes=3)
+    t1 = sweep.run_sweep_on_image(img, gt, base, n, lanes=1)
+    cols = [i for i, f in enumerate(sweep.RECORD_FIELDS) if f != 'time_spended']
+    np.testing.assert_array_equal(t3[:, cols], t1[:, cols])
+    assert (t3[:, 1] == 0).all() and list(t3[:, 0]) == list(range(n))
+    for i in (0, 4):
+        cfg = sweep.sample_trial(base, i)
+        cfg['tie_mode'] = 'canonical'
+        res, _ = find_blobs(cfg, gt.copy(), img, None, False, False)
+        assert t3[i, sweep.RECORD_FIELDS.index('dice_coeff_2')] == res['dice_coeff_2']
+        assert t3[i, sweep.RECORD_FIELDS.index('n_particles')] == res['_summary']['n_particles']
+        assert t3[i, sweep.RECORD_FIELDS.index('tp2')] == res['_records'][-1].tp[1]
+    runner = sweep.UnitRunner(lanes=2)
+    trials = [(0, dict(sweep.sample_trial(base, 0), tie_mode='canonical')),
+              (1, dict(sweep.sample_trial(base, 1), tie_mode='canonical', particle_call_window=5.5)),
+              (2, dict(sweep.sample_trial(base, 2), tie_mode='canonical'))]
+    rows = np.array(runner.run_trials(img, gt, trials))
+    assert list(rows[:, 1]) == [0, -1, 0] and np.isnan(rows[1, 5])
+    np.testing.assert_array_equal(rows[0, cols], t3[0, cols])
+    frames = []
+    for seed in (2022, 2023, 2024):
+        im, g = synth_aoslo(384, 384, 5.8, seed=seed)
+        frames.append((im, g, synth_config(384, 384, 5.8, boundary=15, epoch_num=6, tie_mode='canonical',
+                                           collect_stage_times=False)))
+    tb = sweep.run_batch_of_frames(frames, lanes=2, runner=runner)
+    for i, (im, g, c) in enumerate(frames):
+        res, _ = find_blobs(dict(c), g.copy(), im, None, False, False)
+        assert tb[i, sweep.RECORD_FIELDS.index('dice_coeff_1')] == res['dice_coeff_1']
+        assert tb[i, sweep.RECORD_FIELDS.index('n_particles')] == res['_summary']['n_particles']
+    runner.close()
+
+
+def test_pinned_batch_loader_feeds_find_blobs(tmp_path):
+    """dataio.PinnedBatch: TIFF / CSV decoded into one pinned buffer, one H2D copy, device images handed to find_blobs
+    -- same result as the host-array path."""
+    from test_host_logic import _write_tiff
+    from detecting_cones_aoslo_b200 import dataio
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    pairs = []
+    for k, comp in enumerate((32773, 1)):
+        tp, cp = str(tmp_path / ("f%d.tiff" % k)), str(tmp_path / ("f%d.csv" % k))
+        _write_tiff(tp, img if k == 0 else np.ascontiguousarray(img[:300, :400]), comp)
+        with open(cp, 'w') as f:
+            f.write("0,0\n")
+            for x, y in gt:
+                f.write("%r,%r\n" % (float(x), float(y)))
+        pairs.append((tp, cp))
+    batch = dataio.PinnedBatch(pairs)
+    assert len(batch) == 2 and batch[0][0].is_cuda and batch[1][0].shape == (300, 400)
+    np.testing.assert_array_equal(batch[0][0].cpu().numpy(), img)
+    np.testing.assert_array_equal(batch[0][1], gt)
+    cfg = configs.main_config()
+    a, _ = find_blobs(dict(cfg), batch[0][1].copy(), batch[0][0], None, False, False)
+    b, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    np.testing.assert_array_equal(a["_final_particles"].cpu().numpy(), b["_final_particles"].cpu().numpy())
+    assert a["dice_coeff_2"] == b["dice_coeff_2"]
+
+
+@pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
+def test_multiscale_run_matches_oracle_extension(tie_mode):
+    """BASELINE config 2 in miniature: synthetic lattice of pitch 11, FIVE blobness scales (sigma 1 ... 3, Hessian x
+    sigma^2, scale max -- the extension SURVEY 8c-iii defines; pinned by the oracle only), M = 100 iterations without
+    the early stop: identical particles / flags / counts as the oracle run with the same scales."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    from detecting_cones_aoslo_b200.synth import synth_aoslo, synth_config
+    scales = (1.0, 1.5, 2.0, 2.5, 3.0)
+    img, gt = synth_aoslo(320, 352, 11.0, seed=2022)
+    cfg = synth_config(320, 352, 11.0, boundary=15, epoch_num=100, early_stop=False, tie_mode=tie_mode,
+                       blobness_scales=scales, collect_stage_times=False)
+    ocfg = {k: v for k, v in cfg.items() if k not in ('early_stop', 'tie_mode', 'collect_stage_times', 'blobness_scales')}
+    ref, _ = orc.find_blobs(ocfg, gt.copy(), img, None, False, False, tie_mode=tie_mode, early_stop=False,
+                            scales=scales)
+    res, _ = find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+    assert ref["n_seeds"] > 100 and ref["final_particles"].shape[0] > 300
+    np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["final_particles"])
+    np.testing.assert_array_equal(res["_final_stable"].cpu().numpy(), ref["final_stable"])
+    assert res["_summary"]["n_iterations"] == 100 and res["_summary"]["n_seeds"] == ref["n_seeds"]
+    assert res["dice_coeff_1"] == ref["dice_coeff_1"] and res["dice_coeff_2"] == ref["dice_coeff_2"]
+
+
 def _same_run(a, b):
     np.testing.assert_array_equal(a["_final_particles"].cpu().numpy(), b["_final_particles"].cpu().numpy())
     np.testing.assert_array_equal(a["_final_stable"].cpu().numpy(), b["_final_stable"].cpu().numpy())
