@@ -182,6 +182,11 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_link_geom, 8));
     A(dmalloc(&c->d_link_epoch, 1));
     A(dmalloc(&c->d_link_epoch_ticket, 1));
+    A(dmalloc(&c->d_link_epoch_n, 1));
+    A(dmalloc(&c->d_head_n, c->lk_p.ncell));
+    if (st == AOSLO_OK && cudaMemset(c->d_link_epoch_n, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    if (st == AOSLO_OK && cudaMemset(c->d_head_n, 0, sizeof(unsigned long long) * c->lk_p.ncell) != cudaSuccess)
+        st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_link_epoch, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_link_epoch_ticket, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_ctl, 1));
@@ -267,7 +272,8 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
     if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
-    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket); cudaFree(c->d_ctl); cudaFree(c->d_params);
+    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket);
+    cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_ctl); cudaFree(c->d_params);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
     cudaGetLastError();
@@ -534,10 +540,10 @@ __global__ void __launch_bounds__(kThreads) thin_swap_kernel(const double2* __re
     }
 }
 
-__global__ void loop_begin_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, int* status,
+__global__ void loop_begin_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, const int* n_dead, int* status,
                                   cudaGraphConditionalHandle h_loop, int use_handle, int stamp) {
     if (threadIdx.x != 0) return;
-    const int n = *cnt;
+    const int n = *cnt - *n_dead;
     int go = rp->epoch_num > 0 ? 1 : 0;
     if (n < rp->kk || n < 2) { atomicOr(status, AOSLO_DEV_KNN_SHORT); go = 0; }   // sklearn: n_neighbors > n_samples
     ctl->it = 0;
@@ -546,13 +552,11 @@ __global__ void loop_begin_kernel(RunCtl* ctl, const RunParams* rp, const int* c
     if (stamp) ctl_stamp(ctl, -1);
 }
 
-// after the deletion of an iteration: the survivors' count becomes the current count, and the two branch
-// conditions of this iteration are fixed (resample :256, metrics :320)
-__global__ void iter_mid_kernel(RunCtl* ctl, const RunParams* rp, int* cnt0, const int* cnt1,
-                                cudaGraphConditionalHandle h_res, cudaGraphConditionalHandle h_met, int use_res,
-                                int use_met, int stamp) {
+// after the deletion of an iteration: the two branch conditions of this iteration are fixed (resample :256,
+// metrics :320)
+__global__ void iter_mid_kernel(RunCtl* ctl, const RunParams* rp, cudaGraphConditionalHandle h_res,
+                                cudaGraphConditionalHandle h_met, int use_res, int use_met, int stamp) {
     if (threadIdx.x != 0) return;
-    *cnt0 = *cnt1;
     const int it = ctl->it;
     const int do_res = (it % rp->fix_freq == 3) ? 1 : 0;
     const int do_met = (it % rp->metric_freq == 0 && ctl->n_rec < rp->max_records) ? 1 : 0;
@@ -563,12 +567,12 @@ __global__ void iter_mid_kernel(RunCtl* ctl, const RunParams* rp, int* cnt0, con
     if (stamp) ctl_stamp(ctl, 2);
 }
 
-__global__ void iter_end_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, int* status,
+__global__ void iter_end_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt, const int* n_dead, int* status,
                                 cudaGraphConditionalHandle h_loop, int use_handle, int stamp) {
     if (threadIdx.x != 0) return;
     const int it = ctl->it + 1;
     ctl->it = it;
-    const int n = *cnt;
+    const int n = *cnt - *n_dead;                    // survivors (tombstones are compacted at the next resample)
     int go = it < rp->epoch_num ? 1 : 0;
     // sum(stable) / len(particles) > 0.997 (:381) -- Python true division in float64
     if (rp->early_stop && (double)ctl->n_stable / (double)n > 0.997) go = 0;
@@ -670,47 +674,49 @@ int enqueue_thin_round(RunPlan& P, cudaStream_t q, cudaGraphConditionalHandle h,
     return AOSLO_OK;
 }
 
-int enqueue_resample(RunPlan& P, cudaStream_t q, const int* dn, int* dn_out, bool packed_ready) {
+// resample (:256-264 / :130-152) on buffer 0: [compaction of the survivors,] all stable, gravity field, adding,
+// then a new resample period (S / N structures, non-stable list)
+int enqueue_resample(RunPlan& P, cudaStream_t q, bool first) {
     aoslo_ctx* c = P.ctx;
     const aoslo_config* cfg = P.cfg;
     const int bound = c->cap;
-    AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], bound, 1, dn));
-    AOSLO_TRY(build_cell_list(c, q, c->cl_p, c->d_pos[0], bound, dn));
-    AOSLO_TRY(stage_gravity(c, q, c->d_lut, cfg->reception_field_size, cfg->H, cfg->W, c->d_field, packed_ready));
+    if (!first) AOSLO_TRY(stage_compact(c, q, bound, P.cnt0, P.cnt1, P.hint));
+    AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], bound, 1, P.cnt0));
+    AOSLO_TRY(build_cell_list(c, q, c->cl_p, c->d_pos[0], bound, P.cnt0));
+    AOSLO_TRY(stage_gravity(c, q, c->d_lut, cfg->reception_field_size, cfg->H, cfg->W, c->d_field, !first));
     // the spine kernel reads the base count before it writes the total, so both may be the same scalar
     AOSLO_TRY(stage_add(c, q, c->d_field, cfg->H, cfg->W, cfg->bx, cfg->by, cfg->particle_call_window,
-                        cfg->particle_call_threshold, c->d_pos[0], c->d_stable[0], bound, dn, c->cap, dn_out,
+                        cfg->particle_call_threshold, c->d_pos[0], c->d_stable[0], bound, P.cnt0, c->cap, P.cnt0,
                         &c->d_params->add_thr, true));
-    return AOSLO_OK;
+    return stage_period_begin(c, q, bound, P.cnt0);
 }
 
-int enqueue_metrics(RunPlan& P, cudaStream_t q, const int* dn) {
+int enqueue_metrics(RunPlan& P, cudaStream_t q, int static_it, int static_slot) {
     aoslo_ctx* c = P.ctx;
     const aoslo_config* cfg = P.cfg;
-    return stage_metrics(c, q, c->d_pos[0], c->d_stable[0], c->cap, P.d_gt, P.n_gt, true, false, P.d_Rb, P.fdt, cfg->H,
-                         cfg->W, cfg->bx, cfg->by, 0, c->d_records, c->d_dist_p2g, c->d_dist_g2p, dn,
-                         &c->d_params->n_gt, &c->d_ctl->n_rec, &c->d_ctl->it);
+    const bool dyn = static_slot < 0;
+    return stage_dual_metrics(c, q, c->cap, P.cnt0, P.d_gt, P.n_gt, P.d_Rb, P.fdt, cfg->H, cfg->W, cfg->bx, cfg->by,
+                              dyn ? 0 : static_it, c->d_records + (dyn ? 0 : static_slot), &c->d_params->n_gt,
+                              dyn ? &c->d_ctl->n_rec : nullptr, dyn ? &c->d_ctl->it : nullptr);
 }
 
-// force + move + deletion of one iteration (:185-253): particles in buffer 0 with count *dn; survivors back in
-// buffer 0 with count *dn_out
-int enqueue_step(RunPlan& P, cudaStream_t q, const int* dn, int* dn_out, bool links_ready) {
+// force + move + deletion of one iteration (:185-253) on buffer 0; deleted particles become tombstones
+int enqueue_step(RunPlan& P, cudaStream_t q) {
     aoslo_ctx* c = P.ctx;
     const aoslo_config* cfg = P.cfg;
     const bool pit = cfg->dist_energy_type == AOSLO_ENERGY_PIT;
     const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
     const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
     const double e2 = pit ? cfg->lambda_dist_func : 0.0;
-    AOSLO_TRY(stage_force_move(c, q, c->d_pos[0], c->d_stable[0], c->cap, cfg->dist_n_neighbours, cfg->dist_energy_type,
-                               e0, e1, e2, P.d_grad, P.fdt, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist,
-                               cfg->step_mode, c->d_pos_tmp, dn, links_ready, c->d_stable_tmp, c->d_params));
-    if (P.timing) {
-        stamp_kernel<<<1, 32, 0, q>>>(c->d_ctl, 0);       // force and move are one kernel: the move bucket stays 0
-        AOSLO_LAUNCH_CHECK();
+    for (int phase = 1; phase <= 2; ++phase) {
+        AOSLO_TRY(stage_dual_step(c, q, c->cap, P.cnt0, cfg->dist_n_neighbours, cfg->dist_energy_type, e0, e1, e2,
+                                  P.d_grad, P.d_Rb, P.fdt, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist,
+                                  cfg->step_mode, cfg->threshhold_dist_del, c->d_params, phase));
+        if (phase == 1 && P.timing) {
+            stamp_kernel<<<1, 32, 0, q>>>(c->d_ctl, 0);   // force and move are one kernel: the move bucket stays 0
+            AOSLO_LAUNCH_CHECK();
+        }
     }
-    AOSLO_TRY(stage_delete(c, q, c->d_pos_tmp, c->d_stable_tmp, c->cap, P.d_Rb, P.fdt, cfg->H, cfg->W,
-                           cfg->threshhold_dist_del, AOSLO_TIE_CANONICAL, c->d_pos[0], c->d_stable[0], nullptr, dn_out,
-                           nullptr, dn, 2, &c->d_params->del_thr, P.hint));
     return AOSLO_OK;
 }
 
@@ -765,58 +771,49 @@ int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
             AOSLO_TRY(enqueue_thin_round(P, q, 0, 0));
         }
     }
-    // ---- all stable, LUT, gravity field, adding (:130-152); GT cell list once per run
+    // ---- all stable, LUT, gravity field, adding (:130-152), first resample period; GT cell list once per run
+    int* n_dead = c->d_counters + 7;
     AOSLO_TRY(stage_lut(c, q, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, c->d_lut, rp));
-    AOSLO_TRY(enqueue_resample(P, q, P.cnt0, P.cnt0, false));
+    AOSLO_TRY(enqueue_resample(P, q, true));
     AOSLO_TRY(build_cell_list(c, q, c->cl_g, P.d_gt, P.n_gt, &rp->n_gt));
     // ---- the epoch loop (:173-382)
     if (!P.dynamic_loop && graph) {
-        // unrolled: the branches are static, the count alternates between two scalars, no control kernels
+        // unrolled: the branches are static, no control kernels
         if (P.timing) {
             stamp_kernel<<<1, 32, 0, q>>>(ctl, -1);
             AOSLO_LAUNCH_CHECK();
         }
-        int* cn[2] = {P.cnt0, P.cnt1};
-        int p = 0, n_rec = 0;
-        bool links_valid = false;
+        int n_rec = 0;
         for (int it = 0; it < cfg->epoch_num; ++it) {
-            AOSLO_TRY(enqueue_step(P, q, cn[p], cn[p ^ 1], links_valid));
-            links_valid = false;
-            p ^= 1;
+            AOSLO_TRY(enqueue_step(P, q));
             if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 2); AOSLO_LAUNCH_CHECK(); }
-            if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(enqueue_resample(P, q, cn[p], cn[p], true));
+            if (it % cfg->fix_particles_frequency == 3) AOSLO_TRY(enqueue_resample(P, q, false));
             if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
             if (it % cfg->metric_measure_freq == 0 && P.want_records && n_rec < P.max_records) {
-                // record slot / iteration number are static here
-                AOSLO_TRY(stage_metrics(c, q, c->d_pos[0], c->d_stable[0], c->cap, P.d_gt, P.n_gt, true, false, P.d_Rb,
-                                        P.fdt, H, W, cfg->bx, cfg->by, it, c->d_records + n_rec, c->d_dist_p2g,
-                                        c->d_dist_g2p, cn[p], &rp->n_gt, nullptr, nullptr));
-                links_valid = true;              // the metrics pass left links of buffer 0 behind
+                AOSLO_TRY(enqueue_metrics(P, q, it, n_rec));
                 ++n_rec;
             }
             if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 4); AOSLO_LAUNCH_CHECK(); }
         }
-        if (p != 0) AOSLO_CUDA(cudaMemcpyAsync(P.cnt0, P.cnt1, sizeof(int), cudaMemcpyDeviceToDevice, q));
     } else {
         auto step_and_mid = [&](cudaStream_t b, cudaGraphConditionalHandle h_res, cudaGraphConditionalHandle h_met,
                                 int use_res, int use_met) -> int {
-            AOSLO_TRY(enqueue_step(P, b, P.cnt0, P.cnt1, false));
-            iter_mid_kernel<<<1, 32, 0, b>>>(ctl, rp, P.cnt0, P.cnt1, h_res, h_met, use_res, use_met,
-                                             P.timing ? 1 : 0);
+            AOSLO_TRY(enqueue_step(P, b));
+            iter_mid_kernel<<<1, 32, 0, b>>>(ctl, rp, h_res, h_met, use_res, use_met, P.timing ? 1 : 0);
             AOSLO_LAUNCH_CHECK();
             return AOSLO_OK;
         };
         auto iter_tail = [&](cudaStream_t b, cudaGraphConditionalHandle h_loop, int use) -> int {
-            if (cfg->early_stop) AOSLO_TRY(stage_count_stable(c, b, c->d_stable[0], c->cap, &ctl->n_stable, P.cnt0));
-            iter_end_kernel<<<1, 32, 0, b>>>(ctl, rp, P.cnt0, c->d_status, h_loop, use, P.timing ? 1 : 0);
+            if (cfg->early_stop) AOSLO_TRY(stage_dual_count_stable(c, b, c->cap, P.cnt0, &ctl->n_stable));
+            iter_end_kernel<<<1, 32, 0, b>>>(ctl, rp, P.cnt0, n_dead, c->d_status, h_loop, use, P.timing ? 1 : 0);
             AOSLO_LAUNCH_CHECK();
             return AOSLO_OK;
         };
         if (graph) {
             CondNode loop;
             AOSLO_TRY(new_cond_handle(q, &loop.handle));
-            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, c->d_status, loop.handle, 1, P.timing ? 1 : 0);
+            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, n_dead, c->d_status, loop.handle, 1, P.timing ? 1 : 0);
             AOSLO_LAUNCH_CHECK();
             AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &loop));
             cudaStream_t b = c->cap_stream2;
@@ -829,18 +826,18 @@ int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
                 cudaStream_t b3 = c->cap_stream3;
                 AOSLO_TRY(add_cond_node(b, cudaGraphCondTypeIf, &res));
                 AOSLO_TRY(capture_body(b3, res.body, &P.k_res, [&]() -> int {
-                    AOSLO_TRY(enqueue_resample(P, b3, P.cnt0, P.cnt0, true));
+                    AOSLO_TRY(enqueue_resample(P, b3, false));
                     if (P.timing) { stamp_kernel<<<1, 32, 0, b3>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
                     return AOSLO_OK;
                 }));
                 if (P.want_records) {
                     AOSLO_TRY(add_cond_node(b, cudaGraphCondTypeIf, &met));
-                    AOSLO_TRY(capture_body(b3, met.body, &P.k_met, [&]() { return enqueue_metrics(P, b3, P.cnt0); }));
+                    AOSLO_TRY(capture_body(b3, met.body, &P.k_met, [&]() { return enqueue_metrics(P, b3, 0, -1); }));
                 }
                 return iter_tail(b, loop.handle, 1);
             }));
         } else {
-            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, c->d_status, 0, 0, P.timing ? 1 : 0);
+            loop_begin_kernel<<<1, 32, 0, q>>>(ctl, rp, P.cnt0, n_dead, c->d_status, 0, 0, P.timing ? 1 : 0);
             AOSLO_LAUNCH_CHECK();
             for (;;) {
                 AOSLO_TRY(read_ctl());
@@ -848,14 +845,16 @@ int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
                 AOSLO_TRY(step_and_mid(q, 0, 0, 0, 0));
                 AOSLO_TRY(read_ctl());
                 if (c->h_ctl->do_resample) {
-                    AOSLO_TRY(enqueue_resample(P, q, P.cnt0, P.cnt0, true));
+                    AOSLO_TRY(enqueue_resample(P, q, false));
                     if (P.timing) { stamp_kernel<<<1, 32, 0, q>>>(ctl, 3); AOSLO_LAUNCH_CHECK(); }
                 }
-                if (c->h_ctl->do_metrics && P.want_records) AOSLO_TRY(enqueue_metrics(P, q, P.cnt0));
+                if (c->h_ctl->do_metrics && P.want_records) AOSLO_TRY(enqueue_metrics(P, q, 0, -1));
                 AOSLO_TRY(iter_tail(q, 0, 0));
             }
         }
     }
+    // ---- the survivors, compacted in order, are the result
+    AOSLO_TRY(stage_compact(c, q, c->cap, P.cnt0, P.cnt1, P.hint));
     // ---- final reads: stable count, control block, status, records -> pinned memory
     AOSLO_TRY(stage_count_stable(c, q, c->d_stable[0], c->cap, &ctl->n_stable, P.cnt0));
     run_end_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0);

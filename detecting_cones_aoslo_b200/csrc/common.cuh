@@ -196,6 +196,8 @@ struct aoslo_ctx {
     aoslo::RunParams* h_params = nullptr;   // pinned staging of the per-run upload
     int* d_link_geom = nullptr;          // [8] shift, gw, gh, ncell, tag of lk_p
     unsigned int* d_link_epoch = nullptr;   // build counter = tag of the last build
+    unsigned int* d_link_epoch_n = nullptr; // same for the non-stable structure N of the run loop
+    unsigned long long* d_head_n = nullptr; // [ncell of the finest grid] heads of N
     int* d_link_epoch_ticket = nullptr;
     uint8_t* d_stable_tmp = nullptr;     // [cap] flags of the moved particles (input of the in-loop compaction)
     int loop_hint = 0;                   // launch-size hint of the in-loop compaction (performance only)
@@ -388,6 +390,17 @@ int stage_metrics(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* 
                   int bx, int by, int iteration, aoslo_metrics_record* d_rec, double* d_p2g, double* d_g2p,
                   const int* d_n, const int* d_n_gt = nullptr, int* d_rec_idx = nullptr,
                   const int* d_iteration = nullptr);
+// run loop, tombstone / dual-structure scheme (particles.cu): state lives in buffer 0, tombstone count in
+// d_counters[7]
+int stage_period_begin(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n);
+int stage_dual_step(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, int k, int energy_type, double p0, double p1,
+                    double p2, const void* d_grad, const void* d_Rb, int field_dtype, int H, int W, double lb, double ld,
+                    int step_mode, double del_thr, const RunParams* rp, int phases);
+int stage_compact(aoslo_ctx*, cudaStream_t, int n_bound, int* d_n, int* d_n_scratch, int scan_hint);
+int stage_dual_metrics(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, const double* d_gt, int n_gt,
+                       const void* d_Rb, int field_dtype, int H, int W, int bx, int by, int iteration,
+                       aoslo_metrics_record* d_rec, const int* d_n_gt, int* d_rec_idx, const int* d_iteration);
+int stage_dual_count_stable(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, int* d_out);
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t* d_stable, int n, uint8_t v, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t* d_stable, int n, int* d_out, const int* d_n);
 int coop_blocks_for_delete(int num_sms);

@@ -1229,49 +1229,48 @@ __global__ void __launch_bounds__(kThreads) ns_rows_kernel(LinkView lv, const ui
 // =======================================================================================
 // metrics
 // =======================================================================================
-// Chan / Welford running moments (count, mean, M2): numerically stable and mergeable in a fixed order
+// Moments of the nearest-distance arrays as plain sums: sum d, sum (d - kShift), sum (d - kShift)^2 with a fixed
+// shift near the typical distance (1 px), so that var = (q - l^2 / n) / n does not cancel (worst case, distances of
+// tens of pixels: a few digits of 16, tolerance of the parity tests 1e-12).  Every reduction level is three adds per
+// array -- the Chan / Welford merge this replaces cost two FP64 divisions per level and made the shuffle tree
+// (executed by EVERY thread) four times as long as the queries themselves (ncu: 1 330 instructions per query).
+// The tree order is fixed, so the sums are deterministic.
+constexpr double kMomentShift = 1.0;
 struct Moments {
-    double n, mean, m2, sum;
-    __device__ __forceinline__ void init() { n = 0.0; mean = 0.0; m2 = 0.0; sum = 0.0; }
+    double sum, l, q;
+    __device__ __forceinline__ void init() { sum = 0.0; l = 0.0; q = 0.0; }
     __device__ __forceinline__ void add(double x) {
-        n += 1.0;
-        double d = x - mean;
-        mean += d / n;
-        m2 += d * (x - mean);
+        const double d = x - kMomentShift;
         sum += x;
+        l += d;
+        q += d * d;
     }
-    __device__ __forceinline__ void merge(const Moments& o) {
-        if (o.n == 0.0) return;
-        if (n == 0.0) { *this = o; return; }
-        double nn = n + o.n, d = o.mean - mean;
-        mean += d * (o.n / nn);
-        m2 += o.m2 + d * d * (n * o.n / nn);
-        n = nn;
-        sum += o.sum;
-    }
+    __device__ __forceinline__ void merge(const Moments& o) { sum += o.sum; l += o.l; q += o.q; }
+    __device__ __forceinline__ double var(double n) const { return (q - l * l / n) / n; }    // np.var (ddof = 0)
 };
 
 __device__ __forceinline__ Moments shfl_down_moments(const Moments& m, int o) {
     Moments r;
-    r.n = __shfl_down_sync(0xffffffffu, m.n, o);
-    r.mean = __shfl_down_sync(0xffffffffu, m.mean, o);
-    r.m2 = __shfl_down_sync(0xffffffffu, m.m2, o);
     r.sum = __shfl_down_sync(0xffffffffu, m.sum, o);
+    r.l = __shfl_down_sync(0xffffffffu, m.l, o);
+    r.q = __shfl_down_sync(0xffffffffu, m.q, o);
     return r;
 }
 
 struct MetricsPartial {          // one per block
     Moments p2g, g2p;
     double energy;
+    double pad_;
 };
 
 // L2-coherent read of another block's partial (written before its __threadfence + ticket)
 __device__ __forceinline__ MetricsPartial __ldcg_partial(const MetricsPartial* p) {
     const double* d = reinterpret_cast<const double*>(p);
     MetricsPartial r;
-    r.p2g.n = __ldcg(d + 0); r.p2g.mean = __ldcg(d + 1); r.p2g.m2 = __ldcg(d + 2); r.p2g.sum = __ldcg(d + 3);
-    r.g2p.n = __ldcg(d + 4); r.g2p.mean = __ldcg(d + 5); r.g2p.m2 = __ldcg(d + 6); r.g2p.sum = __ldcg(d + 7);
-    r.energy = __ldcg(d + 8);
+    r.p2g.sum = __ldcg(d + 0); r.p2g.l = __ldcg(d + 1); r.p2g.q = __ldcg(d + 2);
+    r.g2p.sum = __ldcg(d + 3); r.g2p.l = __ldcg(d + 4); r.g2p.q = __ldcg(d + 5);
+    r.energy = __ldcg(d + 6);
+    r.pad_ = 0.0;
     return r;
 }
 
@@ -1400,32 +1399,507 @@ __global__ void __launch_bounds__(kThreads) metrics_pass_kernel(
     rec->n_in_image = __ldcg(&icount[6]);
     rec->pad_ = 0;
     rec->sum_p2g = acc.p2g.sum; rec->sum_g2p = acc.g2p.sum;
-    rec->var_p2g = acc.p2g.m2 / acc.p2g.n; rec->var_g2p = acc.g2p.m2 / acc.g2p.n;
+    rec->var_p2g = acc.p2g.var((double)n); rec->var_g2p = acc.g2p.var((double)n_gt);
     rec->blob_energy_sum = acc.energy;
 }
 
-// one block: merges the per-block partials in a fixed shuffle tree (deterministic) -> record
-__global__ void __launch_bounds__(kScanThreads) metrics_finalize_kernel(
-    const MetricsPartial* __restrict__ partials, int nblocks, const int* __restrict__ icount, int n_host,
-    const int* d_n, int n_gt, int iteration, aoslo_metrics_record* rec) {
-    __shared__ MetricsPartial s_part[kScanThreads / 32];
+// =======================================================================================
+// The run loop's particle structure (aoslo_run, canonical tie order): tombstones + two cell structures
+// =======================================================================================
+// Between two resamples only the non-stable particles move (:216) -- a few thousand of ~145 k on the benchmark
+// frame -- yet rebuilding the cell structure and compacting the arrays after every deletion touches all of them,
+// twice per iteration.  So inside a resample period
+//   * deleted particles stay in the arrays as TOMBSTONES (del[i] = 1, position NaN): indices do not shift, the
+//     relative order of the survivors -- all that the (d^2, index) neighbour order and the row-order deletion rule
+//     depend on -- is unchanged, and the order-preserving compaction runs once per period (before the resample,
+//     and once at the end of the run);
+//   * the STABLE particles are linked once per period (structure S); only the NON-STABLE ones are re-linked after
+//     they move (structure N, a few thousand entries, one small kernel).  A query walks both chains of a cell.
+//     A tombstone needs no test in the candidate loops: its NaN distance never enters a top-k list.
+struct DualView {
+    const int* geom;                 // shift, gw, gh, ncell, tag of S, tag of N
+    const unsigned long long* headS;
+    const unsigned long long* headN;
+    const int* next;                 // shared: a particle is in exactly one structure
+    const double2* pos;
+};
+
+template <int K>
+__device__ __forceinline__ void knn_dual_cell(const DualView& dv, int cell, unsigned int tagS, unsigned int tagN,
+                                              double qx, double qy, TopK<K>& top) {
+    const unsigned long long hs = dv.headS[cell], hn = dv.headN[cell];
+    for (int p = ((unsigned int)(hs >> 32) == tagS) ? (int)(unsigned int)hs : -1; p >= 0; p = dv.next[p]) {
+        const double2 t = dv.pos[p];
+        const double dx = qx - t.x, dy = qy - t.y;
+        top.push(dx * dx + dy * dy, p);
+    }
+    for (int p = ((unsigned int)(hn >> 32) == tagN) ? (int)(unsigned int)hn : -1; p >= 0; p = dv.next[p]) {
+        const double2 t = dv.pos[p];
+        const double dx = qx - t.x, dy = qy - t.y;
+        top.push(dx * dx + dy * dy, p);
+    }
+}
+
+// thread-per-query ring search over S and N (same stopping rule as knn_links_query)
+template <int K>
+__device__ __forceinline__ void knn_dual_query(const DualView& dv, double qx, double qy, TopK<K>& top) {
+    top.init();
+    const int shift = dv.geom[0], gw = dv.geom[1], gh = dv.geom[2];
+    const unsigned int tagS = (unsigned int)dv.geom[4], tagN = (unsigned int)dv.geom[5];
+    const int c = 1 << shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
+    cx = min(cx, gw - 1);
+    cy = min(cy, gh - 1);
+    const int rmax = max(gw, gh);
+    for (int r = 0; r <= rmax; ++r) {
+        const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+        for (int y = max(ylo, 0); y <= min(yhi, gh - 1); ++y) {
+            if (y == ylo || y == yhi) {
+                for (int x = max(xlo, 0); x <= min(xhi, gw - 1); ++x)
+                    knn_dual_cell<K>(dv, y * gw + x, tagS, tagN, qx, qy, top);
+            } else {
+                if (xlo >= 0) knn_dual_cell<K>(dv, y * gw + xlo, tagS, tagN, qx, qy, top);
+                if (xhi < gw) knn_dual_cell<K>(dv, y * gw + xhi, tagS, tagN, qx, qy, top);
+            }
+        }
+        double bound = INFINITY;
+        if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
+        if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
+        if (xhi < gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (bound == INFINITY) break;
+        if (bound > 0.0 && top.d2[K - 1] < bound * bound) break;
+    }
+}
+
+// warp-per-query variant (lanes split the cells of a ring; see knn_links_query_warp)
+template <int K>
+__device__ __forceinline__ void knn_dual_query_warp(const DualView& dv, double qx, double qy, TopK<K>& out) {
+    const int lane = threadIdx.x & 31;
+    TopK<K> mine;
+    mine.init();
+    out.init();
+    const int shift = dv.geom[0], gw = dv.geom[1], gh = dv.geom[2];
+    const unsigned int tagS = (unsigned int)dv.geom[4], tagN = (unsigned int)dv.geom[5];
+    const int c = 1 << shift;
+    int cx = (qx >= 0.0) ? ((int)fmin(qx, 1.0e9) >> shift) : 0;
+    int cy = (qy >= 0.0) ? ((int)fmin(qy, 1.0e9) >> shift) : 0;
+    cx = min(cx, gw - 1);
+    cy = min(cy, gh - 1);
+    const int rmax = max(gw, gh);
+    for (int r = 1; r <= rmax; ++r) {
+        if (r == 1) {
+            if (lane < 9) {
+                const int x = cx + (lane % 3) - 1, y = cy + (lane / 3) - 1;
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_dual_cell<K>(dv, y * gw + x, tagS, tagN, qx, qy, mine);
+            }
+        } else {
+            const int ncells = 8 * r;
+            for (int j = lane; j < ncells; j += 32) {
+                int dx, dy;
+                if (j <= 2 * r) { dx = -r + j; dy = -r; }
+                else if (j <= 4 * r + 1) { dx = -r + (j - 2 * r - 1); dy = r; }
+                else if (j <= 6 * r) { dx = -r; dy = -r + 1 + (j - 4 * r - 2); }
+                else { dx = r; dy = -r + 1 + (j - 6 * r - 1); }
+                const int x = cx + dx, y = cy + dy;
+                if (x >= 0 && x < gw && y >= 0 && y < gh) knn_dual_cell<K>(dv, y * gw + x, tagS, tagN, qx, qy, mine);
+            }
+        }
+        warp_merge_topk<K>(mine, out);
+        const int ylo = cy - r, yhi = cy + r, xlo = cx - r, xhi = cx + r;
+        double bound = INFINITY;
+        if (xlo > 0) bound = fmin(bound, qx - (double)(xlo * c));
+        if (ylo > 0) bound = fmin(bound, qy - (double)(ylo * c));
+        if (xhi < gw - 1) bound = fmin(bound, (double)((xhi + 1) * c) - qx);
+        if (yhi < gh - 1) bound = fmin(bound, (double)((yhi + 1) * c) - qy);
+        if (bound == INFINITY) break;
+        if (bound > 0.0 && out.d2[K - 1] < bound * bound) break;
+    }
+}
+
+__device__ __forceinline__ void link_push(unsigned long long* head, int* next, int cell, unsigned int tag, int i) {
+    const unsigned long long old =
+        atomicExch(&head[cell], ((unsigned long long)tag << 32) | (unsigned long long)(unsigned int)i);
+    next[i] = ((unsigned int)(old >> 32) == tag) ? (int)(unsigned int)old : -1;
+}
+
+// Start of a resample period: clears the tombstones, links the stable particles into S and the non-stable ones into
+// N (+ the non-stable list), fixes the geometry from the count.  The last block publishes geometry and both tags.
+__global__ void __launch_bounds__(kThreads) period_begin_kernel(
+    const double2* __restrict__ pos, const uint8_t* __restrict__ stable, int n_host, const int* d_n, int W, int H,
+    int min_shift, int fixed_shift, int bias_x4, int* geom, unsigned int* epochS, unsigned int* epochN, int* ticket,
+    unsigned long long* headS, unsigned long long* headN, int* next, uint8_t* del, int* ns_list, int* n_ns, int* n_dead,
+    int* status) {
+    const int n = d_n ? *d_n : n_host;
+    const int shift = link_shift_for(n, H, W, min_shift, fixed_shift, bias_x4);
+    const int gw = (W + (1 << shift) - 1) >> shift, gh = (H + (1 << shift) - 1) >> shift;
+    const unsigned int tagS = *epochS + 1u, tagN = *epochN + 1u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double2 p = pos[i];
+        const uint8_t st = stable[i];
+        del[i] = 0;
+        bool bad = false;
+        const int cx = cell_coord(p.x, shift, gw, bad);
+        const int cy = cell_coord(p.y, shift, gh, bad);
+        if (p.x != p.x || p.y != p.y) atomicOr(status, AOSLO_DEV_NAN);
+        else if (bad || p.x >= (double)W || p.y >= (double)H) atomicOr(status, AOSLO_DEV_ESCAPED);
+        if (st) {
+            link_push(headS, next, cy * gw + cx, tagS, i);
+        } else {
+            link_push(headN, next, cy * gw + cx, tagN, i);
+            ns_list[atomicAdd(n_ns, 1)] = i;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            geom[0] = shift; geom[1] = gw; geom[2] = gh; geom[3] = gw * gh; geom[4] = (int)tagS; geom[5] = (int)tagN;
+            *epochS = tagS;
+            *epochN = tagN;
+            *n_dead = 0;
+            *ticket = 0;
+        }
+    }
+}
+
+// After the move: the non-stable survivors take their moved positions (Jacobi: every force was computed from the
+// old ones) and are linked into a fresh N structure.
+__global__ void __launch_bounds__(kThreads) ns_relink_kernel(const int* __restrict__ ns_list,
+                                                             const int* __restrict__ n_ns,
+                                                             const double2* __restrict__ moved, double2* pos,
+                                                             const uint8_t* __restrict__ del, int W, int H, int* geom,
+                                                             unsigned int* epochN, int* ticket,
+                                                             unsigned long long* headN, int* next, int* status) {
+    const int total = *n_ns;
+    const int shift = geom[0], gw = geom[1], gh = geom[2];
+    const unsigned int tagN = *epochN + 1u;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) {
+        const int i = ns_list[q];
+        if (del[i]) continue;
+        const double2 p = moved[i];
+        pos[i] = p;
+        bool bad = false;
+        const int cx = cell_coord(p.x, shift, gw, bad);
+        const int cy = cell_coord(p.y, shift, gh, bad);
+        if (p.x != p.x || p.y != p.y) atomicOr(status, AOSLO_DEV_NAN);
+        else if (bad || p.x >= (double)W || p.y >= (double)H) atomicOr(status, AOSLO_DEV_ESCAPED);
+        link_push(headN, next, cy * gw + cx, tagN, i);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            geom[5] = (int)tagN;
+            *epochN = tagN;
+            *ticket = 0;
+        }
+    }
+}
+
+// force + move of the non-stable survivors (one warp per particle; utils.py:112-134 / :43-58 and
+// pipeline_with_delitions.py:215-245), moved positions into `moved[i]`
+template <int K, typename T>
+__global__ void __launch_bounds__(kThreads) dual_force_move_kernel(
+    DualView dv, const int* __restrict__ ns_list, const int* __restrict__ n_ns, const uint8_t* __restrict__ del,
+    int kk, int energy_type, double p0, double p1, double p2, const T* __restrict__ grad, int H, int W, double lb,
+    double ld, int step_mode, double2* __restrict__ moved, int* status, const RunParams* rp) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_ns;
+    if (rp) { kk = rp->kk; p0 = rp->e0; p1 = rp->e1; p2 = rp->e2; lb = rp->lb; ld = rp->ld; }
+    for (int q = warp; q < total; q += nwarps) {
+        const int i = ns_list[q];
+        if (del[i]) continue;
+        double2 p = dv.pos[i];
+        TopK<K> top;
+        knn_dual_query_warp<K>(dv, p.x, p.y, top);
+        int nb = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (lane == j) nb = top.idx[j];
+        double tx = 0.0, ty = 0.0;
+        if (lane >= 1 && lane < kk) {
+            double2 qn = (nb != 0x7fffffff) ? dv.pos[nb] : make_double2(NAN, NAN);
+            double vx = p.x - qn.x, vy = p.y - qn.y;
+            double nrm = sqrt(vx * vx + vy * vy);
+            if (energy_type == AOSLO_ENERGY_PIT) {
+                double f = energy_pit2(nrm, p0, p1, p2);
+                tx = (vx / nrm) * f;
+                ty = (vy / nrm) * f;
+            } else {
+                double den = nrm / (p1 * p1);
+                tx = vx / den;
+                ty = vy / den;
+            }
+        }
+        double fx = __shfl_sync(0xffffffffu, tx, 1), fy = __shfl_sync(0xffffffffu, ty, 1);
+        for (int j = 2; j < kk; ++j) {
+            fx += __shfl_sync(0xffffffffu, tx, j);
+            fy += __shfl_sync(0xffffffffu, ty, j);
+        }
+        if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
+        if (lane == 0) {
+            bool shortfall = false;
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (j == kk - 1 && top.idx[j] == 0x7fffffff) shortfall = true;
+            if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            if (step_mode >= 0) move_one<T>(p, make_double2(fx, fy), grad, H, W, lb, ld, step_mode, status);
+            moved[i] = p;
+        }
+    }
+}
+
+// deletion rows of the non-stable survivors (kNN(2) at the moved positions) + the compact active list
+__global__ void __launch_bounds__(kThreads) dual_rows_kernel(DualView dv, const uint8_t* __restrict__ stable,
+                                                             const uint8_t* __restrict__ del,
+                                                             const int* __restrict__ ns_list,
+                                                             const int* __restrict__ n_ns, double thr,
+                                                             const double* d_thr, int32_t* knn_idx, double* knn_d2,
+                                                             int* active, int* n_active, int* fallback) {
+    const int lane = threadIdx.x & 31;
+    if (d_thr) thr = *d_thr;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_ns;
+    for (int q = warp; q < total; q += nwarps) {
+        const int i = ns_list[q];
+        if (del[i]) continue;
+        double2 p = dv.pos[i];
+        TopK<2> top;
+        knn_dual_query_warp<2>(dv, p.x, p.y, top);
+        if (lane == 0) {
+            const bool ok = top.idx[1] != 0x7fffffff;
+            const int from = top.idx[0], to = ok ? top.idx[1] : -1;
+            // another particle at distance 0, or nothing found at all: the all-rows path decides
+            if (from != i || !ok || top.d2[1] == 0.0) atomicExch(fallback, 1);
+            knn_idx[2 * (size_t)i] = from;
+            knn_idx[2 * (size_t)i + 1] = to;
+            knn_d2[2 * (size_t)i] = top.d2[0];
+            knn_d2[2 * (size_t)i + 1] = top.d2[1];
+            if (ok && from == i && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
+        }
+    }
+}
+
+// all-rows fallback (a coincidence makes a stable row active, utils.py:253): every survivor's row
+__global__ void __launch_bounds__(kThreads) dual_rows_all_kernel(DualView dv, const uint8_t* __restrict__ stable,
+                                                                 const uint8_t* __restrict__ del, int n_host,
+                                                                 const int* d_n, double thr, const double* d_thr,
+                                                                 int32_t* knn_idx, double* knn_d2, int* active,
+                                                                 int* n_active, int* status, const int* gate) {
+    if (*gate == 0) return;
+    const int n = d_n ? *d_n : n_host;
+    if (d_thr) thr = *d_thr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (del[i]) continue;
+        const double2 p = dv.pos[i];
+        TopK<2> top;
+        knn_dual_query<2>(dv, p.x, p.y, top);
+        const bool ok = top.idx[1] != 0x7fffffff;
+        if (!ok) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+        const int from = top.idx[0], to = ok ? top.idx[1] : -1;
+        knn_idx[2 * (size_t)i] = from;
+        knn_idx[2 * (size_t)i + 1] = to;
+        knn_d2[2 * (size_t)i] = top.d2[0];
+        knn_d2[2 * (size_t)i + 1] = top.d2[1];
+        if (ok && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
+    }
+}
+
+// wavefront resolution of the active rows by ONE block (see delete_resolve_small_kernel); a victim becomes a
+// tombstone: del = 1, position NaN (it drops out of every later neighbour search by itself)
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) dual_resolve_kernel(
+    double2* pos, const int32_t* __restrict__ knn_idx, const int* __restrict__ active_a, int* n_active_a,
+    const int* __restrict__ active_b, int* n_active_b, int* fallback, unsigned int* d_epoch, int W, int H,
+    const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del, uint8_t* astate, int* n_dead, int* status) {
+    __shared__ int s_pending, s_deleted;
+    const unsigned int epoch = *d_epoch;
+    const bool use_b = *fallback != 0;
+    const int* __restrict__ active = use_b ? active_b : active_a;
+    const int na = use_b ? *n_active_b : *n_active_a;
+    if (threadIdx.x == 0) s_deleted = 0;
+    for (int a = threadIdx.x; a < na; a += blockDim.x) astate[a] = 1;
+    __syncthreads();
+    for (unsigned int round = 1; na > 0; ++round) {
+        const unsigned long long hi = ((unsigned long long)epoch << 44) | ((unsigned long long)round << 32);
+        for (int a = threadIdx.x; a < na; a += blockDim.x) {
+            if (!astate[a]) continue;
+            const int i = active[a];
+            const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i])], key);
+            atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i + 1])], key);
+        }
+        if (threadIdx.x == 0) s_pending = 0;
+        __threadfence();
+        __syncthreads();
+        int pending = 0;
+        for (int a = threadIdx.x; a < na; a += blockDim.x) {
+            if (!astate[a]) continue;
+            const int i = active[a];
+            const int from = __ldcg(&knn_idx[2 * (size_t)i]), to = __ldcg(&knn_idx[2 * (size_t)i + 1]);
+            const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
+            if (__ldcg(&touch[from]) == key && __ldcg(&touch[to]) == key) {
+                if (!__ldcg(&del[from]) && !__ldcg(&del[to])) {
+                    const double e1 = energy_at<T>(Rb, pos[from], W, H, status);
+                    const double e2 = energy_at<T>(Rb, pos[to], W, H, status);
+                    const int victim = (e1 < e2) ? from : to;
+                    __stcg(&del[victim], (uint8_t)1);
+                    pos[victim] = make_double2(NAN, NAN);
+                    atomicAdd(&s_deleted, 1);
+                }
+                astate[a] = 0;
+            } else {
+                ++pending;
+            }
+        }
+        if (pending) atomicAdd(&s_pending, pending);
+        __threadfence();
+        __syncthreads();
+        const int left = s_pending;
+        __syncthreads();
+        if (left == 0) break;
+        if (round >= 4000u) { if (threadIdx.x == 0) atomicOr(status, AOSLO_DEV_CAPACITY); break; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                   // ready for the next call
+        *d_epoch = epoch + 1;
+        *n_dead += s_deleted;
+        *n_active_a = 0;
+        *n_active_b = 0;
+        *fallback = 0;
+    }
+}
+
+struct KeepAliveOp {                           // order-preserving compaction of the survivors
+    const double2* pos;
+    const uint8_t* stable;
+    const uint8_t* del;
+    double2* pos_out;
+    uint8_t* stable_out;
+    __device__ int value(int i) const { return del[i] ? 0 : 1; }
+    __device__ void emit(int i, int v, int dst) const {
+        if (!v) return;
+        pos_out[dst] = pos[i];
+        stable_out[dst] = stable[i];
+    }
+};
+
+__global__ void __launch_bounds__(kThreads) copy_particles_kernel(const double2* __restrict__ pos_in,
+                                                                  const uint8_t* __restrict__ st_in, const int* cnt_in,
+                                                                  double2* __restrict__ pos_out,
+                                                                  uint8_t* __restrict__ st_out, int* cnt_out,
+                                                                  int* n_dead) {
+    const int n = *cnt_in;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        pos_out[i] = pos_in[i];
+        st_out[i] = st_in[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *cnt_out = n;                              // no other thread of this kernel reads it
+        if (n_dead) *n_dead = 0;
+    }
+}
+
+// metrics over the survivors (see metrics_pass_kernel); GT -> nearest particle searches S and N
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dual_metrics_kernel(
+    CellView cl_g, DualView dv, const uint8_t* __restrict__ stable, const uint8_t* __restrict__ del, int n_host,
+    const int* d_n, const int* d_n_dead, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W,
+    int bx, int by, int* icount /*[9]: 8 counts + block ticket*/, MetricsPartial* partials, int iteration,
+    aoslo_metrics_record* rec, int* status, const int* d_n_gt, int* d_rec_idx, const int* d_iteration) {
+    const int n = d_n ? *d_n : n_host;
+    if (d_n_gt) n_gt = *d_n_gt;
+    const int total = n + n_gt;
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tp1 tp2 fn1 fn2 fp1 fp2 nin nst
+    Moments mp, mg;
+    mp.init(); mg.init();
+    double energy = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        TopK<1> top;
+        if (i < n) {
+            if (del[i]) continue;
+            const double2 p = dv.pos[i];
+            knn_cells_query<1>(cl_g, p.x, p.y, top);
+            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            const double d = sqrt(top.d2[0]);
+            const bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) &&
+                                (p.y < (double)(H - by));
+            c[6] += inside;
+            c[4] += inside && (d > 1.42);
+            c[5] += inside && (d > 2.83);
+            c[7] += stable[i] ? 1 : 0;
+            mp.add(d);
+            energy += energy_at<T>(Rb, p, W, H, status);
+        } else {
+            const double2 g = gt[i - n];
+            knn_dual_query<1>(dv, g.x, g.y, top);
+            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            const double d = sqrt(top.d2[0]);
+            c[0] += (d <= 1.42); c[2] += (d > 1.42);
+            c[1] += (d <= 2.83); c[3] += (d > 2.83);
+            mg.add(d);
+        }
+    }
+    __shared__ MetricsPartial s_part[kThreads / 32];
+    __shared__ int s_c[8];
+    if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int v = c[j];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[j], v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        Moments a = shfl_down_moments(mp, o), b = shfl_down_moments(mg, o);
+        double e = __shfl_down_sync(0xffffffffu, energy, o);
+        mp.merge(a); mg.merge(b); energy += e;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_part[threadIdx.x >> 5].p2g = mp;
+        s_part[threadIdx.x >> 5].g2p = mg;
+        s_part[threadIdx.x >> 5].energy = energy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MetricsPartial acc = s_part[0];
+        for (int w = 1; w < kThreads / 32; ++w) {
+            acc.p2g.merge(s_part[w].p2g);
+            acc.g2p.merge(s_part[w].g2p);
+            acc.energy += s_part[w].energy;
+        }
+        acc.pad_ = 0.0;
+        partials[blockIdx.x] = acc;
+    }
+    if (threadIdx.x < 8 && s_c[threadIdx.x]) atomicAdd(&icount[threadIdx.x], s_c[threadIdx.x]);
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&icount[8], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     MetricsPartial acc;
     acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {      // nblocks <= blockDim in practice
-        acc.p2g.merge(partials[b].p2g);
-        acc.g2p.merge(partials[b].g2p);
-        acc.energy += partials[b].energy;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) {
+        const MetricsPartial pb = __ldcg_partial(partials + b);
+        acc.p2g.merge(pb.p2g);
+        acc.g2p.merge(pb.g2p);
+        acc.energy += pb.energy;
     }
     for (int o = 16; o > 0; o >>= 1) {
         Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
         double e = __shfl_down_sync(0xffffffffu, acc.energy, o);
         acc.p2g.merge(a); acc.g2p.merge(g); acc.energy += e;
     }
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        int nw = blockDim.x >> 5;
-        if (threadIdx.x < nw) acc = s_part[threadIdx.x];
+        if (threadIdx.x < kThreads / 32) acc = s_part[threadIdx.x];
         else { acc.p2g.init(); acc.g2p.init(); acc.energy = 0.0; }
         for (int o = 16; o > 0; o >>= 1) {
             Moments a = shfl_down_moments(acc.p2g, o), g = shfl_down_moments(acc.g2p, o);
@@ -1434,19 +1908,32 @@ __global__ void __launch_bounds__(kScanThreads) metrics_finalize_kernel(
         }
     }
     if (threadIdx.x != 0) return;
-    const int n = d_n ? *d_n : n_host;
+    const int n_alive = n - *d_n_dead;
+    if (d_rec_idx) { const int slot = *d_rec_idx; rec += slot; *d_rec_idx = slot + 1; }
+    if (d_iteration) iteration = *d_iteration;
     rec->iteration = iteration;
-    rec->n_particles = n;
-    rec->n_stable = icount[7];
+    rec->n_particles = n_alive;
+    rec->n_stable = __ldcg(&icount[7]);
     rec->n_gt = n_gt;
-    rec->tp[0] = icount[0]; rec->tp[1] = icount[1];
-    rec->fn[0] = icount[2]; rec->fn[1] = icount[3];
-    rec->fp[0] = icount[4]; rec->fp[1] = icount[5];
-    rec->n_in_image = icount[6];
+    rec->tp[0] = __ldcg(&icount[0]); rec->tp[1] = __ldcg(&icount[1]);
+    rec->fn[0] = __ldcg(&icount[2]); rec->fn[1] = __ldcg(&icount[3]);
+    rec->fp[0] = __ldcg(&icount[4]); rec->fp[1] = __ldcg(&icount[5]);
+    rec->n_in_image = __ldcg(&icount[6]);
     rec->pad_ = 0;
     rec->sum_p2g = acc.p2g.sum; rec->sum_g2p = acc.g2p.sum;
-    rec->var_p2g = acc.p2g.m2 / acc.p2g.n; rec->var_g2p = acc.g2p.m2 / acc.g2p.n;
+    rec->var_p2g = acc.p2g.var((double)n_alive); rec->var_g2p = acc.g2p.var((double)n_gt);
     rec->blob_energy_sum = acc.energy;
+}
+
+__global__ void __launch_bounds__(kThreads) dual_count_stable_kernel(const uint8_t* __restrict__ stable,
+                                                                     const uint8_t* __restrict__ del, int n_host,
+                                                                     const int* d_n, int* out) {
+    const int n = d_n ? *d_n : n_host;
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        c += (stable[i] && !del[i]) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 __global__ void set_all_stable_kernel(uint8_t* stable, int n_host, const int* d_n, uint8_t v) {
@@ -1734,6 +2221,123 @@ int stage_set_stable(aoslo_ctx* ctx, cudaStream_t s, uint8_t* d_stable, int n, u
 int stage_count_stable(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_stable, int n, int* d_out, const int* d_n) {
     AOSLO_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int), s));
     count_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, d_n, d_out);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// ---- host drivers of the run loop's tombstone / dual-structure scheme (aoslo_run, canonical tie order) ----
+static DualView dual_view(aoslo_ctx* ctx) {
+    return DualView{ctx->d_link_geom, ctx->lk_p.head, ctx->d_head_n, ctx->lk_p.next, (const double2*)ctx->d_pos[0]};
+}
+
+// start of a resample period on buffer 0: tombstones cleared, S / N linked, non-stable list collected
+int stage_period_begin(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n) {
+    int* n_ns = ctx->d_counters + 13;
+    AOSLO_CUDA(cudaMemsetAsync(n_ns, 0, sizeof(int), s));
+    period_begin_kernel<<<ctx->nb, kThreads, 0, s>>>(
+        (const double2*)ctx->d_pos[0], ctx->d_stable[0], n_bound, d_n, ctx->W, ctx->H, ctx->lk_p.min_shift,
+        ctx->lk_p.fixed_shift, kLinkBiasSteady, ctx->d_link_geom, ctx->d_link_epoch, ctx->d_link_epoch_n,
+        ctx->d_link_epoch_ticket, ctx->lk_p.head, ctx->d_head_n, ctx->lk_p.next, ctx->d_del, ctx->d_ns_list, n_ns,
+        ctx->d_counters + 7, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// one iteration: force + move of the non-stable survivors, re-link, deletion rows, resolve (no compaction)
+int stage_dual_step(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, int k, int energy_type, double p0,
+                    double p1, double p2, const void* d_grad, const void* d_Rb, int field_dtype, int H, int W, double lb,
+                    double ld, int step_mode, double del_thr, const RunParams* rp, int phases) {
+    // phases: bit 0 = force + move, bit 1 = re-link + deletion (the caller may put a time stamp between them)
+    if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
+    int* n_ns = ctx->d_counters + 13;
+    int* n_active = ctx->d_counters + 12;
+    int* n_active_b = ctx->d_counters + 14;
+    int* fallback = ctx->d_counters + 15;
+    int* n_dead = ctx->d_counters + 7;
+    const DualView dv = dual_view(ctx);
+    const int kk = k + 1;
+    if (phases & 1) {
+#define AOSLO_DFM(KT, TT)                                                                                         \
+    dual_force_move_kernel<KT, TT><<<ctx->nb, kThreads, 0, s>>>(dv, ctx->d_ns_list, n_ns, ctx->d_del, kk,          \
+                                                                energy_type, p0, p1, p2, (const TT*)d_grad, H, W,  \
+                                                                lb, ld, step_mode, (double2*)ctx->d_pos_tmp,       \
+                                                                ctx->d_status, rp)
+    if (field_dtype == AOSLO_F32) {
+        if (kk <= 2) AOSLO_DFM(2, float); else if (kk <= 4) AOSLO_DFM(4, float); else AOSLO_DFM(8, float);
+    } else {
+        if (kk <= 2) AOSLO_DFM(2, double); else if (kk <= 4) AOSLO_DFM(4, double); else AOSLO_DFM(8, double);
+    }
+#undef AOSLO_DFM
+    AOSLO_LAUNCH_CHECK();
+    }
+    if (!(phases & 2)) return AOSLO_OK;
+    ns_relink_kernel<<<ctx->nb, kThreads, 0, s>>>(ctx->d_ns_list, n_ns, (const double2*)ctx->d_pos_tmp,
+                                                  (double2*)ctx->d_pos[0], ctx->d_del, W, H, ctx->d_link_geom,
+                                                  ctx->d_link_epoch_n, ctx->d_link_epoch_ticket, ctx->d_head_n,
+                                                  ctx->lk_p.next, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    dual_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(dv, ctx->d_stable[0], ctx->d_del, ctx->d_ns_list, n_ns, del_thr,
+                                                  rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2,
+                                                  ctx->d_active, n_active, fallback);
+    AOSLO_LAUNCH_CHECK();
+    dual_rows_all_kernel<<<ctx->nb, kThreads, 0, s>>>(dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, del_thr,
+                                                      rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2,
+                                                      ctx->d_active_b, n_active_b, ctx->d_status, fallback);
+    AOSLO_LAUNCH_CHECK();
+    if (field_dtype == AOSLO_F32)
+        dual_resolve_kernel<float><<<1, kScanThreads, 0, s>>>((double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_active,
+                                                              n_active, ctx->d_active_b, n_active_b, fallback,
+                                                              ctx->d_epoch, W, H, (const float*)d_Rb, ctx->d_touch,
+                                                              ctx->d_del, ctx->d_rowstate, n_dead, ctx->d_status);
+    else
+        dual_resolve_kernel<double><<<1, kScanThreads, 0, s>>>((double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_active,
+                                                               n_active, ctx->d_active_b, n_active_b, fallback,
+                                                               ctx->d_epoch, W, H, (const double*)d_Rb, ctx->d_touch,
+                                                               ctx->d_del, ctx->d_rowstate, n_dead, ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// order-preserving compaction of the survivors of buffer 0 (through buffer 1 and back); *d_n becomes the survivor
+// count, the tombstone counter is reset
+int stage_compact(aoslo_ctx* ctx, cudaStream_t s, int n_bound, int* d_n, int* d_n_scratch, int scan_hint) {
+    KeepAliveOp op{(const double2*)ctx->d_pos[0], ctx->d_stable[0], ctx->d_del, (double2*)ctx->d_pos[1],
+                   ctx->d_stable[1]};
+    AOSLO_TRY(ordered_scan(ctx, s, op, scan_hint > 0 ? scan_hint : n_bound, n_bound, d_n, d_n_scratch, nullptr, 0,
+                           nullptr));
+    copy_particles_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)ctx->d_pos[1], ctx->d_stable[1], d_n_scratch,
+                                                       (double2*)ctx->d_pos[0], ctx->d_stable[0], d_n,
+                                                       ctx->d_counters + 7);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_dual_metrics(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, const double* d_gt, int n_gt,
+                       const void* d_Rb, int field_dtype, int H, int W, int bx, int by, int iteration,
+                       aoslo_metrics_record* d_rec, const int* d_n_gt, int* d_rec_idx, const int* d_iteration) {
+    if (n_gt > ctx->gt_cap) return AOSLO_ERR_CAPACITY;
+    if (n_gt < 1) return AOSLO_ERR_INVALID;
+    int* icount = ctx->d_counters + 16;
+    AOSLO_CUDA(cudaMemsetAsync(icount, 0, sizeof(int) * 9, s));
+    MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
+    const DualView dv = dual_view(ctx);
+    if (field_dtype == AOSLO_F32)
+        dual_metrics_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
+            view_of(ctx->cl_g), dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, ctx->d_counters + 7,
+            (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, icount, partials, iteration, d_rec,
+            ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
+    else
+        dual_metrics_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
+            view_of(ctx->cl_g), dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, ctx->d_counters + 7,
+            (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, icount, partials, iteration, d_rec,
+            ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+int stage_dual_count_stable(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, int* d_out) {
+    AOSLO_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int), s));
+    dual_count_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(ctx->d_stable[0], ctx->d_del, n_bound, d_n, d_out);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
