@@ -1652,74 +1652,16 @@ __global__ void __launch_bounds__(kThreads) dual_force_move_kernel(
     }
 }
 
-// deletion rows of the non-stable survivors (kNN(2) at the moved positions) + the compact active list
-__global__ void __launch_bounds__(kThreads) dual_rows_kernel(DualView dv, const uint8_t* __restrict__ stable,
-                                                             const uint8_t* __restrict__ del,
-                                                             const int* __restrict__ ns_list,
-                                                             const int* __restrict__ n_ns, double thr,
-                                                             const double* d_thr, int32_t* knn_idx, double* knn_d2,
-                                                             int* active, int* n_active, int* fallback) {
-    const int lane = threadIdx.x & 31;
-    if (d_thr) thr = *d_thr;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = *n_ns;
-    for (int q = warp; q < total; q += nwarps) {
-        const int i = ns_list[q];
-        if (del[i]) continue;
-        double2 p = dv.pos[i];
-        TopK<2> top;
-        knn_dual_query_warp<2>(dv, p.x, p.y, top);
-        if (lane == 0) {
-            const bool ok = top.idx[1] != 0x7fffffff;
-            const int from = top.idx[0], to = ok ? top.idx[1] : -1;
-            // another particle at distance 0, or nothing found at all: the all-rows path decides
-            if (from != i || !ok || top.d2[1] == 0.0) atomicExch(fallback, 1);
-            knn_idx[2 * (size_t)i] = from;
-            knn_idx[2 * (size_t)i + 1] = to;
-            knn_d2[2 * (size_t)i] = top.d2[0];
-            knn_d2[2 * (size_t)i + 1] = top.d2[1];
-            if (ok && from == i && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
-        }
-    }
-}
-
-// all-rows fallback (a coincidence makes a stable row active, utils.py:253): every survivor's row
-__global__ void __launch_bounds__(kThreads) dual_rows_all_kernel(DualView dv, const uint8_t* __restrict__ stable,
-                                                                 const uint8_t* __restrict__ del, int n_host,
-                                                                 const int* d_n, double thr, const double* d_thr,
-                                                                 int32_t* knn_idx, double* knn_d2, int* active,
-                                                                 int* n_active, int* status, const int* gate) {
-    if (*gate == 0) return;
-    const int n = d_n ? *d_n : n_host;
-    if (d_thr) thr = *d_thr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (del[i]) continue;
-        const double2 p = dv.pos[i];
-        TopK<2> top;
-        knn_dual_query<2>(dv, p.x, p.y, top);
-        const bool ok = top.idx[1] != 0x7fffffff;
-        if (!ok) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-        const int from = top.idx[0], to = ok ? top.idx[1] : -1;
-        knn_idx[2 * (size_t)i] = from;
-        knn_idx[2 * (size_t)i + 1] = to;
-        knn_d2[2 * (size_t)i] = top.d2[0];
-        knn_d2[2 * (size_t)i + 1] = top.d2[1];
-        if (ok && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
-    }
-}
-
-// wavefront resolution of the active rows by ONE block (see delete_resolve_small_kernel); a victim becomes a
-// tombstone: del = 1, position NaN (it drops out of every later neighbour search by itself)
+// Wavefront resolution of the active rows by ONE block (see delete_resolve_small_kernel); a victim becomes a
+// tombstone: del = 1, position NaN (it drops out of every later neighbour search by itself).  Called by the last
+// block of dual_rows_kernel.
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) dual_resolve_kernel(
-    double2* pos, const int32_t* __restrict__ knn_idx, const int* __restrict__ active_a, int* n_active_a,
-    const int* __restrict__ active_b, int* n_active_b, int* fallback, unsigned int* d_epoch, int W, int H,
-    const T* __restrict__ Rb, unsigned long long* touch, uint8_t* del, uint8_t* astate, int* n_dead, int* status) {
+__device__ void dual_resolve_block(double2* pos, const int32_t* knn_idx, const int* active, int* n_active,
+                                   unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb,
+                                   unsigned long long* touch, uint8_t* del, uint8_t* astate, int* n_dead, int* status) {
     __shared__ int s_pending, s_deleted;
     const unsigned int epoch = *d_epoch;
-    const bool use_b = *fallback != 0;
-    const int* __restrict__ active = use_b ? active_b : active_a;
-    const int na = use_b ? *n_active_b : *n_active_a;
+    const int na = __ldcg(n_active);
     if (threadIdx.x == 0) s_deleted = 0;
     for (int a = threadIdx.x; a < na; a += blockDim.x) astate[a] = 1;
     __syncthreads();
@@ -1727,7 +1669,7 @@ __global__ void __launch_bounds__(kScanThreads) dual_resolve_kernel(
         const unsigned long long hi = ((unsigned long long)epoch << 44) | ((unsigned long long)round << 32);
         for (int a = threadIdx.x; a < na; a += blockDim.x) {
             if (!astate[a]) continue;
-            const int i = active[a];
+            const int i = __ldcg(&active[a]);
             const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
             atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i])], key);
             atomicMax(&touch[__ldcg(&knn_idx[2 * (size_t)i + 1])], key);
@@ -1738,13 +1680,15 @@ __global__ void __launch_bounds__(kScanThreads) dual_resolve_kernel(
         int pending = 0;
         for (int a = threadIdx.x; a < na; a += blockDim.x) {
             if (!astate[a]) continue;
-            const int i = active[a];
+            const int i = __ldcg(&active[a]);
             const int from = __ldcg(&knn_idx[2 * (size_t)i]), to = __ldcg(&knn_idx[2 * (size_t)i + 1]);
             const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
             if (__ldcg(&touch[from]) == key && __ldcg(&touch[to]) == key) {
                 if (!__ldcg(&del[from]) && !__ldcg(&del[to])) {
-                    const double e1 = energy_at<T>(Rb, pos[from], W, H, status);
-                    const double e2 = energy_at<T>(Rb, pos[to], W, H, status);
+                    const double2 pf = make_double2(__ldcg(&pos[from].x), __ldcg(&pos[from].y));
+                    const double2 pt = make_double2(__ldcg(&pos[to].x), __ldcg(&pos[to].y));
+                    const double e1 = energy_at<T>(Rb, pf, W, H, status);
+                    const double e2 = energy_at<T>(Rb, pt, W, H, status);
                     const int victim = (e1 < e2) ? from : to;
                     __stcg(&del[victim], (uint8_t)1);
                     pos[victim] = make_double2(NAN, NAN);
@@ -1767,10 +1711,62 @@ __global__ void __launch_bounds__(kScanThreads) dual_resolve_kernel(
     if (threadIdx.x == 0) {                   // ready for the next call
         *d_epoch = epoch + 1;
         *n_dead += s_deleted;
-        *n_active_a = 0;
-        *n_active_b = 0;
-        *fallback = 0;
+        *n_active = 0;
     }
+}
+
+// Deletion of one iteration (utils.py:245-278 on the tombstone structure): rows of the non-stable survivors
+// (kNN(2) at the moved positions) -> compact active list -> the LAST block to finish resolves it (wavefront rounds,
+// one block; no second launch).
+//
+// Why the rows of the non-stable particles suffice.  A row is active only if its `from` -- the first entry of its
+// (d^2, index)-ordered neighbour list -- is non-stable and its neighbour is closer than the threshold.  `from` is the
+// row's own particle unless other particles sit at exactly the same position; then EVERY row of that coincident group
+// has the same two endpoints, the group's two lowest indices a < b, and only row a can act: the reference walks the
+// rows in index order, row a comes first and either deletes one of {a, b} or finds one of them already deleted, so the
+// later rows of the group find an endpoint deleted and do nothing.  Row a is active iff a is non-stable -- and then a
+// is in the non-stable list and `from == a` in its own row.  So: rows whose `from` is another particle are skipped,
+// stable rows never need to be looked at, and the result equals the sequential walk over all rows.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) dual_rows_kernel(DualView dv, double2* pos,
+                                                             const uint8_t* __restrict__ stable, uint8_t* del,
+                                                             const int* __restrict__ ns_list,
+                                                             const int* __restrict__ n_ns, double thr,
+                                                             const double* d_thr, int32_t* knn_idx, double* knn_d2,
+                                                             int* active, int* n_active, int* ticket,
+                                                             unsigned int* d_epoch, int W, int H,
+                                                             const T* __restrict__ Rb, unsigned long long* touch,
+                                                             uint8_t* astate, int* n_dead, int* status) {
+    const int lane = threadIdx.x & 31;
+    if (d_thr) thr = *d_thr;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = *n_ns;
+    for (int q = warp; q < total; q += nwarps) {
+        const int i = ns_list[q];
+        if (del[i]) continue;
+        double2 p = dv.pos[i];
+        TopK<2> top;
+        knn_dual_query_warp<2>(dv, p.x, p.y, top);
+        if (lane == 0) {
+            const bool ok = top.idx[1] != 0x7fffffff;
+            const int from = top.idx[0], to = ok ? top.idx[1] : -1;
+            if (!ok) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+            knn_idx[2 * (size_t)i] = from;
+            knn_idx[2 * (size_t)i + 1] = to;
+            knn_d2[2 * (size_t)i] = top.d2[0];
+            knn_d2[2 * (size_t)i + 1] = top.d2[1];
+            if (ok && from == i && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
+        }
+    }
+    __shared__ int s_last;
+    __threadfence();                           // this block's rows / list entries are visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ticket = 0;
+    dual_resolve_block<T>(pos, knn_idx, active, n_active, d_epoch, W, H, Rb, touch, del, astate, n_dead, status);
 }
 
 struct KeepAliveOp {                           // order-preserving compaction of the survivors
@@ -2251,8 +2247,6 @@ int stage_dual_step(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n,
     if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     int* n_ns = ctx->d_counters + 13;
     int* n_active = ctx->d_counters + 12;
-    int* n_active_b = ctx->d_counters + 14;
-    int* fallback = ctx->d_counters + 15;
     int* n_dead = ctx->d_counters + 7;
     const DualView dv = dual_view(ctx);
     const int kk = k + 1;
@@ -2276,25 +2270,20 @@ int stage_dual_step(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n,
                                                   ctx->d_link_epoch_n, ctx->d_link_epoch_ticket, ctx->d_head_n,
                                                   ctx->lk_p.next, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
-    dual_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(dv, ctx->d_stable[0], ctx->d_del, ctx->d_ns_list, n_ns, del_thr,
-                                                  rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2,
-                                                  ctx->d_active, n_active, fallback);
-    AOSLO_LAUNCH_CHECK();
-    dual_rows_all_kernel<<<ctx->nb, kThreads, 0, s>>>(dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, del_thr,
-                                                      rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2,
-                                                      ctx->d_active_b, n_active_b, ctx->d_status, fallback);
-    AOSLO_LAUNCH_CHECK();
     if (field_dtype == AOSLO_F32)
-        dual_resolve_kernel<float><<<1, kScanThreads, 0, s>>>((double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_active,
-                                                              n_active, ctx->d_active_b, n_active_b, fallback,
-                                                              ctx->d_epoch, W, H, (const float*)d_Rb, ctx->d_touch,
-                                                              ctx->d_del, ctx->d_rowstate, n_dead, ctx->d_status);
+        dual_rows_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
+            dv, (double2*)ctx->d_pos[0], ctx->d_stable[0], ctx->d_del, ctx->d_ns_list, n_ns, del_thr,
+            rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active,
+            ctx->d_link_epoch_ticket, ctx->d_epoch, W, H, (const float*)d_Rb, ctx->d_touch, ctx->d_rowstate, n_dead,
+            ctx->d_status);
     else
-        dual_resolve_kernel<double><<<1, kScanThreads, 0, s>>>((double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_active,
-                                                               n_active, ctx->d_active_b, n_active_b, fallback,
-                                                               ctx->d_epoch, W, H, (const double*)d_Rb, ctx->d_touch,
-                                                               ctx->d_del, ctx->d_rowstate, n_dead, ctx->d_status);
+        dual_rows_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
+            dv, (double2*)ctx->d_pos[0], ctx->d_stable[0], ctx->d_del, ctx->d_ns_list, n_ns, del_thr,
+            rp ? &rp->del_thr : nullptr, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active,
+            ctx->d_link_epoch_ticket, ctx->d_epoch, W, H, (const double*)d_Rb, ctx->d_touch, ctx->d_rowstate, n_dead,
+            ctx->d_status);
     AOSLO_LAUNCH_CHECK();
+    (void)n_bound; (void)d_n;
     return AOSLO_OK;
 }
 
