@@ -183,6 +183,8 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_link_epoch, 1));
     A(dmalloc(&c->d_link_epoch_ticket, 1));
     A(dmalloc(&c->d_link_epoch_n, 1));
+    A(dmalloc(&c->d_map_epoch, 1));
+    if (st == AOSLO_OK && cudaMemset(c->d_map_epoch, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_head_n, c->lk_p.ncell));
     if (st == AOSLO_OK && cudaMemset(c->d_link_epoch_n, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_head_n, 0, sizeof(unsigned long long) * c->lk_p.ncell) != cudaSuccess)
@@ -245,6 +247,8 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK) { unsigned int one = 1u; if (cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice) != cudaSuccess) st = AOSLO_ERR_CUDA; }
     if (st == AOSLO_OK && cudaMemset(c->d_counters, 0, sizeof(int) * 32) != cudaSuccess) st = AOSLO_ERR_CUDA;
+    // d_field doubles as the thinning rounds' pixel map ((tag << 32) | index words): tag 0 is never valid
+    if (st == AOSLO_OK && cudaMemset(c->d_field, 0, sizeof(double) * (size_t)H * W) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st != AOSLO_OK) { aoslo_ctx_destroy(c); return st; }
     *out = c;
     return AOSLO_OK;
@@ -273,7 +277,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
     if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
     cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket);
-    cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_ctl); cudaFree(c->d_params);
+    cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_map_epoch); cudaFree(c->d_ctl); cudaFree(c->d_params);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
     cudaGetLastError();
@@ -667,7 +671,7 @@ int enqueue_thin_round(RunPlan& P, cudaStream_t q, cudaGraphConditionalHandle h,
     const aoslo_config* cfg = P.cfg;
     AOSLO_TRY(stage_delete(c, q, c->d_pos[0], c->d_stable[0], P.inner, P.d_Rb, P.fdt, cfg->H, cfg->W,
                            cfg->thinning_threshold, AOSLO_TIE_CANONICAL, c->d_pos[1], c->d_stable[1], nullptr, P.cnt1,
-                           nullptr, P.cnt0, 0, &c->d_params->thin_thr, 0));
+                           nullptr, P.cnt0, 3, &c->d_params->thin_thr, 0));
     thin_swap_kernel<<<c->nb, kThreads, 0, q>>>((const double2*)c->d_pos[1], c->d_stable[1], P.cnt1,
                                                 (double2*)c->d_pos[0], c->d_stable[0], P.cnt0, c->d_ctl, h, use_handle);
     AOSLO_LAUNCH_CHECK();

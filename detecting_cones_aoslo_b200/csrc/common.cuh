@@ -197,6 +197,7 @@ struct aoslo_ctx {
     int* d_link_geom = nullptr;          // [8] shift, gw, gh, ncell, tag of lk_p
     unsigned int* d_link_epoch = nullptr;   // build counter = tag of the last build
     unsigned int* d_link_epoch_n = nullptr; // same for the non-stable structure N of the run loop
+    unsigned int* d_map_epoch = nullptr;    // tag counter of the thinning rounds' pixel map (lives in d_field)
     unsigned long long* d_head_n = nullptr; // [ncell of the finest grid] heads of N
     int* d_link_epoch_ticket = nullptr;
     uint8_t* d_stable_tmp = nullptr;     // [cap] flags of the moved particles (input of the in-loop compaction)

@@ -647,6 +647,8 @@ struct DeleteParams {
     int* status;
 };
 
+constexpr int kCoopThreads = 1024;     // block size of the cooperative (grid-synchronising) deletion kernel
+
 template <typename T>
 __device__ __forceinline__ double energy_at(const T* Rb, double2 p, int W, int H, int* status) {
     int ix = (int)p.x, iy = (int)p.y;
@@ -658,7 +660,7 @@ __device__ __forceinline__ double energy_at(const T* Rb, double2 p, int W, int H
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p, const T* Rb) {
+__global__ void __launch_bounds__(kCoopThreads) delete_resolve_kernel(DeleteParams p, const T* Rb) {
     cg::grid_group grid = cg::this_grid();
     const int n = p.d_n ? *p.d_n : p.n_host;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -713,6 +715,81 @@ __global__ void __launch_bounds__(kThreads) delete_resolve_kernel(DeleteParams p
         if (p.counters[round % 3] == 0) break;
     }
     if (tid == 0 && p.rounds_out) *p.rounds_out = round;
+}
+
+// ---- thinning rounds (aoslo_run): nearest neighbour through a PIXEL MAP ---------------------------------------
+// During the thinning (:115-120) the particles are the seeds: distinct integer pixels in raster order, and the
+// order-preserving compaction keeps them in raster order.  So (1) a pixel -> index map answers "who is at (x, y)" with
+// one load, (2) a row is only active when its neighbour is closer than the threshold (3 px), i.e. within a fixed
+// stencil, and (3) the canonical (d^2, index) order among equidistant neighbours is the raster order of their pixels.
+// Walking the stencil offsets sorted by (d^2, dy, dx) and stopping at the first occupied pixel therefore yields exactly
+// the row (self, nearest, d^2) the cell-list search yields, with coalesced loads instead of chained ones; a row without
+// a neighbour inside the stencil is inactive and gets to = -1.  Map words are (tag << 32) | index (no clearing).
+constexpr int kThinMaxD2 = 16;                 // stencil for thresholds <= 4 px
+struct ThinStencil { int n; signed char dx[64], dy[64], d2[64]; };
+
+static ThinStencil make_thin_stencil() {
+    ThinStencil t{};
+    t.n = 0;
+    for (int d2 = 1; d2 < kThinMaxD2; ++d2)
+        for (int dy = -3; dy <= 3; ++dy)
+            for (int dx = -3; dx <= 3; ++dx)
+                if (dx * dx + dy * dy == d2) {
+                    t.dx[t.n] = (signed char)dx; t.dy[t.n] = (signed char)dy; t.d2[t.n] = (signed char)d2;
+                    ++t.n;
+                }
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) thin_map_scatter_kernel(const double2* __restrict__ pos, int n_host,
+                                                                    const int* d_n, int W, int H,
+                                                                    unsigned long long* map, unsigned int* epoch,
+                                                                    int* ticket, int* geom, int* status) {
+    const int n = d_n ? *d_n : n_host;
+    const unsigned int tag = *epoch + 1u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double2 p = pos[i];
+        const int x = (int)p.x, y = (int)p.y;
+        if (!(p.x >= 0.0 && p.y >= 0.0 && x < W && y < H)) { atomicOr(status, AOSLO_DEV_ESCAPED); continue; }
+        map[(size_t)y * W + x] = ((unsigned long long)tag << 32) | (unsigned long long)(unsigned int)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+            geom[6] = (int)tag;
+            *epoch = tag;
+            *ticket = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) thin_map_rows_kernel(const double2* __restrict__ pos, int n_host,
+                                                                 const int* d_n, int W, int H,
+                                                                 const unsigned long long* __restrict__ map,
+                                                                 const int* __restrict__ geom, ThinStencil st,
+                                                                 double thr, const double* d_thr, int32_t* knn_idx,
+                                                                 double* knn_d2) {
+    const int n = d_n ? *d_n : n_host;
+    if (d_thr) thr = *d_thr;
+    const unsigned int tag = (unsigned int)geom[6];
+    const double thr2 = thr * thr;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double2 p = pos[i];
+        const int x = (int)p.x, y = (int)p.y;
+        int to = -1, d2 = 0;
+        for (int o = 0; o < st.n; ++o) {
+            if ((double)st.d2[o] >= thr2) break;                 // dist < thr  <=>  d^2 < thr^2 (exact: small integers)
+            const int xx = x + st.dx[o], yy = y + st.dy[o];
+            if (xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
+            const unsigned long long w = map[(size_t)yy * W + xx];
+            if ((unsigned int)(w >> 32) == tag) { to = (int)(unsigned int)w; d2 = st.d2[o]; break; }
+        }
+        knn_idx[2 * (size_t)i] = i;
+        knn_idx[2 * (size_t)i + 1] = to;
+        knn_d2[2 * (size_t)i] = 0.0;
+        knn_d2[2 * (size_t)i + 1] = (to >= 0) ? (double)d2 : INFINITY;
+    }
 }
 
 // kNN(k=2) rows of the deletion step on the linked cells + compact list of the active rows
@@ -1473,7 +1550,10 @@ __device__ __forceinline__ void knn_dual_query(const DualView& dv, double qx, do
     }
 }
 
-// warp-per-query variant (lanes split the cells of a ring; see knn_links_query_warp)
+// warp-per-query variant (lanes split the cells; see knn_links_query_warp).  Rings 0-2 -- the 5 x 5 block, one cell
+// per lane -- are visited TOGETHER: with the 4 px cells of the steady state the 4th neighbour (~1 cone pitch away)
+// lies beyond the 3 x 3 block's guaranteed radius, so ring 2 was needed for nearly every query and cost a second
+// round of dependent loads + a second merge; the extra cells are free (idle lanes).  Further rings one at a time.
 template <int K>
 __device__ __forceinline__ void knn_dual_query_warp(const DualView& dv, double qx, double qy, TopK<K>& out) {
     const int lane = threadIdx.x & 31;
@@ -1488,10 +1568,10 @@ __device__ __forceinline__ void knn_dual_query_warp(const DualView& dv, double q
     cx = min(cx, gw - 1);
     cy = min(cy, gh - 1);
     const int rmax = max(gw, gh);
-    for (int r = 1; r <= rmax; ++r) {
-        if (r == 1) {
-            if (lane < 9) {
-                const int x = cx + (lane % 3) - 1, y = cy + (lane / 3) - 1;
+    for (int r = 2; r <= rmax; ++r) {
+        if (r == 2) {
+            if (lane < 25) {
+                const int x = cx + (lane % 5) - 2, y = cy + (lane / 5) - 2;
                 if (x >= 0 && x < gw && y >= 0 && y < gh) knn_dual_cell<K>(dv, y * gw + x, tagS, tagN, qx, qy, mine);
             }
         } else {
@@ -1992,7 +2072,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
     int* n_ns = ctx->d_counters + 13;
     int* n_active_b = ctx->d_counters + 14;
     int* fallback = ctx->d_counters + 15;
-    const bool small = mode != 0;
+    const bool small = mode == 1 || mode == 2;
     const bool use_ns = (mode == 2) && tie_mode == AOSLO_TIE_CANONICAL;
     if (small) {
         if (use_ns) {
@@ -2034,7 +2114,20 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         AOSLO_LAUNCH_CHECK();
         return AOSLO_OK;
     } else {
-        AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
+        if (mode == 3 && thr <= 4.0) {
+            // thinning round of aoslo_run: seeds are distinct integer pixels in raster order (see thin_map_rows_kernel)
+            static const ThinStencil stencil = make_thin_stencil();
+            unsigned long long* map = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the resample
+            thin_map_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n, d_n, W, H, map,
+                                                                 ctx->d_map_epoch, ctx->d_link_epoch_ticket,
+                                                                 ctx->d_link_geom, ctx->d_status);
+            AOSLO_LAUNCH_CHECK();
+            thin_map_rows_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n, d_n, W, H, map, ctx->d_link_geom,
+                                                              stencil, thr, d_thr, ctx->d_knn_idx, ctx->d_knn_d2);
+            AOSLO_LAUNCH_CHECK();
+        } else {
+            AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
+        }
         DeleteParams p;
         p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
         p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.d_thr = d_thr; p.W = W; p.H = H;
@@ -2042,9 +2135,9 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         p.counters = ctx->d_counters + 8; p.rounds_out = d_rounds_out; p.status = ctx->d_status;
         void* args[] = {&p, (void*)&d_Rb};
         int blocks = ctx->coop_blocks;
-        int need = (n + kThreads - 1) / kThreads;   // n is an upper bound when the count lives on the device
+        int need = (n + kCoopThreads - 1) / kCoopThreads;   // n is an upper bound when the count lives on the device
         if (need < blocks) blocks = need < 1 ? 1 : need;
-        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kThreads), args, 0, s));
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)delete_resolve_kernel<T>, dim3(blocks), dim3(kCoopThreads), args, 0, s));
         count_launch();
     }
     if (d_deleted_out) AOSLO_CUDA(cudaMemcpyAsync(d_deleted_out, ctx->d_del, n, cudaMemcpyDeviceToDevice, s));
@@ -2265,7 +2358,8 @@ int stage_dual_step(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n,
     AOSLO_LAUNCH_CHECK();
     }
     if (!(phases & 2)) return AOSLO_OK;
-    ns_relink_kernel<<<ctx->nb, kThreads, 0, s>>>(ctx->d_ns_list, n_ns, (const double2*)ctx->d_pos_tmp,
+    // the non-stable list is short (thousands): a quarter of the grid keeps the ticket chain short
+    ns_relink_kernel<<<ctx->num_sms, kThreads, 0, s>>>(ctx->d_ns_list, n_ns, (const double2*)ctx->d_pos_tmp,
                                                   (double2*)ctx->d_pos[0], ctx->d_del, W, H, ctx->d_link_geom,
                                                   ctx->d_link_epoch_n, ctx->d_link_epoch_ticket, ctx->d_head_n,
                                                   ctx->lk_p.next, ctx->d_status);
@@ -2427,11 +2521,11 @@ int stage_classify(aoslo_ctx* ctx, cudaStream_t s, const double* d_g2p, int n_gt
 
 int coop_blocks_for_delete(int num_sms) {
     int per_sm_f = 0, per_sm_d = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, delete_resolve_kernel<float>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, delete_resolve_kernel<double>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, delete_resolve_kernel<float>, kCoopThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, delete_resolve_kernel<double>, kCoopThreads, 0);
     int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 1) per_sm = 1;        // one 1024-thread block per SM: the grid barrier costs per block
     return per_sm * num_sms;
 }
 
