@@ -143,12 +143,14 @@ class ClockSampler:
 
 def k1_dram_traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum per K1 launch from the committed ncu --set full capture
-    (profiles/r01_k1_traffic.json, written by scripts/summarise_profiles.py); None if absent."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_k1_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"][key])
-    except Exception:
-        return None
+    (profiles/r02_k1_traffic.json, else r01; written by scripts/summarise_profiles.py); None if absent."""
+    for name in ("r02_k1_traffic.json", "r01_k1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["dram_bytes_per_launch"][key])
+        except Exception:
+            continue
+    return None
 
 
 def measured_hbm_peak():
@@ -531,7 +533,7 @@ def run_gpu(args):
         a.record()
         for _ in range(REP):
             for j in range(NB):
-                eng.blobness(s_img[j], 'custom', 'np_grad', (1.0,), torch.float64, out=(d_rb[j], d_g[j]))
+                eng.blobness(s_img[j], 'custom', 'np_grad', tuple(WL['scales']), torch.float64, out=(d_rb[j], d_g[j]))
         b.record()
         torch.cuda.synchronize()
         if i >= 2:

@@ -133,6 +133,7 @@ struct K1Tuning {
     int pair_th = 0;         // tile height of the f32 pair kernel (0 = chosen per image)
     int pair_occ = 0;        // CTAs per SM of the f32 pair kernel (0 = by tile height)
     int dtile_th = 0;        // tile height of the f64 tile kernel (0 = 32)
+    int dtile_occ = 0;       // CTAs per SM of the f64 tile kernel (0 = by tile height)
     int k1_kernel = 0;       // 0 auto, 1 generic tile kernel, 2 band kernel, 3 f64 tile kernel
 };
 
