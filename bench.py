@@ -305,6 +305,7 @@ class Lane:
         from detecting_cones_aoslo_b200 import _lib
         torch = self.torch
         with torch.cuda.stream(self.stream):
+            self.eng.clear_status()                      # stream ordered; read back with the run's summary
             if time_k1:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()

@@ -71,6 +71,7 @@ SYMBOLS = {
     "aoslo_ctx_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "aoslo_ctx_destroy": (_i, [_vp]),
     "aoslo_ctx_status": (_i, [_vp, _vp, _ip, _i]),
+    "aoslo_ctx_clear_status": (_i, [_vp, _vp]),
     "aoslo_ctx_capacity": (_i, [_vp]),
     "aoslo_ctx_set_blocking_sync": (_i, [_vp, _i]),
     "aoslo_ctx_set_tuning": (_i, [_vp, C.c_char_p, _i]),

@@ -314,6 +314,12 @@ extern "C" int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out,
     return AOSLO_OK;
 }
 
+extern "C" int aoslo_ctx_clear_status(aoslo_ctx* ctx, void* stream) {
+    if (!ctx) return AOSLO_ERR_INVALID;
+    AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), (cudaStream_t)stream));
+    return AOSLO_OK;
+}
+
 extern "C" int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0,
                                     int pitch0_bytes, int x_min, int x_max, int y_min, int y_max, int bx, int by,
                                     uint8_t* d_img_out, int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw,
@@ -509,7 +515,7 @@ __global__ void run_begin_kernel(RunCtl* ctl, int* status, int* counters) {
     if (threadIdx.x != 0) return;
     RunCtl z = {};
     *ctl = z;
-    *status = 0;
+    (void)status;             // sticky: conditions raised before the run (the field's eigenvalue assert) are kept
     counters[12] = 0; counters[13] = 0; counters[14] = 0; counters[15] = 0;
     counters[4] = 0; counters[5] = 0;
 }
@@ -1033,7 +1039,6 @@ int run_sklearn(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const v
                 int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
                 aoslo_run_summary* h_summary, float* h_stage_ms) {
     const int H = cfg->H, W = cfg->W, cap = ctx->cap;
-    AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), s));
     float acc_ms[5] = {0, 0, 0, 0, 0};
     // stage timing: CUDA events on the launch stream, resolved once at the end (no extra syncs)
     std::vector<cudaEvent_t>& pool = ctx->ev_pool;

@@ -175,6 +175,10 @@ class Engine:
         check(lib.aoslo_ctx_status(self._h, self._stream(), C.byref(w), 1 if clear else 0), "aoslo_ctx_status")
         return w.value
 
+    def clear_status(self):
+        """Zero the status word, stream ordered (no host synchronisation)."""
+        check(lib.aoslo_ctx_clear_status(self._h, self._stream()), "aoslo_ctx_clear_status")
+
     def raise_on_status(self):
         w = self.status(clear=True)
         if w:
@@ -377,8 +381,9 @@ class Engine:
         return self._fields[key]
 
     def run(self, cfg_struct, Rb, grad, gt, max_records=None, collect_times=True):
-        """aoslo_run.  collect_times=False skips the five stage timings, which lets the library run the
-        epoch loop from a cached CUDA graph (canonical tie order, early stop off)."""
+        """aoslo_run.  The status word is sticky: call clear_status() before the field computation of a new run
+        (find_blobs does); summ.status then carries the field's eigenvalue assert as well as the run's conditions.
+        collect_times=False skips the five stage timings (one-thread time-stamp kernels in the run graph)."""
         if max_records is None:
             max_records = cfg_struct.epoch_num // max(1, cfg_struct.metric_measure_freq) + 2
         recs = (_lib.MetricsRecord * max_records)()

@@ -151,7 +151,7 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     eng = engine if engine is not None else get_engine(H, W, n_gt=GT_data.shape[0])
     if eng.H != H or eng.W != W or eng.gt_cap < GT_data.shape[0]:
         raise ValueError('engine was created for a different padded shape / GT capacity')
-    eng.status(clear=True)
+    eng.clear_status()                                  # stream ordered; the word is read once, after the run
     # reference :26-33: GT -= 1 on the CALLER's array (host side effect), then round / crop / mirror
     # padding -- on the device (aoslo_prepare_inputs)
     GT_data = GT_enumerate_from_zero(GT_data)
@@ -160,7 +160,9 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
     Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype,
                             out=eng.field_buffers(field_dtype))
-    eng.raise_on_status()                               # assert (eigs[0] > eigs[1]).all()  (:43)
+    if mode != 'fused':
+        eng.raise_on_status()                           # assert (eigs[0] > eigs[1]).all()  (:43)
+    # fused: the assert flag stays in the status word and is raised from the run's summary (one sync per call)
 
     if mode == 'fused':
         time_spended = _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn)
@@ -187,7 +189,7 @@ def run_on_field(eng, cur_config, Rb, grad, d_gt, USE_WANDB=False, experiment_id
     t0 = time.time()
     if cur_config['blobness_formula'] not in ('simple_div', 'custom', 'div_corrected'):
         raise NotImplementedError
-    eng.status(clear=True)
+    eng.clear_status()
     if cur_config['metric_algo'] == 'hangarian' or _get(cur_config, 'engine_mode', 'fused') == 'staged':
         _run_staged(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn, None)
     else:

@@ -129,6 +129,8 @@ int aoslo_set_wait_policy(int device, int policy);
 int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int particle_capacity, int gt_capacity);
 int aoslo_ctx_destroy(aoslo_ctx* ctx);
 int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear);
+/* zeroes the status word, stream ordered (no host synchronisation) */
+int aoslo_ctx_clear_status(aoslo_ctx* ctx, void* stream);
 int aoslo_ctx_capacity(aoslo_ctx* ctx);
 /* implementation knobs (defaults come from the environment once, at aoslo_ctx_create): "k1_tma" 0|1|2,
  * "pair_th", "pair_occ", "dtile_th" (0 = automatic), "k1_kernel" 0 auto | 1 generic tile | 2 band | 3 f64 tile,
@@ -238,7 +240,9 @@ int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const v
  * fixpoint, the early stop and the resample / metrics branches); the host synchronises once, at the end.
  * All value parameters of `cfg` are uploaded per call, so runs that differ only in values (a sweep) share the
  * graph; d_Rb, d_grad, d_gt must be stable addresses for the graph to be reused.
- * AOSLO_TIE_SKLEARN: stage calls with one host round trip per kNN (host-built tree). */
+ * AOSLO_TIE_SKLEARN: stage calls with one host round trip per kNN (host-built tree).
+ * summary.status = the context's status word at the end of the run; it is NOT cleared at the start, so a condition
+ * raised by aoslo_blobness on the same stream (AOSLO_DEV_EIG_ASSERT) is reported with the run's own. */
 int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
               int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
               double* d_particles_out, uint8_t* d_stable_out, aoslo_run_summary* h_summary, float* h_stage_ms);

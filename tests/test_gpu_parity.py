@@ -207,6 +207,20 @@ def test_errors_match_reference():
         gpu_utils.calc_grad_field(np.zeros((8, 8)), 'nope')
 
 
+def test_find_blobs_raises_the_eigenvalue_assert_of_the_reference():
+    """A flat frame violates `assert (eigs[0] > eigs[1]).all()` (pipeline_with_delitions.py:43): the flag raised by the
+    blobness kernel stays in the status word and comes back with the run's summary (no extra synchronisation)."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    flat = np.full_like(img, 90)
+    for tie_mode in ("canonical", "sklearn"):
+        with pytest.raises(AssertionError):
+            find_blobs(configs.variant(configs.main_config(), tie_mode=tie_mode), gt.copy(), flat, None, False, False)
+    # the next call on the same cached engine starts from a clean status word
+    res, _ = find_blobs(configs.main_config(), gt.copy(), img, None, False, False)
+    assert res["_summary"]["status"] == 0
+
+
 def test_device_input_preparation_matches_host():
     """aoslo_prepare_inputs (np.round + crop_image + mirror_padding_image on the device) == host path."""
     from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs
