@@ -1065,7 +1065,16 @@ int run_sklearn(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const v
     AOSLO_TRY(read_int(ctx, s, d_cnt[cur], &n));
     if (n > cap) return AOSLO_ERR_CAPACITY;
     h_summary->n_seeds = n;
-    if (n < 2) { h_summary->status = AOSLO_DEV_KNN_SHORT; return AOSLO_OK; }
+    // too few points for a neighbour search (sklearn raises): report it together with whatever the status word
+    // already holds (the field's eigenvalue assert)
+    auto short_exit = [&]() -> int {
+        int word = 0;
+        AOSLO_TRY(read_int(ctx, s, ctx->d_status, &word));
+        h_summary->status = word | AOSLO_DEV_KNN_SHORT;
+        ctx->last_n = 0;
+        return AOSLO_OK;
+    };
+    if (n < 2) return short_exit();
     AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 0, nullptr));
     // ---- thinning to a fixpoint (:115-120)
     int rounds = 0;
@@ -1083,7 +1092,7 @@ int run_sklearn(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const v
     }
     h_summary->n_after_thinning = n;
     h_summary->n_thinning_rounds = rounds;
-    if (n < 2) { h_summary->status = AOSLO_DEV_KNN_SHORT; return AOSLO_OK; }
+    if (n < 2) return short_exit();
     // ---- all stable, gravity field, adding (:130-152)
     AOSLO_TRY(stage_lut(ctx, s, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, ctx->d_lut));
