@@ -178,7 +178,6 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         A(alloc_links(c->lk_p, H, W, cap, lshift));
     }
     A(dmalloc(&c->d_pos_tmp, (size_t)cap * 2));
-    A(dmalloc(&c->d_stable_tmp, cap));
     A(dmalloc(&c->d_link_geom, 8));
     A(dmalloc(&c->d_link_epoch, 1));
     A(dmalloc(&c->d_link_epoch_ticket, 1));
@@ -207,11 +206,12 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
         c->tune.k1_kernel = !strcmp(e, "tile") ? 1 : !strcmp(e, "band") ? 2 : !strcmp(e, "dtile") ? 3 : 0;
     A(dmalloc(&c->d_epoch, 1));
     A(dmalloc(&c->d_active, cap));
-    A(dmalloc(&c->d_active_b, cap));
     A(dmalloc(&c->d_ns_list, cap));
     A(dmalloc(&c->d_knn_idx, kn));
     A(dmalloc(&c->d_knn_d2, kn));
     A(dmalloc(&c->d_block_sums, kMaxScanBlocks + 1));
+    A(dmalloc(&c->d_scan_ticket, 1));
+    if (st == AOSLO_OK && cudaMemset(c->d_scan_ticket, 0, sizeof(int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_touch, cap));
     A(dmalloc(&c->d_del, cap));
     A(dmalloc(&c->d_rowstate, cap));
@@ -259,8 +259,8 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_status); cudaFree(c->d_counters); cudaFreeHost(c->h_pinned);
     free_cell_list(c->cl_p); free_cell_list(c->cl_g);
-    cudaFree(c->lk_p.head); cudaFree(c->lk_p.next); cudaFree(c->d_pos_tmp); cudaFree(c->d_active); cudaFree(c->d_active_b); cudaFree(c->d_ns_list);
-    cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_block_sums);
+    cudaFree(c->lk_p.head); cudaFree(c->lk_p.next); cudaFree(c->d_pos_tmp); cudaFree(c->d_active); cudaFree(c->d_ns_list);
+    cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_block_sums); cudaFree(c->d_scan_ticket);
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
@@ -276,7 +276,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
     if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
-    cudaFree(c->d_stable_tmp); cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket);
+    cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket);
     cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_map_epoch); cudaFree(c->d_ctl); cudaFree(c->d_params);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
@@ -435,8 +435,7 @@ extern "C" int aoslo_classify(aoslo_ctx* ctx, void* stream, const double* d_dist
 }
 
 // One loop iteration without the resample / metrics tail: distance force, move, deletion
-// (reference pipeline_with_delitions.py:173-253).  Same code path as inside aoslo_run, incl. the
-// non-stable-list fast path and its all-rows fallback in the canonical tie order.
+// (reference pipeline_with_delitions.py:173-253), on the kernels aoslo_run executes per epoch.
 extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb,
                              const void* d_grad, int field_dtype, const double* d_particles,
                              const uint8_t* d_stable, int n, double* d_particles_out, uint8_t* d_stable_out,
@@ -452,29 +451,39 @@ extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* c
     const double e0 = pit ? cfg->mu_dist_func : cfg->dist_alpha;
     const double e1 = pit ? cfg->sigma_dist_func : cfg->dist_sigma;
     const double e2 = pit ? cfg->lambda_dist_func : 0.0;
-    const double* moved;
-    int mode;
     AOSLO_TRY(epoch_guard(ctx, s, 2u));              // the 20-bit touch epoch must not wrap (one resolve per call)
     // a call that failed between the force step and the deletion must not leak its non-stable list
     AOSLO_CUDA(cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(int) * 4, s));
     if (cfg->tie_mode == AOSLO_TIE_CANONICAL) {
-        AOSLO_TRY(stage_force_move(ctx, s, d_particles, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2, d_grad,
-                                   field_dtype, cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode,
-                                   ctx->d_pos_tmp, nullptr, false));
-        moved = ctx->d_pos_tmp;
-        mode = 2;
-    } else {
-        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos_tmp, d_particles, sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
-        AOSLO_TRY(stage_force(ctx, s, ctx->d_pos_tmp, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2,
-                              cfg->tie_mode, ctx->d_force, nullptr));
-        AOSLO_TRY(stage_move(ctx, s, ctx->d_pos_tmp, d_stable, n, d_grad, field_dtype, cfg->H, cfg->W, ctx->d_force,
-                             cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, nullptr));
-        moved = ctx->d_pos_tmp;
-        mode = 1;
+        // the code path of aoslo_run: particles into buffer 0, one resample period (S / N structures, non-stable
+        // list), one step on the tombstone structure, order-preserving compaction of the survivors
+        int* cnt0 = ctx->d_counters + 4;
+        int* cnt1 = ctx->d_counters + 5;
+        ctx->h_pinned[8] = n;
+        AOSLO_CUDA(cudaMemcpyAsync(cnt0, ctx->h_pinned + 8, sizeof(int), cudaMemcpyHostToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos[0], d_particles, sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(ctx->d_stable[0], d_stable, n, cudaMemcpyDeviceToDevice, s));
+        AOSLO_TRY(stage_period_begin(ctx, s, n, cnt0));
+        AOSLO_TRY(stage_dual_step(ctx, s, n, cnt0, k, cfg->dist_energy_type, e0, e1, e2, d_grad, d_Rb, field_dtype,
+                                  cfg->H, cfg->W, cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode,
+                                  cfg->threshhold_dist_del, nullptr, 3));
+        ++ctx->epoch;
+        AOSLO_TRY(stage_compact(ctx, s, n, cnt0, cnt1, 0));
+        AOSLO_TRY(read_int(ctx, s, cnt0, h_n_out));
+        const int m = *h_n_out;
+        AOSLO_CUDA(cudaMemcpyAsync(d_particles_out, ctx->d_pos[0], sizeof(double) * 2 * m, cudaMemcpyDeviceToDevice, s));
+        AOSLO_CUDA(cudaMemcpyAsync(d_stable_out, ctx->d_stable[0], m, cudaMemcpyDeviceToDevice, s));
+        return AOSLO_OK;
     }
-    AOSLO_TRY(stage_delete(ctx, s, moved, d_stable, n, d_Rb, field_dtype, cfg->H, cfg->W, cfg->threshhold_dist_del,
-                           cfg->tie_mode, d_particles_out, d_stable_out, nullptr, ctx->d_counters, nullptr, nullptr,
-                           mode));
+    // sklearn tie order: the stage kernels of run_sklearn (host-built tree per neighbour search)
+    AOSLO_CUDA(cudaMemcpyAsync(ctx->d_pos_tmp, d_particles, sizeof(double) * 2 * n, cudaMemcpyDeviceToDevice, s));
+    AOSLO_TRY(stage_force(ctx, s, ctx->d_pos_tmp, d_stable, n, k, cfg->dist_energy_type, e0, e1, e2, cfg->tie_mode,
+                          ctx->d_force, nullptr));
+    AOSLO_TRY(stage_move(ctx, s, ctx->d_pos_tmp, d_stable, n, d_grad, field_dtype, cfg->H, cfg->W, ctx->d_force,
+                         cfg->lambda_blob, cfg->lambda_dist, cfg->step_mode, nullptr));
+    AOSLO_TRY(stage_delete(ctx, s, ctx->d_pos_tmp, d_stable, n, d_Rb, field_dtype, cfg->H, cfg->W,
+                           cfg->threshhold_dist_del, cfg->tie_mode, d_particles_out, d_stable_out, nullptr,
+                           ctx->d_counters, nullptr, nullptr, 1));
     return read_int(ctx, s, ctx->d_counters, h_n_out);
 }
 

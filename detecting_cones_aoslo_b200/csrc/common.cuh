@@ -179,7 +179,6 @@ struct aoslo_ctx {
     aoslo::CellLinks lk_p;            // particles (kNN)
     double* d_pos_tmp = nullptr;      // [cap*2] moved positions (Jacobi move writes here)
     int* d_active = nullptr;          // [cap] compact list of active deletion rows (non-stable path)
-    int* d_active_b = nullptr;        // [cap] same, all-rows fallback
     int* d_ns_list = nullptr;         // [cap] compact list of non-stable particles
     int blocking_sync = 0;            // 1: host waits sleep on a blocking event instead of spinning
     cudaEvent_t ev_block = nullptr;
@@ -201,7 +200,6 @@ struct aoslo_ctx {
     unsigned int* d_map_epoch = nullptr;    // tag counter of the thinning rounds' pixel map (lives in d_field)
     unsigned long long* d_head_n = nullptr; // [ncell of the finest grid] heads of N
     int* d_link_epoch_ticket = nullptr;
-    uint8_t* d_stable_tmp = nullptr;     // [cap] flags of the moved particles (input of the in-loop compaction)
     int loop_hint = 0;                   // launch-size hint of the in-loop compaction (performance only)
     aoslo::K1Tuning tune;
     int last_n = 0, last_buf = 0;        // where the final particles of the last run live (aoslo_read_particles)
@@ -210,6 +208,7 @@ struct aoslo_ctx {
     int32_t* d_knn_idx = nullptr;     // [max(cap,gt_cap) * KMAX]
     double* d_knn_d2 = nullptr;
     int* d_block_sums = nullptr;      // [kMaxScanBlocks + 1]
+    int* d_scan_ticket = nullptr;     // last-block ticket of scan_count_kernel
     unsigned long long* d_touch = nullptr;  // [cap]
     uint8_t* d_del = nullptr;         // [cap]
     uint8_t* d_rowstate = nullptr;    // [cap]
@@ -238,7 +237,7 @@ struct aoslo_ctx {
 namespace aoslo {
 
 // ---------------------------------------------------------------------------------------
-// Ordered compaction / exclusive scan in three phases (count, spine, emit).  `Op` provides
+// Ordered compaction / exclusive scan in two launches (count + spine by the last block, emit).  `Op` provides
 //   __device__ int  value(int i) const      -- the integer to be scanned (0/1 for a compaction)
 //   __device__ void emit(int i, int v, int exclusive_prefix) const
 // The element count may live on the device (d_m != nullptr) so that callers never
@@ -282,26 +281,49 @@ __device__ __forceinline__ void scan_span(int m, int& lo, int& hi) {
     hi = (int)(h < m ? h : m);
 }
 
+// Phase 1 + 2: every block sums its span; the LAST block to finish (ticket) turns the block sums into exclusive
+// offsets (+ base) and stores the total -- the former one-block spine kernel, without its launch.
+// `clamp` > 0: the stored total never exceeds it (an over-full append raises AOSLO_DEV_CAPACITY in `status` and later
+// kernels iterate over at most `clamp` rows -- the buffers' capacity).
 template <class Op>
-__global__ void __launch_bounds__(kScanThreads) scan_count_kernel(Op op, int m_host, const int* d_m,
-                                                                 int* block_sums) {
+__global__ void __launch_bounds__(kScanThreads) scan_count_kernel(Op op, int m_host, const int* d_m, int* block_sums,
+                                                                 int* ticket, int* d_total, const int* d_base,
+                                                                 int base_host, int* d_total_added, int clamp,
+                                                                 int* status) {
     __shared__ int sw[33];
+    __shared__ int s_last;
     int m = d_m ? *d_m : m_host;
+    const int base = d_base ? *d_base : base_host;       // read before the last block may overwrite it (d_total)
     int lo, hi;
     scan_span(m, lo, hi);
     int acc = 0;
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += op.value(i);
     int total;
     block_excl_scan(acc, sw, total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) {
+        __stcg(&block_sums[blockIdx.x], total);
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nblocks = (int)gridDim.x;                  // <= kMaxScanBlocks = blockDim.x
+    int v = (threadIdx.x < nblocks) ? __ldcg(&block_sums[threadIdx.x]) : 0;
+    int grand;
+    int excl = block_excl_scan(v, sw, grand);
+    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = base + excl;
+    if (threadIdx.x == 0) {
+        int t = base + grand;
+        if (clamp > 0 && t > clamp) {                    // the emit phase skips the rows beyond the capacity
+            t = clamp;
+            if (status) atomicOr(status, AOSLO_DEV_CAPACITY);
+        }
+        if (d_total) *d_total = t;
+        if (d_total_added) *d_total_added = grand;
+        *ticket = 0;
+    }
 }
-
-// one block: exclusive scan of the block sums; writes total (+ base) to d_total
-// `clamp` > 0: the stored total never exceeds it (an over-full append raises AOSLO_DEV_CAPACITY in `status`
-// and later kernels iterate over at most `clamp` rows -- the buffers' capacity)
-__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
-                                                                  const int* d_base, int base_host,
-                                                                  int* d_total_added, int clamp, int* status);
 
 template <class Op>
 __global__ void __launch_bounds__(kScanThreads) scan_emit_kernel(Op op, int m_host, const int* d_m,
@@ -323,7 +345,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_emit_kernel(Op op, int m_ho
 
 int scan_blocks_for(int m_capacity);
 
-// host driver: runs the three phases on `stream`.
+// host driver: two launches on `stream` (count + spine, emit).
 //   d_total      <- base + sum(value)      (may be nullptr)
 //   d_total_added<- sum(value)             (may be nullptr)
 // `base` (offset added to every prefix handed to emit) comes from *d_base if non-null.
@@ -331,10 +353,8 @@ template <class Op>
 int ordered_scan(aoslo_ctx* ctx, cudaStream_t s, Op op, int m_capacity, int m_host, const int* d_m,
                  int* d_total, const int* d_base, int base_host, int* d_total_added, int clamp = 0) {
     int nb = scan_blocks_for(m_capacity);
-    scan_count_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
-    AOSLO_LAUNCH_CHECK();
-    scan_spine_kernel<<<1, kScanThreads, 0, s>>>(ctx->d_block_sums, nb, d_total, d_base, base_host, d_total_added,
-                                                 clamp, ctx->d_status);
+    scan_count_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums, ctx->d_scan_ticket, d_total,
+                                                      d_base, base_host, d_total_added, clamp, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
     scan_emit_kernel<Op><<<nb, kScanThreads, 0, s>>>(op, m_host, d_m, ctx->d_block_sums);
     AOSLO_LAUNCH_CHECK();
@@ -355,8 +375,7 @@ int kd_reserve(aoslo_ctx* ctx);
 int epoch_guard(aoslo_ctx* ctx, cudaStream_t s, unsigned int calls_ahead);
 int stream_wait(aoslo_ctx* ctx, cudaStream_t s);   // host waits for the stream (spin or blocking event)
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                int bias_x4, const uint8_t* prep_stable = nullptr, double* prep_pos_out = nullptr,
-                uint8_t* prep_stable_out = nullptr);
+                int bias_x4);
 int build_cell_list(aoslo_ctx* ctx, cudaStream_t s, CellList& cl, const double* d_pos, int n_host, const int* d_n);
 int knn_sklearn(aoslo_ctx* ctx, cudaStream_t s, const double* d_points, int n_points, const double* d_query,
                 int n_query, int k, int32_t* d_idx, double* d_d2);
@@ -369,10 +388,6 @@ int stage_delete(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d
                  int field_dtype, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
                  uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode,
                  const double* d_thr = nullptr, int scan_hint = 0);
-int stage_force_move(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* d_stable, int n, int k,
-                     int energy_type, double p0, double p1, double p2, const void* d_grad, int field_dtype, int H,
-                     int W, double lb, double ld, int step_mode, double* d_pos_out, const int* d_n, bool links_ready,
-                     uint8_t* d_stable_copy = nullptr, const RunParams* rp = nullptr);
 int stage_seed(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int H, int W, int bx, int by, double thr,
                double* d_pos, int cap, int* d_n_out, const double* d_thr = nullptr, bool clamp_count = false);
 int stage_lut(aoslo_ctx*, cudaStream_t, int rfs, double mu, double sigma, double lam, double* d_lut,

@@ -25,28 +25,8 @@ namespace cg = cooperative_groups;
 namespace aoslo {
 
 // =======================================================================================
-// scan spine
+// ordered scan helpers
 // =======================================================================================
-__global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(int* block_sums, int nblocks, int* d_total,
-                                                                  const int* d_base, int base_host,
-                                                                  int* d_total_added, int clamp, int* status) {
-    __shared__ int sw[33];
-    int base = d_base ? *d_base : base_host;
-    int v = (threadIdx.x < nblocks) ? block_sums[threadIdx.x] : 0;
-    int total;
-    int excl = block_excl_scan(v, sw, total);
-    if (threadIdx.x < nblocks) block_sums[threadIdx.x] = base + excl;
-    if (threadIdx.x == 0) {
-        int t = base + total;
-        if (clamp > 0 && t > clamp) {             // the emit phase skipped the rows beyond the capacity
-            t = clamp;
-            if (status) atomicOr(status, AOSLO_DEV_CAPACITY);
-        }
-        if (d_total) *d_total = t;
-        if (d_total_added) *d_total_added = total;
-    }
-}
-
 int scan_blocks_for(int m_capacity) {
     int nb = (m_capacity + kScanThreads - 1) / kScanThreads;
     if (nb < 1) nb = 1;
@@ -221,28 +201,16 @@ __host__ __device__ inline int link_shift_for(int n, int H, int W, int min_shift
 // Build of the linked cells in ONE kernel, without clearing the heads: a head word is (tag << 32) | index and only
 // words carrying the tag of the current build are valid.  The tag is a device counter: every thread reads it at
 // kernel start, the LAST block to finish (ticket) publishes tag + geometry for the kernels that follow.
-// PREP additionally does ns_prepare_kernel's work in the same pass (copy to the move buffers, clear the
-// deletion flags, collect the non-stable list).
-template <bool PREP>
 __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restrict__ pos, int n_host,
                                                         const int* d_n, int W, int H, int min_shift, int fixed_shift,
                                                         int bias_x4, int* geom, unsigned int* epoch, int* ticket,
-                                                        unsigned long long* head, int* next, int* status,
-                                                        const uint8_t* __restrict__ stable, double2* pos_out,
-                                                        uint8_t* stable_out, uint8_t* del, int* ns_list, int* n_ns) {
+                                                        unsigned long long* head, int* next, int* status) {
     const int n = d_n ? *d_n : n_host;
     const int shift = link_shift_for(n, H, W, min_shift, fixed_shift, bias_x4);
     const int gw = (W + (1 << shift) - 1) >> shift, gh = (H + (1 << shift) - 1) >> shift;
     const unsigned int tag = *epoch + 1u;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double2 p = pos[i];
-        if (PREP) {
-            const uint8_t st = stable[i];
-            pos_out[i] = p;
-            if (stable_out) stable_out[i] = st;
-            del[i] = 0;
-            if (!st) ns_list[atomicAdd(n_ns, 1)] = i;
-        }
         bool bad = false;
         int cx = cell_coord(p.x, shift, gw, bad);
         int cy = cell_coord(p.y, shift, gh, bad);
@@ -265,18 +233,10 @@ __global__ void __launch_bounds__(kThreads) link_kernel(const double2* __restric
 
 // n_host is the count, or (with d_n) only its launch-size upper bound
 int build_links(aoslo_ctx* ctx, cudaStream_t s, CellLinks& lk, const double* d_pos, int n_host, const int* d_n,
-                int bias_x4, const uint8_t* prep_stable, double* prep_pos_out, uint8_t* prep_stable_out) {
-    if (prep_stable)
-        link_kernel<true><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->W, ctx->H, lk.min_shift,
-                                                       lk.fixed_shift, bias_x4, ctx->d_link_geom, ctx->d_link_epoch,
-                                                       ctx->d_link_epoch_ticket, lk.head, lk.next, ctx->d_status,
-                                                       prep_stable, (double2*)prep_pos_out, prep_stable_out, ctx->d_del,
-                                                       ctx->d_ns_list, ctx->d_counters + 13);
-    else
-        link_kernel<false><<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->W, ctx->H, lk.min_shift,
-                                                        lk.fixed_shift, bias_x4, ctx->d_link_geom, ctx->d_link_epoch,
-                                                        ctx->d_link_epoch_ticket, lk.head, lk.next, ctx->d_status, nullptr,
-                                                        nullptr, nullptr, nullptr, nullptr, nullptr);
+                int bias_x4) {
+    link_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, ctx->W, ctx->H, lk.min_shift,
+                                             lk.fixed_shift, bias_x4, ctx->d_link_geom, ctx->d_link_epoch,
+                                             ctx->d_link_epoch_ticket, lk.head, lk.next, ctx->d_status);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
@@ -1205,106 +1165,6 @@ __global__ void __launch_bounds__(kThreads) move_kernel(double2* pos, const uint
     }
 }
 
-// ---- non-stable list path of the run loop (canonical tie order) --------------------------------
-// Only non-stable particles move (:216) and only rows whose `from` is non-stable can delete
-// (utils.py:253); `from` is the row's own particle unless two particles coincide.  So the loop works
-// on the compact list of non-stable particles with one WARP per query; a coincidence (distance 0 to
-// another particle) raises `fallback`, which re-runs the step on all rows (knn2_rows_kernel).
-__global__ void __launch_bounds__(kThreads) ns_prepare_kernel(const double2* __restrict__ pos,
-                                                              const uint8_t* __restrict__ stable, int n_host,
-                                                              const int* d_n, double2* __restrict__ pos_out,
-                                                              uint8_t* __restrict__ stable_out,
-                                                              uint8_t* __restrict__ del, int* ns_list, int* n_ns) {
-    int n = d_n ? *d_n : n_host;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint8_t st = stable[i];
-        pos_out[i] = pos[i];
-        if (stable_out) stable_out[i] = st;
-        del[i] = 0;
-        if (!st) ns_list[atomicAdd(n_ns, 1)] = i;
-    }
-}
-
-template <int K, typename T>
-__global__ void __launch_bounds__(kThreads) ns_force_move_kernel(
-    LinkView lv, const int* __restrict__ ns_list, const int* __restrict__ n_ns, int kk, int energy_type, double p0,
-    double p1, double p2, const T* __restrict__ grad, int H, int W, double lb, double ld, int step_mode,
-    double2* __restrict__ pos_out, int* status, const RunParams* rp) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = *n_ns;
-    if (rp) { kk = rp->kk; p0 = rp->e0; p1 = rp->e1; p2 = rp->e2; lb = rp->lb; ld = rp->ld; }
-    for (int q = warp; q < total; q += nwarps) {
-        const int i = ns_list[q];
-        double2 p = lv.pos[i];
-        TopK<K> top;
-        knn_links_query_warp<K>(lv, p.x, p.y, top);
-        // lane j computes the term of neighbour j (column 0 is dropped); lane 0 sums them in order
-        int nb = 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < K; ++j)
-            if (lane == j) nb = top.idx[j];
-        double tx = 0.0, ty = 0.0;
-        if (lane >= 1 && lane < kk) {
-            double2 qn = (nb != 0x7fffffff) ? lv.pos[nb] : make_double2(NAN, NAN);
-            double vx = p.x - qn.x, vy = p.y - qn.y;
-            double nrm = sqrt(vx * vx + vy * vy);
-            if (energy_type == AOSLO_ENERGY_PIT) {
-                double f = energy_pit2(nrm, p0, p1, p2);
-                tx = (vx / nrm) * f;
-                ty = (vy / nrm) * f;
-            } else {
-                double den = nrm / (p1 * p1);
-                tx = vx / den;
-                ty = vy / den;
-            }
-        }
-        double fx = __shfl_sync(0xffffffffu, tx, 1), fy = __shfl_sync(0xffffffffu, ty, 1);
-        for (int j = 2; j < kk; ++j) {
-            fx += __shfl_sync(0xffffffffu, tx, j);
-            fy += __shfl_sync(0xffffffffu, ty, j);
-        }
-        if (energy_type == AOSLO_ENERGY_EXP) { fx = p0 * fx; fy = p0 * fy; }
-        if (lane == 0) {
-            bool shortfall = false;
-#pragma unroll
-            for (int j = 0; j < K; ++j)
-                if (j == kk - 1 && top.idx[j] == 0x7fffffff) shortfall = true;
-            if (shortfall) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-            if (step_mode >= 0) move_one<T>(p, make_double2(fx, fy), grad, H, W, lb, ld, step_mode, status);
-            pos_out[i] = p;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kThreads) ns_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
-                                                           const int* __restrict__ ns_list,
-                                                           const int* __restrict__ n_ns, double thr,
-                                                           const double* d_thr, int32_t* knn_idx, double* knn_d2,
-                                                           int* active, int* n_active, int* fallback) {
-    const int lane = threadIdx.x & 31;
-    if (d_thr) thr = *d_thr;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = *n_ns;
-    for (int q = warp; q < total; q += nwarps) {
-        const int i = ns_list[q];
-        double2 p = lv.pos[i];
-        TopK<2> top;
-        knn_links_query_warp<2>(lv, p.x, p.y, top);
-        if (lane == 0) {
-            const bool ok = top.idx[1] != 0x7fffffff;
-            const int from = top.idx[0], to = ok ? top.idx[1] : -1;
-            // another particle at distance 0, or nothing found at all: the all-rows path decides
-            if (from != i || !ok || top.d2[1] == 0.0) atomicExch(fallback, 1);
-            knn_idx[2 * (size_t)i] = from;
-            knn_idx[2 * (size_t)i + 1] = to;
-            knn_d2[2 * (size_t)i] = top.d2[0];
-            knn_d2[2 * (size_t)i + 1] = top.d2[1];
-            if (ok && from == i && !stable[from] && sqrt(top.d2[1]) < thr) active[atomicAdd(n_active, 1)] = i;
-        }
-    }
-}
-
 // =======================================================================================
 // metrics
 // =======================================================================================
@@ -2065,29 +1925,15 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                    const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
                    uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode,
                    const double* d_thr, int scan_hint) {
-    // mode 0: cooperative all-rows resolve; 1: compact active list + one block; 2: as 1, rows taken from
-    // the non-stable list left by stage_force_move (canonical run loop)
+    // mode 0: cooperative all-rows resolve (3: with the pixel-map neighbour search of aoslo_run's thinning rounds);
+    // 1: compact active list + one resolving block (the sklearn-order run loop)
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     if (n < 2) return AOSLO_ERR_INVALID;   // sklearn: n_neighbors=2 > n_samples
     if (d_n && d_n == d_n_out) return AOSLO_ERR_INVALID;   // the count is double-buffered
     int* n_active = ctx->d_counters + 12;
-    int* n_ns = ctx->d_counters + 13;
-    int* n_active_b = ctx->d_counters + 14;
-    int* fallback = ctx->d_counters + 15;
-    const bool small = mode == 1 || mode == 2;
-    const bool use_ns = (mode == 2) && tie_mode == AOSLO_TIE_CANONICAL;
+    const bool small = mode == 1;
     if (small) {
-        if (use_ns) {
-            AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
-            LinkView lv = link_view(ctx, ctx->lk_p, d_pos);
-            ns_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, ctx->d_ns_list, n_ns, thr, d_thr, ctx->d_knn_idx,
-                                                        ctx->d_knn_d2, ctx->d_active, n_active, fallback);
-            AOSLO_LAUNCH_CHECK();
-            knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(lv, d_stable, n, d_n, thr, d_thr, ctx->d_knn_idx,
-                                                          ctx->d_knn_d2, ctx->d_del, ctx->d_active_b, n_active_b,
-                                                          ctx->d_status, fallback);
-            AOSLO_LAUNCH_CHECK();
-        } else if (tie_mode == AOSLO_TIE_CANONICAL) {
+        if (tie_mode == AOSLO_TIE_CANONICAL) {
             AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
             knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx, ctx->lk_p, d_pos), d_stable, n, d_n, thr, d_thr,
                                                           ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_del, ctx->d_active,
@@ -2104,9 +1950,8 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         // the number of compaction blocks is a launch-size choice only (any count is correct for any n)
         const int nb_scan = scan_blocks_for(scan_hint > 0 ? scan_hint : n);
         delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
-            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active,
-            use_ns ? ctx->d_active_b : nullptr, use_ns ? n_active_b : nullptr, use_ns ? fallback : nullptr,
-            use_ns ? n_ns : nullptr, n, d_n, ctx->d_epoch, W, H, d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate,
+            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active, nullptr, nullptr, nullptr,
+            nullptr, n, d_n, ctx->d_epoch, W, H, d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate,
             ctx->d_block_sums, nb_scan, d_n_out, ctx->d_status);
         AOSLO_LAUNCH_CHECK();
         ++ctx->epoch;                               // host-side upper estimate of the device epoch
@@ -2156,40 +2001,6 @@ int stage_delete(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint
                                      d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode, d_thr, scan_hint);
     return stage_delete_t<double>(ctx, s, d_pos, d_stable, n, (const double*)d_Rb, H, W, thr, tie_mode, d_pos_out,
                                   d_stable_out, d_deleted_out, d_n_out, d_rounds_out, d_n, mode, d_thr, scan_hint);
-}
-
-// force + move of the run loop (canonical tie order): copy positions + collect the non-stable list,
-// then one warp per non-stable particle (kNN on the linked cells, force, Jacobi move into d_pos_out).
-// Leaves ctx->d_ns_list / counters[13] for stage_delete(mode 2) and zeroes ctx->d_del.
-int stage_force_move(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const uint8_t* d_stable, int n, int k,
-                     int energy_type, double p0, double p1, double p2, const void* d_grad, int field_dtype, int H,
-                     int W, double lb, double ld, int step_mode, double* d_pos_out, const int* d_n,
-                     bool links_ready, uint8_t* d_stable_copy, const RunParams* rp) {
-    if (k < 1 || k + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
-    if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
-    int* n_ns = ctx->d_counters + 13;          // zero here: reset by the resolve kernel / by the callers
-    if (!links_ready) {
-        // one pass: link the particles and do ns_prepare's work (copy, clear flags, non-stable list)
-        AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady, d_stable, d_pos_out, d_stable_copy));
-    } else {
-        ns_prepare_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, d_stable, n, d_n, (double2*)d_pos_out,
-                                                       d_stable_copy, ctx->d_del, ctx->d_ns_list, n_ns);
-        AOSLO_LAUNCH_CHECK();
-    }
-    LinkView lv = link_view(ctx, ctx->lk_p, d_pos);
-    const int kk = k + 1;
-#define AOSLO_FM(KT, TT)                                                                                          \
-    ns_force_move_kernel<KT, TT><<<ctx->nb, kThreads, 0, s>>>(lv, ctx->d_ns_list, n_ns, kk, energy_type, p0, p1, p2, \
-                                                              (const TT*)d_grad, H, W, lb, ld, step_mode,          \
-                                                              (double2*)d_pos_out, ctx->d_status, rp)
-    if (field_dtype == AOSLO_F32) {
-        if (kk <= 2) AOSLO_FM(2, float); else if (kk <= 4) AOSLO_FM(4, float); else AOSLO_FM(8, float);
-    } else {
-        if (kk <= 2) AOSLO_FM(2, double); else if (kk <= 4) AOSLO_FM(4, double); else AOSLO_FM(8, double);
-    }
-#undef AOSLO_FM
-    AOSLO_LAUNCH_CHECK();
-    return AOSLO_OK;
 }
 
 // clamp_count: the stored count never exceeds cap (graph path); otherwise the caller compares it with cap
