@@ -572,6 +572,9 @@ def run_gpu(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(), "batch": B,
+                       "tie_order": "canonical (distance, index) order: the all-GPU mode, pinned by the oracle's canonical "
+                                    "variant (same order in the CPU arm); the as-is reference order (sklearn KD tree) "
+                                    "is the `faithful` key",
                        "step": "one step = %d frames run concurrently (one CUDA stream + context each)" % B,
                        "padded_shape": [H, W], "n_gt": lane0.n_gt,
                        "n_particles_final": int(summ.n_particles), "n_seeds": int(summ.n_seeds),
