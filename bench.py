@@ -346,9 +346,10 @@ def run_gpu(args):
     # and waits for the device.  8 lanes saturate one B200 (1/2/4/8 lanes: 295/450/600/690 runs/s) and were
     # also the best setting on the 8-GPU / 32-core box (4388 runs/s vs 3826 with 4 lanes per GPU).
     # lanes per GPU: 8 saturate most of one B200 (4 / 8 / 12 / 16 / 24 lanes: 680 / 845 / 863 / 878 / 904 runs/s, e2e
-    # 550 / 696 / 743 / 754 / 804); more lanes mainly hide the host side of the end-to-end path, so the default
-    # follows the cores available per rank (8 on the 8-GPU / 32-core box, 16 on a single-GPU box)
-    B = args.batch if args.batch > 0 else max(1, min(cores, max(WL['lanes'], min(2 * WL['lanes'], cores // max(1, world)))))
+    # 550 / 696 / 743 / 754 / 804 -- more lanes mainly hide the host side of the end-to-end path).  The default stays 8
+    # at every N so that the per-GPU configuration of the weak-scaling run is the same (8 lanes per GPU were also the
+    # best setting on the 8-GPU / 32-core box).
+    B = args.batch if args.batch > 0 else max(1, min(WL['lanes'], cores))
     # host wait policy: spin unless the lane threads of all ranks oversubscribe the cores, then yield
     # (measured on the 8-GPU / 32-core box before the CUDA-graph loop: 2938 runs/s with yield vs 2639 with spin)
     policy = os.environ.get("AOSLO_BENCH_WAIT_POLICY", "2" if world * B * 2 > cores else "")
