@@ -757,9 +757,7 @@ __global__ void __launch_bounds__(kThreads) thin_map_rows_kernel(const double2* 
 __global__ void __launch_bounds__(kThreads) knn2_rows_kernel(LinkView lv, const uint8_t* __restrict__ stable,
                                                              int n_host, const int* d_n, double thr,
                                                              const double* d_thr, int32_t* knn_idx, double* knn_d2,
-                                                             uint8_t* del, int* active, int* n_active, int* status,
-                                                             const int* gate) {
-    if (gate && *gate == 0) return;            // fallback of the non-stable-list path: nothing coincided
+                                                             uint8_t* del, int* active, int* n_active, int* status) {
     int n = d_n ? *d_n : n_host;
     if (d_thr) thr = *d_thr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -799,9 +797,8 @@ __global__ void __launch_bounds__(kThreads) collect_active_kernel(const int32_t*
 // running next to it).  `touch` is never reset: keys carry a per-call epoch.
 template <typename T>
 __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
-    const double2* __restrict__ pos, int32_t* knn_idx, double* knn_d2, const int* __restrict__ active_a,
-    int* n_active_a, const int* __restrict__ active_b, int* n_active_b, int* fallback, int* n_ns, int n_host,
-    const int* d_n, unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb,
+    const double2* __restrict__ pos, int32_t* knn_idx, double* knn_d2, const int* __restrict__ active,
+    int* n_active, int n_host, const int* d_n, unsigned int* d_epoch, int W, int H, const T* __restrict__ Rb,
     unsigned long long* touch, uint8_t* del, uint8_t* astate, int* block_sums, int nb_scan, int* d_n_out,
     int* status) {
     __shared__ int s_pending;
@@ -812,13 +809,7 @@ __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
     const unsigned int epoch = *d_epoch;
     for (int b = threadIdx.x; b < kMaxScanBlocks; b += blockDim.x) s_hist[b] = 0;
     __syncthreads();
-    // list B (all-rows fallback, built by the gated knn2_rows_kernel) supersedes list A (rows of the
-    // non-stable particles) when some particle had another one at distance 0.  The fallback
-    // stays a grid-wide kernel: it does fire (a moved particle landing on an occupied pixel), and one
-    // block redoing 145 k queries was measured at 1.7 ms.
-    const bool use_b = (fallback != nullptr) && (*fallback != 0);
-    const int* __restrict__ active = use_b ? active_b : active_a;
-    const int na = use_b ? *n_active_b : *n_active_a;
+    const int na = *n_active;
     // span of one compaction block (scan_span with blockDim = kScanThreads, gridDim = nb_scan)
     int per = 1;
     if (block_sums) {
@@ -884,10 +875,7 @@ __global__ void __launch_bounds__(kScanThreads) delete_resolve_small_kernel(
     }
     if (threadIdx.x == 0) {                   // ready for the next call
         *d_epoch = epoch + 1;
-        *n_active_a = 0;
-        if (n_active_b) *n_active_b = 0;
-        if (fallback) *fallback = 0;
-        if (n_ns) *n_ns = 0;
+        *n_active = 0;
     }
 }
 
@@ -1937,7 +1925,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
             AOSLO_TRY(build_links(ctx, s, ctx->lk_p, d_pos, n, d_n, kLinkBiasSteady));
             knn2_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(link_view(ctx, ctx->lk_p, d_pos), d_stable, n, d_n, thr, d_thr,
                                                           ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_del, ctx->d_active,
-                                                          n_active, ctx->d_status, nullptr);
+                                                          n_active, ctx->d_status);
             AOSLO_LAUNCH_CHECK();
         } else {
             AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
@@ -1950,8 +1938,8 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         // the number of compaction blocks is a launch-size choice only (any count is correct for any n)
         const int nb_scan = scan_blocks_for(scan_hint > 0 ? scan_hint : n);
         delete_resolve_small_kernel<T><<<1, kScanThreads, 0, s>>>(
-            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active, nullptr, nullptr, nullptr,
-            nullptr, n, d_n, ctx->d_epoch, W, H, d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate,
+            (const double2*)d_pos, ctx->d_knn_idx, ctx->d_knn_d2, ctx->d_active, n_active, n, d_n, ctx->d_epoch, W, H,
+            d_Rb, ctx->d_touch, ctx->d_del, ctx->d_rowstate,
             ctx->d_block_sums, nb_scan, d_n_out, ctx->d_status);
         AOSLO_LAUNCH_CHECK();
         ++ctx->epoch;                               // host-side upper estimate of the device epoch

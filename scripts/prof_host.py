@@ -1,17 +1,36 @@
-import cProfile, pstats, sys, time
-sys.path.insert(0, '.')
-import numpy as np, torch
+"""Host-side profile of the end-to-end call: where the Python / driver time of find_blobs goes (cProfile, one lane,
+2048^2 benchmark frame, canonical tie order, pinned host buffers)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
 import bench
-from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
-img, gt, cfg = bench.make_workload(0)
-for _ in range(2):
-    find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+
+lane = bench.Lane(0, torch.device("cuda", 0))
+for _ in range(5):
+    lane.run_e2e()
 torch.cuda.synchronize()
-pr = cProfile.Profile(); pr.enable()
-t=time.perf_counter()
-for _ in range(3):
-    find_blobs(dict(cfg), gt.copy(), img, None, False, False)
+N = 50
+t = time.perf_counter()
+for _ in range(N):
+    lane.run_e2e()
 torch.cuda.synchronize()
-print('per call ms', (time.perf_counter()-t)/3*1e3)
+print("e2e wall per call: %.3f ms" % ((time.perf_counter() - t) / N * 1e3))
+t = time.perf_counter()
+for _ in range(N):
+    lane.run_resident()
+torch.cuda.synchronize()
+print("resident wall per call: %.3f ms" % ((time.perf_counter() - t) / N * 1e3))
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(N):
+    lane.run_e2e()
 pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(25)
+st = pstats.Stats(pr)
+st.sort_stats("tottime").print_stats(22)

@@ -530,10 +530,10 @@ def _iterate_oracle(p, st, Rb, grad, cfg, tie_mode):
 
 
 @pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
-def test_iterate_matches_oracle_incl_coincidence_fallback(zoo_field, tie_mode):
-    """aoslo_iterate (= one epoch of aoslo_run).  Case B puts a non-stable particle next to a stable one
-    so that it steps ONTO it: the non-stable-list path must detect the coincidence, fall back to the
-    all-rows deletion and still agree with the oracle."""
+def test_iterate_matches_oracle_incl_coincident_particles(zoo_field, tie_mode):
+    """aoslo_iterate (= one epoch of aoslo_run, on the same kernels).  Case B puts non-stable particles next to stable
+    ones so that they step ONTO them: only the rows of the non-stable particles are evaluated (the argument why that
+    suffices is in dual_rows_kernel), and the result must still equal the oracle's walk over all rows."""
     from detecting_cones_aoslo_b200.pipeline_with_delitions import make_config_struct
     from detecting_cones_aoslo_b200.utils import get_engine
     cfg, img, gt, Rb, grad = zoo_field
