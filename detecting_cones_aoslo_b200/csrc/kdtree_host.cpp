@@ -37,7 +37,7 @@ struct Builder {
 
     // depth < kParallelDepth: the two subtrees (disjoint ranges of idx, disjoint nodes) are built by two threads --
     // the result is the same sequence of std::nth_element calls on the same ranges, only not one after the other
-    static constexpr int kParallelDepth = 3;
+    int parallel_depth = 3;              // 8 threads; 16 on hosts with >= 16 hardware threads (set by the caller)
     static constexpr int kParallelMinPoints = 2048;
 
     void build(int i_node, int idx_start, int idx_end, int depth = 0) {
@@ -65,7 +65,7 @@ struct Builder {
             if (spread[j] > max_spread) { max_spread = spread[j]; j_max = j; }
         IndexComparator cmp{data, j_max};
         std::nth_element(idx + idx_start, idx + idx_start + n_mid, idx + idx_end, cmp);
-        if (depth < kParallelDepth && n_points >= kParallelMinPoints) {
+        if (depth < parallel_depth && n_points >= kParallelMinPoints) {
             std::thread left([=] { build(2 * i_node + 1, idx_start, idx_start + n_mid, depth + 1); });
             build(2 * i_node + 2, idx_start + n_mid, idx_end, depth + 1);
             left.join();
@@ -97,6 +97,8 @@ extern "C" int aoslo_kdtree_build_host(const double* h_points, int n, int32_t* h
         h_node_bounds[4 * (size_t)i + 2] = 0; h_node_bounds[4 * (size_t)i + 3] = 0;
     }
     Builder b{h_points, h_idx_array, h_node_start, h_node_end, h_node_bounds, n_nodes};
+    static const unsigned hw = std::thread::hardware_concurrency();
+    b.parallel_depth = hw >= 16 ? 4 : 3;
     b.build(0, 0, n);
     return AOSLO_OK;
 }
