@@ -324,13 +324,15 @@ extern "C" int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t*
                                     int pitch0_bytes, int x_min, int x_max, int y_min, int y_max, int bx, int by,
                                     uint8_t* d_img_out, int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw,
                                     double* d_gt_out, int* h_n_gt_out) {
-    if (!ctx || !d_raw_img || !d_img_out || !h_n_gt_out) return AOSLO_ERR_INVALID;
+    if (!ctx || !d_raw_img || !d_img_out) return AOSLO_ERR_INVALID;
     if (n_gt_raw > 0 && (!d_gt_minus1 || !d_gt_out)) return AOSLO_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    AOSLO_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), s));
+    int* d_count = ctx->d_counters + 30;             // dedicated: aoslo_run(n_gt = -1) reads it on the device
+    AOSLO_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
     AOSLO_TRY(stage_prepare(ctx, s, d_raw_img, H0, W0, pitch0_bytes, x_min, x_max, y_min, y_max, bx, by, d_img_out,
-                            out_pitch_bytes, d_gt_minus1, n_gt_raw, d_gt_out, ctx->d_counters));
-    return read_int(ctx, s, ctx->d_counters, h_n_gt_out);
+                            out_pitch_bytes, d_gt_minus1, n_gt_raw, d_gt_out, d_count));
+    if (!h_n_gt_out) return AOSLO_OK;                // the caller does not need the count on the host: no sync
+    return read_int(ctx, s, d_count, h_n_gt_out);
 }
 
 extern "C" int aoslo_seed(aoslo_ctx* ctx, void* stream, const void* d_Rb, int field_dtype, int H, int W, int bx,
@@ -604,6 +606,11 @@ __global__ void iter_end_kernel(RunCtl* ctl, const RunParams* rp, const int* cnt
 
 __global__ void stamp_kernel(RunCtl* ctl, int bucket) {
     if (threadIdx.x == 0) ctl_stamp(ctl, bucket);
+}
+
+// n_gt = -1: the GT count of the run is the device scalar left by aoslo_prepare_inputs
+__global__ void params_ngt_kernel(RunParams* rp, const int* d_n_gt) {
+    if (threadIdx.x == 0) rp->n_gt = *d_n_gt;
 }
 
 __global__ void run_end_kernel(RunCtl* ctl, const int* cnt) {
@@ -894,7 +901,8 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
                   aoslo_run_summary* h_summary, float* h_stage_ms) {
     const int H = cfg->H, W = cfg->W;
     RunPlan P;
-    P.ctx = ctx; P.cfg = cfg; P.d_Rb = d_Rb; P.d_grad = d_grad; P.fdt = field_dtype; P.d_gt = d_gt; P.n_gt = n_gt;
+    P.ctx = ctx; P.cfg = cfg; P.d_Rb = d_Rb; P.d_grad = d_grad; P.fdt = field_dtype; P.d_gt = d_gt;
+    P.n_gt = n_gt < 0 ? ctx->gt_cap : n_gt;          // launch-size bound only: the kernels read the device count
     P.want_records = h_records != nullptr && max_records > 0;
     P.max_records = P.want_records ? max_records : 0;
     P.timing = h_stage_ms != nullptr;
@@ -926,6 +934,10 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
         r.fix_freq = cfg->fix_particles_frequency; r.metric_freq = cfg->metric_measure_freq;
         r.epoch_num = cfg->epoch_num; r.early_stop = cfg->early_stop; r.max_records = P.max_records; r.n_gt = n_gt;
         AOSLO_CUDA(cudaMemcpyAsync(ctx->d_params, ctx->h_params, sizeof(RunParams), cudaMemcpyHostToDevice, s));
+        if (n_gt < 0) {
+            params_ngt_kernel<<<1, 32, 0, s>>>(ctx->d_params, ctx->d_counters + 30);
+            AOSLO_LAUNCH_CHECK();
+        }
     }
     AOSLO_TRY(epoch_guard(ctx, s, (unsigned)cfg->epoch_num + 1u));
     ctx->epoch += (unsigned)cfg->epoch_num;          // upper estimate of the resolve calls of this run
@@ -1198,7 +1210,8 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
                          int max_records, double* d_particles_out, uint8_t* d_stable_out,
                          aoslo_run_summary* h_summary, float* h_stage_ms) {
     if (!ctx || !cfg || !d_Rb || !d_grad || !d_gt || !h_summary) return AOSLO_ERR_INVALID;
-    if (cfg->H != ctx->H || cfg->W != ctx->W || n_gt < 1 || n_gt > ctx->gt_cap) return AOSLO_ERR_INVALID;
+    if (cfg->H != ctx->H || cfg->W != ctx->W || n_gt == 0 || n_gt > ctx->gt_cap) return AOSLO_ERR_INVALID;
+    if (n_gt < 0 && cfg->tie_mode != AOSLO_TIE_CANONICAL) return AOSLO_ERR_INVALID;   // the host-tree path needs it
     if (cfg->dist_n_neighbours < 1 || cfg->dist_n_neighbours + 1 > AOSLO_KMAX) return AOSLO_ERR_UNSUPPORTED;
     if (cfg->particle_call_window < 1 || cfg->reception_field_size < 1 || cfg->reception_field_size > 64)
         return AOSLO_ERR_UNSUPPORTED;

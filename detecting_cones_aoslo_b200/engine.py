@@ -89,7 +89,7 @@ class Engine:
         view.copy_(torch.as_tensor(img), non_blocking=False)
         return view
 
-    def prepare_inputs(self, img, gt_minus1, region, boundary):
+    def prepare_inputs(self, img, gt_minus1, region, boundary, sync=True):
         """Device-side np.round + crop_image + mirror_padding_image (reference
         pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array; gt_minus1: (n,2) float64 host
         array ALREADY shifted by -1 (the in-place side effect stays on the host).  Returns the padded
@@ -132,7 +132,11 @@ class Engine:
                                        int(region['x_min']), int(region['x_max']), int(region['y_min']),
                                        int(region['y_max']), int(boundary['x']), int(boundary['y']),
                                        self._p(buf), pitch, self._p(d_gt_raw), g.shape[0], self._p(d_gt),
-                                       C.byref(self._n_out)), "aoslo_prepare_inputs")
+                                       C.byref(self._n_out) if sync else None), "aoslo_prepare_inputs")
+        if not sync:
+            # the cropped GT count stays on the device (aoslo_run reads it there): no host synchronisation;
+            # the returned view has the RAW length, only its first <count> rows are data
+            return buf[:, :self.W], d_gt[: g.shape[0]]
         return buf[:, :self.W], d_gt[: self._n_out.value]
 
     def empty(self, shape, dtype):
@@ -380,7 +384,7 @@ class Engine:
             self._fields[key] = (self.field(self.H, self.W, dtype), self.field(self.H, self.W, dtype, 2))
         return self._fields[key]
 
-    def run(self, cfg_struct, Rb, grad, gt, max_records=None, collect_times=True):
+    def run(self, cfg_struct, Rb, grad, gt, max_records=None, collect_times=True, n_gt_on_device=False):
         """aoslo_run.  The status word is sticky: call clear_status() before the field computation of a new run
         (find_blobs does); summ.status then carries the field's eigenvalue assert as well as the run's conditions.
         collect_times=False skips the five stage timings (one-thread time-stamp kernels in the run graph)."""
@@ -390,7 +394,8 @@ class Engine:
         summ = _lib.RunSummary()
         ms = (C.c_float * 5)() if collect_times else None
         check(lib.aoslo_run(self._h, self._stream(), C.byref(cfg_struct), self._pf(Rb), self._pf(grad), self._fdt(Rb),
-                            self._p(gt), gt.shape[0], recs, max_records, None, None, C.byref(summ), ms),
+                            self._p(gt), -1 if n_gt_on_device else gt.shape[0], recs, max_records, None, None,
+                            C.byref(summ), ms),
               "aoslo_run")
         # the final particles are copied out AFTER the run, sized by its result (no capacity-sized output)
         n = summ.n_particles

@@ -155,7 +155,11 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     # reference :26-33: GT -= 1 on the CALLER's array (host side effect), then round / crop / mirror
     # padding -- on the device (aoslo_prepare_inputs)
     GT_data = GT_enumerate_from_zero(GT_data)
-    d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary)
+    # fused canonical run: the cropped GT count is only needed on the device, so nothing synchronises between the
+    # upload and the end of the run
+    lazy_gt = (mode == 'fused' and _get(cur_config, 'tie_mode', 'sklearn') == 'canonical'
+               and cur_config['metric_algo'] == 'Chamfer' and GT_data.shape[0] > 0)
+    d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary, sync=not lazy_gt)
     if d_gt.shape[0] < 1:
         raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
     Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype,
@@ -165,7 +169,8 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
     # fused: the assert flag stays in the status word and is raised from the run's summary (one sync per call)
 
     if mode == 'fused':
-        time_spended = _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn)
+        time_spended = _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
+                                  n_gt_on_device=lazy_gt)
     else:
         time_spended = _run_staged(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
                                    trace)
@@ -213,13 +218,16 @@ def _log_record(log_fn, it, pm, lsa_sum, lsa_mean, lsa_var, blob_sum, blob_mean,
     log_fn(logs)
 
 
-def _run_fused(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_idx, log_fn):
+def _run_fused(eng, cur_config, Rb, grad, d_gt, result, use_wandb, experiment_idx, log_fn, n_gt_on_device=False):
     cfg = make_config_struct(cur_config, eng.H, eng.W, metric_every_iteration=use_wandb)
     if cfg.step_mode < 0:
         raise NotImplementedError("unknown step_mode is a silent no-op in the reference; use engine_mode='staged'")
     if cur_config['metric_algo'] != 'Chamfer':
         raise ValueError                                   # 'hangarian' runs in the staged driver (find_blobs)
-    summ, recs, pos, st, ms = eng.run(cfg, Rb, grad, d_gt, collect_times=bool(_get(cur_config, 'collect_stage_times', True)))
+    summ, recs, pos, st, ms = eng.run(cfg, Rb, grad, d_gt, collect_times=bool(_get(cur_config, 'collect_stage_times', True)),
+                                      n_gt_on_device=n_gt_on_device)
+    if n_gt_on_device and recs and recs[0].n_gt < 1:      # every GT point fell outside the region (sklearn raises)
+        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
     if summ.status:
         _lib.raise_device_status(summ.status)
     for rec in recs:

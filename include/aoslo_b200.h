@@ -144,7 +144,8 @@ int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable);
  * (image_transformation.py:6-21; the reference's region asserts -> AOSLO_ERR_INVALID) and
  * mirror_padding_image (:23-35).  d_raw_img: (H0,W0) u8; d_img_out: (H,W) u8 with the given pitch,
  * H = (y_max-y_min) + 2*by, W = (x_max-x_min) + 2*bx (must equal the context's shape);
- * GT rows kept when strictly inside the region, order preserved; count -> *h_n_gt_out. */
+ * GT rows kept when strictly inside the region, order preserved; count -> *h_n_gt_out (one host synchronisation),
+ * or h_n_gt_out = NULL: the count stays on the device for aoslo_run(..., n_gt = -1) and nothing synchronises. */
 int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0, int pitch0_bytes,
                          int x_min, int x_max, int y_min, int y_max, int bx, int by, uint8_t* d_img_out,
                          int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw, double* d_gt_out,
@@ -241,6 +242,8 @@ int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const v
  * All value parameters of `cfg` are uploaded per call, so runs that differ only in values (a sweep) share the
  * graph; d_Rb, d_grad, d_gt must be stable addresses for the graph to be reused.
  * AOSLO_TIE_SKLEARN: stage calls with one host round trip per kNN (host-built tree).
+ * n_gt = -1 (canonical tie order only): the GT count is the device scalar the last aoslo_prepare_inputs of this
+ * context left behind (d_gt must be its d_gt_out); the count comes back in the records' n_gt field.
  * summary.status = the context's status word at the end of the run; it is NOT cleared at the start, so a condition
  * raised by aoslo_blobness on the same stream (AOSLO_DEV_EIG_ASSERT) is reported with the run's own. */
 int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void* d_Rb, const void* d_grad,
