@@ -221,6 +221,18 @@ def test_find_blobs_raises_the_eigenvalue_assert_of_the_reference():
     assert res["_summary"]["status"] == 0
 
 
+def test_find_blobs_without_ground_truth_in_the_region_raises_like_sklearn():
+    """Every GT point outside the region: the reference's NearestNeighbors raises ValueError on the empty array.  In the
+    canonical fused path the cropped count never reaches the host before the run; it comes back with the records."""
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    far = gt.copy()
+    far[:, 0] += 400.0                                   # all points right of the 50..150 crop
+    for tie_mode in ("canonical", "sklearn"):
+        with pytest.raises(ValueError):
+            find_blobs(configs.variant(configs.main_config(), tie_mode=tie_mode), far.copy(), img, None, False, False)
+
+
 def test_device_input_preparation_matches_host():
     """aoslo_prepare_inputs (np.round + crop_image + mirror_padding_image on the device) == host path."""
     from detecting_cones_aoslo_b200.pipeline_with_delitions import prepare_inputs
