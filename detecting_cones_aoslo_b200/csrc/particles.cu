@@ -16,6 +16,9 @@
 //   move_kernel                      the move step                 (pipeline_with_delitions.py:215-245)
 //   metrics kernels                  calc_dist_to_neares x2, get_particles_in_image, calc_acc_metrics,
 //                                    calc_metrics('Chamfer'), calc_blob_energy (utils.py:214-242, :378-418, :137-144)
+// The whole-run loop of aoslo_run (canonical tie order) works on a tombstone + two-structure layout of the same
+// arithmetic (period_begin / dual_force_move / ns_relink / dual_rows / dual_metrics, "The run loop's particle
+// structure" below); its thinning rounds find their neighbours through a pixel map (thin_map_*).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
