@@ -751,6 +751,38 @@ def test_sweep_runner_lanes_shared_field_and_failures(tmp_path):
     runner.close()
 
 
+def test_sweep_cli_sweep_and_grid_modes(tmp_path):
+    """`python -m detecting_cones_aoslo_b200.sweep` (replaces main_with_delitions.py + the wandb agent): the sweep mode
+    writes benchmarking_chamfer.csv with one row per trial, sorted by dice_coeff_1, equal to find_blobs per trial; the
+    grid mode over a directory holding the shipped image reproduces the reference's config_zoo result
+    (dice_2 = 0.9343206696716033) through the TIFF / CSV loader with the header-row quirk."""
+    import pandas as pd
+    from test_host_logic import _write_tiff
+    from detecting_cones_aoslo_b200 import sweep
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    d = tmp_path / "all_dataset"
+    d.mkdir()
+    _write_tiff(str(d / "frame.tiff"), img, 32773)
+    with open(d / "frame.csv", "w") as f:
+        f.write("1.5,30\n")                                  # the line pd.read_csv eats as a header
+        for x, y in gt:
+            f.write("%r,%r\n" % (float(x), float(y)))
+    out = tmp_path / "sweep.csv"
+    assert sweep.main(["sweep", "--image", str(d / "frame.tiff"), "--gt", str(d / "frame.csv"), "--trials", "5",
+                       "--lanes", "2", "--out", str(out)]) == 0
+    t = pd.read_csv(out)
+    assert len(t) == 5 and list(t["dice_coeff_1"]) == sorted(t["dice_coeff_1"])
+    cfg = sweep.sample_trial(configs.zoo_config(), 3)
+    cfg["tie_mode"] = "canonical"
+    res, _ = find_blobs(cfg, gt.copy(), img, None, False, False)
+    assert np.isclose(t["dice_coeff_2"], res["dice_coeff_2"], rtol=0, atol=0).any()
+    out2 = tmp_path / "benchmarking_chamfer.csv"
+    assert sweep.main(["grid", "--dataset", str(d), "--lanes", "1", "--out", str(out2)]) == 0
+    g = pd.read_csv(out2)
+    assert len(g) == 1 and g["dice_coeff_2"][0] == 0.9343206696716033 and g["dice_coeff_1"][0] == 0.833386591678916
+
+
 def test_pinned_batch_loader_feeds_find_blobs(tmp_path):
     """dataio.PinnedBatch: TIFF / CSV decoded into one pinned buffer, one H2D copy, device images handed to find_blobs
     -- same result as the host-array path."""
