@@ -771,7 +771,7 @@ def test_sweep_cli_sweep_and_grid_modes(tmp_path):
     out = tmp_path / "sweep.csv"
     assert sweep.main(["sweep", "--image", str(d / "frame.tiff"), "--gt", str(d / "frame.csv"), "--trials", "5",
                        "--lanes", "2", "--out", str(out)]) == 0
-    t = pd.read_csv(out)
+    t = pd.read_csv(out, float_precision='round_trip')
     assert len(t) == 5 and list(t["dice_coeff_1"]) == sorted(t["dice_coeff_1"])
     cfg = sweep.sample_trial(configs.zoo_config(), 3)
     cfg["tie_mode"] = "canonical"
@@ -779,7 +779,7 @@ def test_sweep_cli_sweep_and_grid_modes(tmp_path):
     assert np.isclose(t["dice_coeff_2"], res["dice_coeff_2"], rtol=0, atol=0).any()
     out2 = tmp_path / "benchmarking_chamfer.csv"
     assert sweep.main(["grid", "--dataset", str(d), "--lanes", "1", "--out", str(out2)]) == 0
-    g = pd.read_csv(out2)
+    g = pd.read_csv(out2, float_precision='round_trip')
     assert len(g) == 1 and g["dice_coeff_2"][0] == 0.9343206696716033 and g["dice_coeff_1"][0] == 0.833386591678916
 
 
