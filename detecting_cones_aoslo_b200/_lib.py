@@ -59,6 +59,15 @@ class RunSummary(C.Structure):
     ]
 
 
+class TrialResult(C.Structure):
+    _fields_ = [
+        ("error", C.c_int32), ("pad_", C.c_int32),
+        ("summary", RunSummary), ("last", MetricsRecord),
+        ("dice_coeff_1", C.c_double), ("dice_coeff_2", C.c_double),
+        ("best_lsa_mean", C.c_double), ("best_blobEn_mean", C.c_double),
+    ]
+
+
 # every symbol include/aoslo_b200.h declares: name -> (restype, argtypes)
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 _ip = C.POINTER(C.c_int)
@@ -93,6 +102,7 @@ SYMBOLS = {
     "aoslo_iterate": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _ip]),
     "aoslo_run": (_i, [_vp, _vp, C.POINTER(Config), _vp, _vp, _i, _vp, _i, C.POINTER(MetricsRecord), _i, _vp, _vp,
                        C.POINTER(RunSummary), C.POINTER(C.c_float)]),
+    "aoslo_sweep": (_i, [_vp, _vp, C.POINTER(Config), _i, _vp, _vp, _i, _vp, _i, C.POINTER(TrialResult)]),
     "aoslo_read_particles": (_i, [_vp, _vp, _vp, _vp, _i]),
     "aoslo_tiff_info": (_i, [C.c_char_p, _ip, _ip, _ip, _ip]),
     "aoslo_tiff_read_gray8": (_i, [C.c_char_p, _vp, _i]),

@@ -1251,6 +1251,42 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     return AOSLO_OK;
 }
 
+extern "C" int aoslo_sweep(aoslo_ctx* ctx, void* stream, const aoslo_config* h_cfgs, int n_trials, const void* d_Rb,
+                           const void* d_grad, int field_dtype, const double* d_gt, int n_gt,
+                           aoslo_trial_result* h_results) {
+    if (!ctx || !h_cfgs || !h_results || n_trials < 0) return AOSLO_ERR_INVALID;
+    std::vector<aoslo_metrics_record> recs;
+    for (int t = 0; t < n_trials; ++t) {
+        const aoslo_config& cfg = h_cfgs[t];
+        aoslo_trial_result& r = h_results[t];
+        memset(&r, 0, sizeof(r));
+        r.dice_coeff_1 = -INFINITY; r.dice_coeff_2 = -INFINITY;
+        r.best_lsa_mean = INFINITY; r.best_blobEn_mean = -INFINITY;
+        if (cfg.metric_measure_freq < 1 || cfg.epoch_num < 0) { r.error = AOSLO_ERR_INVALID; continue; }
+        const int max_rec = cfg.epoch_num / cfg.metric_measure_freq + 2;
+        recs.resize((size_t)max_rec);
+        AOSLO_CUDA(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), (cudaStream_t)stream));
+        r.error = aoslo_run(ctx, stream, &cfg, d_Rb, d_grad, field_dtype, d_gt, n_gt, recs.data(), max_rec, nullptr,
+                            nullptr, &r.summary, nullptr);
+        if (r.error == AOSLO_ERR_CUDA) return r.error;          // a CUDA error is not a property of the trial
+        if (r.error != AOSLO_OK) continue;
+        for (int i = 0; i < r.summary.n_records; ++i) {
+            const aoslo_metrics_record& m = recs[i];
+            // calc_acc_metrics (utils.py:378-402) + the tracking of :335-359
+            const double d1 = 2.0 * m.tp[0] / (2.0 * m.tp[0] + m.fp[0] + m.fn[0]);
+            const double d2 = 2.0 * m.tp[1] / (2.0 * m.tp[1] + m.fp[1] + m.fn[1]);
+            if (r.dice_coeff_1 < d1 * 0.995) r.dice_coeff_1 = d1;
+            if (r.dice_coeff_2 < d2 * 0.995) r.dice_coeff_2 = d2;
+            const double lsa_mean = m.sum_p2g / m.n_particles + m.sum_g2p / m.n_gt;
+            const double blob_mean = m.blob_energy_sum / m.n_particles;
+            if (r.best_lsa_mean > lsa_mean) r.best_lsa_mean = lsa_mean;
+            if (r.best_blobEn_mean < blob_mean) r.best_blobEn_mean = blob_mean;
+        }
+        if (r.summary.n_records > 0) r.last = recs[r.summary.n_records - 1];
+    }
+    return AOSLO_OK;
+}
+
 extern "C" int aoslo_read_particles(aoslo_ctx* ctx, void* stream, double* d_particles_out, uint8_t* d_stable_out,
                                     int n) {
     if (!ctx || n < 0 || n > ctx->last_n) return AOSLO_ERR_INVALID;

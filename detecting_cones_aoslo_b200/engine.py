@@ -376,6 +376,16 @@ class Engine:
         return pos_out[:m], st_out[:m]
 
     # ------------------------------------------------------------------ L5 whole run
+    def sweep(self, cfg_structs, Rb, grad, gt):
+        """aoslo_sweep: the configurations of `cfg_structs` (list of _lib.Config) back to back on one field ->
+        list of _lib.TrialResult."""
+        n = len(cfg_structs)
+        cfgs = (_lib.Config * max(n, 1))(*cfg_structs)
+        res = (_lib.TrialResult * max(n, 1))()
+        check(lib.aoslo_sweep(self._h, self._stream(), cfgs, n, self._pf(Rb), self._pf(grad), self._fdt(Rb),
+                              self._p(gt), gt.shape[0], res), "aoslo_sweep")
+        return [res[i] for i in range(n)]
+
     def field_buffers(self, dtype):
         """Context-owned (H,W) / (H,W,2) field buffers: stable addresses let aoslo_run replay its cached
         CUDA graph instead of re-capturing it."""

@@ -173,6 +173,19 @@ def _record_of(unit, result, seconds):
     return pack_record(unit, result, result.get('_summary'), last, seconds)
 
 
+def _record_of_trial(unit, tr, seconds):
+    """aoslo_trial_result (C ABI, aoslo_sweep) -> record row."""
+    if tr.error != 0:
+        return failed_record(unit)
+    s = tr.summary
+    if s.status != 0:                       # a device-side condition (escaped particle, NaN, capacity, ...): the
+        return failed_record(unit)          # reference's find_blobs would have raised
+    row = [unit, 0, s.n_iterations, s.n_particles, s.n_seeds,
+           tr.last.tp[0], tr.last.fp[0], tr.last.fn[0], tr.last.tp[1], tr.last.fp[1], tr.last.fn[1],
+           tr.dice_coeff_1, tr.dice_coeff_2, tr.best_lsa_mean, tr.best_blobEn_mean, seconds]
+    return np.asarray(row, dtype=np.float64)
+
+
 def gather_records(local_records, n_units, device=None):
     """All-gather the per-unit records of every rank -> (n_units, RECORD_LEN) table ordered by unit.
     Equal counts are required by all_gather: shards are padded with NaN rows to the largest shard."""
@@ -281,6 +294,64 @@ class UnitRunner:
         rows.sort(key=lambda r: r[0])
         return rows
 
+    def _pool_trials(self, members, Rb, grad, d_gt, H, W, chunk=4):
+        """Trials on one field: the lanes pull chunks of trials and hand each chunk to ONE aoslo_sweep call (C ABI:
+        the trials of a chunk run back to back on the lane's stream, best-result bookkeeping included); trials the
+        C entry point does not cover (`hangarian` metric, staged mode) go through find_blobs' Python driver."""
+        from . import pipeline_with_delitions as pwd
+        torch = self.torch
+        q = queue.Queue()
+        for i in range(0, len(members), chunk):
+            q.put(members[i:i + chunk])
+        rows, lock = [], threading.Lock()
+
+        def loop(lane):
+            torch.cuda.set_device(self.device)
+            eng = self._engine(lane, H, W, d_gt.shape[0])
+            with torch.cuda.stream(self._streams[lane]):
+                while True:
+                    try:
+                        jobs = q.get_nowait()
+                    except queue.Empty:
+                        return
+                    t0 = time.perf_counter()
+                    out, fast, structs = [], [], []
+                    for unit, cfg in jobs:
+                        try:
+                            if cfg['metric_algo'] != 'Chamfer' or cfg.get('engine_mode', 'fused') != 'fused' or \
+                                    cfg['blobness_formula'] not in ('simple_div', 'custom'):
+                                res = pwd.run_on_field(eng, cfg, Rb, grad, d_gt)
+                                out.append(_record_of(unit, res, time.perf_counter() - t0))
+                                continue
+                            cs = pwd.make_config_struct(cfg, H, W)
+                            if cs.step_mode < 0:
+                                raise NotImplementedError
+                            fast.append(unit)
+                            structs.append(cs)
+                        except Exception:                   # noqa: BLE001 -- a failing unit must not stop the rank
+                            out.append(failed_record(unit))
+                    if structs:
+                        try:
+                            trs = eng.sweep(structs, Rb, grad, d_gt)
+                            dt = (time.perf_counter() - t0) / len(structs)
+                            out += [_record_of_trial(u, tr, dt) for u, tr in zip(fast, trs)]
+                        except Exception:                   # noqa: BLE001
+                            out += [failed_record(u) for u in fast]
+                    with lock:
+                        rows.extend(out)
+
+        n = min(self.lanes, max(1, q.qsize()))
+        if n == 1:
+            loop(0)
+        else:
+            ts = [threading.Thread(target=loop, args=(i,)) for i in range(n)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        rows.sort(key=lambda r: r[0])
+        return rows
+
     # ---- cfg5: many configurations on ONE image; the field is computed once per field key
     def run_trials(self, img, gt, trials):
         """trials: list of (unit_id, cur_config).  `gt` is the raw CSV array (1-based), left untouched."""
@@ -312,12 +383,7 @@ class UnitRunner:
                 master.raise_on_status()
             self._streams[0].synchronize()                   # the lanes read Rb / grad / d_gt from here on
 
-            def work(lane, job, Rb=Rb, grad=grad, d_gt=d_gt, H=H, W=W):
-                unit, cfg = job
-                eng = self._engine(lane, H, W, d_gt.shape[0])
-                return pwd.run_on_field(eng, cfg, Rb, grad, d_gt)
-
-            rows += self._pool(members, work)
+            rows += self._pool_trials(members, Rb, grad, d_gt, H, W)
         rows.sort(key=lambda r: r[0])
         return rows
 

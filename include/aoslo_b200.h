@@ -250,6 +250,26 @@ int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const void*
               int field_dtype, const double* d_gt, int n_gt, aoslo_metrics_record* h_records, int max_records,
               double* d_particles_out, uint8_t* d_stable_out, aoslo_run_summary* h_summary, float* h_stage_ms);
 
+/* ---- L6 sweep: `n_trials` configurations on ONE blobness field (replaces the per-trial body of the wandb agent loop,
+ * main_with_delitions.py:81-132: every trial of the sweep re-runs find_blobs on the same image, and no swept
+ * parameter changes the field).  Trials run back to back on `stream` (one aoslo_run each: in the canonical tie order
+ * trials that differ only in value parameters share one cached CUDA graph).  Per trial: the run summary, the last
+ * metrics record and the best-result bookkeeping of find_blobs' non-wandb branch (:335-359: dice with the 0.5 %
+ * hysteresis, min Chamfer mean, max mean blob energy).  A trial that fails (argument error, device condition) gets
+ * its code in `error` / `summary.status` and does not stop the sweep (the reference's driver catches and continues,
+ * :125-132).  Run several contexts on several streams for concurrency (sweep.UnitRunner). */
+typedef struct {
+    int32_t error;                  /* aoslo_status of the trial's aoslo_run (0 = ok)          */
+    int32_t pad_;
+    aoslo_run_summary summary;
+    aoslo_metrics_record last;      /* last metrics evaluation of the trial                    */
+    double dice_coeff_1, dice_coeff_2;          /* result['dice_coeff_1' / '2']                */
+    double best_lsa_mean, best_blobEn_mean;     /* result['best_lsa_mean' / 'best_blobEn_mean'] */
+} aoslo_trial_result;
+
+int aoslo_sweep(aoslo_ctx* ctx, void* stream, const aoslo_config* h_cfgs, int n_trials, const void* d_Rb,
+                const void* d_grad, int field_dtype, const double* d_gt, int n_gt, aoslo_trial_result* h_results);
+
 /* final particles / stable flags of the last aoslo_run on this context (the first n rows, n <= summary.n_particles),
  * copied device -> device on `stream`: lets the caller size its output after the run instead of passing
  * capacity-sized buffers to aoslo_run (whose d_particles_out / d_stable_out may be NULL). */
