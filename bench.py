@@ -325,9 +325,13 @@ class Lane:
         records)."""
         from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
         with self.torch.cuda.stream(self.stream):
-            np.copyto(self.gt_scratch, self.gt)
             res, _ = find_blobs(dict(self.cfg, **over), self.gt_scratch, self.img, None, False, False, engine=self.eng)
         return res
+
+    def prep_e2e(self):
+        """this step's host input: find_blobs shifts the caller's GT array in place (reference :26), so the bench
+        hands it a fresh copy every step -- made before the timed region, like the L2 flush"""
+        np.copyto(self.gt_scratch, self.gt)
 
 
 def run_gpu(args):
@@ -383,9 +387,12 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_step(fn, active):
+    def timed_step(fn, active, prep=None):
         """one step = every active lane once, concurrently; returns device ms (CUDA events on `main`,
-        lane streams forked from / joined to it)."""
+        lane streams forked from / joined to it).  `prep` builds the step's host inputs, untimed."""
+        if prep is not None:
+            for ln in active:
+                prep(ln)
         evict_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(main)
@@ -455,14 +462,14 @@ def run_gpu(args):
 
     # ---- end to end through the reference-facing entry point, HOST buffers in, records out
     for _ in range(min(2, args.warmup)):
-        timed_step(lambda ln: ln.run_e2e(), lanes)
+        timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e)
     barrier()
-    e2e_ms = [timed_step(lambda ln: ln.run_e2e(), lanes) for _ in range(args.steps)]
+    e2e_ms = [timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e) for _ in range(args.steps)]
     te = torch.tensor([float(sum(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * B / (float(te.item()) / 1e3)
-    e2e_lat = [timed_step(lambda ln: ln.run_e2e(), [lane0]) for _ in range(args.steps)]
+    e2e_lat = [timed_step(lambda ln: ln.run_e2e(), [lane0], Lane.prep_e2e) for _ in range(args.steps)]
     d2h = summ.n_records * 88 + 32 + 4
 
     # ---- blobness MPix/s (second half of BASELINE.json's metric): K1 alone, f32 fields (north_star's field
@@ -551,9 +558,11 @@ def run_gpu(args):
     faithful = None
     if not args.no_faithful:
         fo = dict(tie_mode='sklearn', early_stop=True)
+        lane0.prep_e2e()
         lane0.run_e2e(**fo)
-        f_lat = [timed_step(lambda ln: ln.run_e2e(**fo), [lane0]) for _ in range(2)]
-        f_all = [timed_step(lambda ln: ln.run_e2e(**fo), lanes) for _ in range(2)]
+        f_lat = [timed_step(lambda ln: ln.run_e2e(**fo), [lane0], Lane.prep_e2e) for _ in range(2)]
+        f_all = [timed_step(lambda ln: ln.run_e2e(**fo), lanes, Lane.prep_e2e) for _ in range(2)]
+        lane0.prep_e2e()
         fres = lane0.run_e2e(**fo)
         faithful = {"mode": "tie_mode='sklearn' (the reference's KD-tree neighbour order), early stop on: find_blobs' "
                             "default; end to end with host buffers",

@@ -293,6 +293,7 @@ extern "C" int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value) 
     else if (!strcmp(key, "pair_th")) ctx->tune.pair_th = value;
     else if (!strcmp(key, "pair_occ")) ctx->tune.pair_occ = value;
     else if (!strcmp(key, "dtile_th")) ctx->tune.dtile_th = value;
+    else if (!strcmp(key, "dtile_split")) ctx->tune.dtile_split = value;
     else if (!strcmp(key, "dtile_occ")) ctx->tune.dtile_occ = value;
     else if (!strcmp(key, "k1_kernel")) ctx->tune.k1_kernel = value;
     else if (!strcmp(key, "no_graph")) ctx->no_graph = value ? 1 : 0;

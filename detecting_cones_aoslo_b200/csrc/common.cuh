@@ -134,8 +134,9 @@ struct K1Tuning {
     int k1_tma = 1;          // 0: cp.async staging, plain stores; 1: TMA tensor loads; 2: TMA tensor stores too
     int pair_th = 0;         // tile height of the f32 pair kernel (0 = chosen per image)
     int pair_occ = 0;        // CTAs per SM of the f32 pair kernel (0 = by tile height)
-    int dtile_th = 0;        // tile height of the f64 tile kernel (0 = 32)
+    int dtile_th = 0;        // tile height of the f64 tile kernel (0 = 32, 16 for frames of less than half a wave)
     int dtile_occ = 0;       // CTAs per SM of the f64 tile kernel (0 = by tile height)
+    int dtile_split = 1;     // 16-row remainder tiles instead of a nearly empty last wave of full tiles
     int k1_kernel = 0;       // 0 auto, 1 generic tile kernel, 2 band kernel, 3 f64 tile kernel
 };
 

@@ -133,7 +133,8 @@ int aoslo_ctx_status(aoslo_ctx* ctx, void* stream, int* h_status_out, int clear)
 int aoslo_ctx_clear_status(aoslo_ctx* ctx, void* stream);
 int aoslo_ctx_capacity(aoslo_ctx* ctx);
 /* implementation knobs (defaults come from the environment once, at aoslo_ctx_create): "k1_tma" 0|1|2,
- * "pair_th", "pair_occ", "dtile_th" (0 = automatic), "k1_kernel" 0 auto | 1 generic tile | 2 band | 3 f64 tile,
+ * "pair_th", "pair_occ", "dtile_th", "dtile_occ" (0 = automatic), "dtile_split" 0|1,
+ * "k1_kernel" 0 auto | 1 generic tile | 2 band | 3 f64 tile,
  * "no_graph" 1 = run aoslo_run's canonical path eagerly (debugging / profiling).  Results do not depend on them. */
 int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value);
 /* 1: host-side waits of this context sleep on a blocking-sync event instead of spinning (use when many

@@ -17,7 +17,7 @@ import torch
 from detecting_cones_aoslo_b200.engine import Engine
 from detecting_cones_aoslo_b200.synth import synth_aoslo
 
-DEFAULTS = dict(k1_tma=1, pair_th=0, pair_occ=0, dtile_th=0, dtile_occ=0, k1_kernel=0)
+DEFAULTS = dict(k1_tma=1, pair_th=0, pair_occ=0, dtile_th=0, dtile_occ=0, dtile_split=1, k1_kernel=0)
 
 
 def main():
@@ -46,7 +46,9 @@ def main():
         if f[1] == "band":
             knobs["k1_kernel"] = 2
         elif f[0] == "f64":
-            knobs.update(k1_kernel=3, dtile_th=int(f[1]), dtile_occ=int(f[2]) if len(f) > 2 else 0)
+            # f64:<th>:<occ>[:nosplit]
+            knobs.update(k1_kernel=3, dtile_th=int(f[1]), dtile_occ=int(f[2]) if len(f) > 2 else 0,
+                         dtile_split=0 if (len(f) > 3 and f[3] == "nosplit") else 1)
         elif f[1] != "auto":
             knobs.update(pair_th=int(f[1]), pair_occ=int(f[2]) if len(f) > 2 else 0)
         eng.set_tuning(**knobs)
