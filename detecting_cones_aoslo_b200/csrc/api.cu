@@ -530,7 +530,6 @@ __global__ void run_begin_kernel(RunCtl* ctl, int* status, int* counters) {
     (void)status;             // sticky: conditions raised before the run (the field's eigenvalue assert) are kept
     counters[12] = 0; counters[13] = 0; counters[14] = 0; counters[15] = 0;
     counters[4] = 0; counters[5] = 0;
-    counters[8] = 0; counters[9] = 0;          // wavefront round / pending rows of the thinning rounds
 }
 
 __global__ void after_seed_kernel(RunCtl* ctl, const int* cnt, cudaGraphConditionalHandle h_thin, int use_handle) {
@@ -688,46 +687,15 @@ struct RunPlan {
     int* cnt0;
     int* cnt1;
     // kernel launches per body, counted while capturing (gpu_launches bookkeeping)
-    int k_static = 0, k_thin = 0, k_wave = 0, k_iter = 0, k_res = 0, k_met = 0;
+    int k_static = 0, k_thin = 0, k_iter = 0, k_res = 0, k_met = 0;
 };
 
-template <class F>
-int capture_body(cudaStream_t q, cudaGraph_t body, int* counter, F fn);
-
-// One thinning round (del_close_particles(thr = 3), :118) on buffer 0: rows through the pixel map, the wavefront
-// rounds of the greedy resolution as a NESTED WHILE node (two ordinary kernels per round: no cooperative launch),
-// order-preserving compaction into buffer 1, swap back.  Thresholds above the stencil radius take the generic
-// cell-list search + cooperative resolve.
 int enqueue_thin_round(RunPlan& P, cudaStream_t q, cudaGraphConditionalHandle h, int use_handle) {
     aoslo_ctx* c = P.ctx;
     const aoslo_config* cfg = P.cfg;
-    if (cfg->thinning_threshold > 4.0) {
-        AOSLO_TRY(stage_delete(c, q, c->d_pos[0], c->d_stable[0], P.inner, P.d_Rb, P.fdt, cfg->H, cfg->W,
-                               cfg->thinning_threshold, AOSLO_TIE_CANONICAL, c->d_pos[1], c->d_stable[1], nullptr,
-                               P.cnt1, nullptr, P.cnt0, 0, &c->d_params->thin_thr, 0));
-    } else {
-        if (use_handle) {
-            CondNode wave;
-            AOSLO_TRY(new_cond_handle(q, &wave.handle));
-            AOSLO_TRY(stage_thin_rows(c, q, P.inner, P.cnt0, cfg->thinning_threshold, &c->d_params->thin_thr, c->d_ctl,
-                                      wave.handle, 1));
-            AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &wave));
-            cudaStream_t b3 = c->cap_stream3;
-            AOSLO_TRY(capture_body(b3, wave.body, &P.k_wave, [&]() {
-                return stage_thin_wave(c, b3, P.inner, P.cnt0, P.d_Rb, P.fdt, c->d_ctl, wave.handle, 1);
-            }));
-        } else {
-            AOSLO_TRY(stage_thin_rows(c, q, P.inner, P.cnt0, cfg->thinning_threshold, &c->d_params->thin_thr, c->d_ctl,
-                                      0, 0));
-            for (;;) {
-                AOSLO_CUDA(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, q));
-                AOSLO_TRY(stream_wait(c, q));
-                if (!c->h_ctl->wave_cond) break;
-                AOSLO_TRY(stage_thin_wave(c, q, P.inner, P.cnt0, P.d_Rb, P.fdt, c->d_ctl, 0, 0));
-            }
-        }
-        AOSLO_TRY(stage_thin_compact(c, q, P.inner, P.cnt0, P.cnt1));
-    }
+    AOSLO_TRY(stage_delete(c, q, c->d_pos[0], c->d_stable[0], P.inner, P.d_Rb, P.fdt, cfg->H, cfg->W,
+                           cfg->thinning_threshold, AOSLO_TIE_CANONICAL, c->d_pos[1], c->d_stable[1], nullptr, P.cnt1,
+                           nullptr, P.cnt0, 3, &c->d_params->thin_thr, 0));
     thin_swap_kernel<<<c->nb, kThreads, 0, q>>>((const double2*)c->d_pos[1], c->d_stable[1], P.cnt1,
                                                 (double2*)c->d_pos[0], c->d_stable[0], P.cnt0, c->d_ctl, h, use_handle);
     AOSLO_LAUNCH_CHECK();
@@ -1034,14 +1002,12 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
             }
             hit->graph = graph;                      // kept alive with its conditional handles
             hit->key.assign((const unsigned char*)&key, (const unsigned char*)&key + sizeof(key));
-            hit->static_kernels = P.k_static; hit->thin_kernels = P.k_thin; hit->wave_kernels = P.k_wave;
-            hit->iter_kernels = P.k_iter;
+            hit->static_kernels = P.k_static; hit->thin_kernels = P.k_thin; hit->iter_kernels = P.k_iter;
             hit->resample_kernels = P.k_res; hit->metrics_kernels = P.k_met;
         }
         hit->stamp = ++ctx->graph_clock;
         AOSLO_CUDA(cudaGraphLaunch(hit->exec, s));
-        P.k_static = hit->static_kernels; P.k_thin = hit->thin_kernels; P.k_wave = hit->wave_kernels;
-        P.k_iter = hit->iter_kernels;
+        P.k_static = hit->static_kernels; P.k_thin = hit->thin_kernels; P.k_iter = hit->iter_kernels;
         P.k_res = hit->resample_kernels; P.k_met = hit->metrics_kernels;
     }
     // ---- the one synchronisation of the run
@@ -1070,7 +1036,7 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
         for (int i = 0; i < 5; ++i) h_stage_ms[i] = (float)((double)r.acc_ns[i] * 1e-6);
     if (!ctx->no_graph) {
         // kernels the graph executed: static nodes + the bodies as often as the control block says they ran
-        long long k = P.k_static + (long long)r.thin_rounds * P.k_thin + (long long)r.wave_rounds * P.k_wave;
+        long long k = P.k_static + (long long)r.thin_rounds * P.k_thin;
         if (P.dynamic_loop) {
             int n_res = 0;
             for (int it = 0; it < it_done; ++it) if (it % cfg->fix_particles_frequency == 3) ++n_res;

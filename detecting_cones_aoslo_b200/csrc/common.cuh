@@ -109,8 +109,6 @@ struct RunCtl {
     int loop_cond;
     int do_resample, do_metrics;
     int n_final;
-    int wave_cond;           // thinning: rows still pending after the last wavefront round (inner WHILE node)
-    int wave_rounds;         // wavefront rounds executed in this run (launch bookkeeping)
     int pad_;
     unsigned long long t_last;       // %globaltimer of the last stage boundary
     unsigned long long acc_ns[5];    // the reference's five time_spended buckets
@@ -144,8 +142,7 @@ struct RunGraph {            // one cached instantiation
     std::vector<unsigned char> key;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int static_kernels = 0, thin_kernels = 0, wave_kernels = 0, iter_kernels = 0, resample_kernels = 0,
-        metrics_kernels = 0;
+    int static_kernels = 0, thin_kernels = 0, iter_kernels = 0, resample_kernels = 0, metrics_kernels = 0;
     unsigned long long stamp = 0;    // LRU
 };
 
@@ -413,12 +410,6 @@ int stage_metrics(aoslo_ctx*, cudaStream_t, const double* d_pos, const uint8_t* 
                   const int* d_iteration = nullptr);
 // run loop, tombstone / dual-structure scheme (particles.cu): state lives in buffer 0, tombstone count in
 // d_counters[7]
-// thinning round of aoslo_run in pieces (the wavefront rounds are the body of a nested WHILE graph node)
-int stage_thin_rows(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, double thr, const double* d_thr, RunCtl* ctl,
-                    unsigned long long wave_handle, int use_handle);
-int stage_thin_wave(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, const void* d_Rb, int field_dtype,
-                    RunCtl* ctl, unsigned long long wave_handle, int use_handle);
-int stage_thin_compact(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, int* d_n_out);
 int stage_period_begin(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n);
 int stage_dual_step(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, int k, int energy_type, double p0, double p1,
                     double p2, const void* d_grad, const void* d_Rb, int field_dtype, int H, int W, double lb, double ld,

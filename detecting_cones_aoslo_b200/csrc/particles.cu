@@ -727,22 +727,16 @@ __global__ void __launch_bounds__(kThreads) thin_map_scatter_kernel(const double
     }
 }
 
-// wave = 1 (aoslo_run): the kernel also initialises the wavefront state of the round (rowstate / del / touch, the
-// number of active rows); its last block opens the wavefront loop (round 1, condition = "rows are pending")
 __global__ void __launch_bounds__(kThreads) thin_map_rows_kernel(const double2* __restrict__ pos, int n_host,
                                                                  const int* d_n, int W, int H,
                                                                  const unsigned long long* __restrict__ map,
                                                                  const int* __restrict__ geom, ThinStencil st,
                                                                  double thr, const double* d_thr, int32_t* knn_idx,
-                                                                 double* knn_d2, int wave, uint8_t* rowstate,
-                                                                 uint8_t* del, unsigned long long* touch, int* ctrs,
-                                                                 int* ticket, RunCtl* ctl,
-                                                                 cudaGraphConditionalHandle h_wave, int use_handle) {
+                                                                 double* knn_d2) {
     const int n = d_n ? *d_n : n_host;
     if (d_thr) thr = *d_thr;
     const unsigned int tag = (unsigned int)geom[6];
     const double thr2 = thr * thr;
-    int active = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double2 p = pos[i];
         const int x = (int)p.x, y = (int)p.y;
@@ -758,89 +752,6 @@ __global__ void __launch_bounds__(kThreads) thin_map_rows_kernel(const double2* 
         knn_idx[2 * (size_t)i + 1] = to;
         knn_d2[2 * (size_t)i] = 0.0;
         knn_d2[2 * (size_t)i + 1] = (to >= 0) ? (double)d2 : INFINITY;
-        if (wave) {
-            rowstate[i] = to >= 0 ? 1 : 0;          // every seed is non-stable: a row is active iff it has a neighbour
-            del[i] = 0;
-            touch[i] = 0ull;
-            active += to >= 0 ? 1 : 0;
-        }
-    }
-    if (!wave) return;
-    for (int o = 16; o > 0; o >>= 1) active += __shfl_down_sync(0xffffffffu, active, o);
-    if ((threadIdx.x & 31) == 0 && active) atomicAdd(&ctrs[1], active);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
-        __threadfence();
-        const int pending = atomicAdd(&ctrs[1], 0);
-        ctrs[0] = 1;                                 // wavefront round
-        ctrs[1] = 0;
-        ctl->wave_cond = pending > 0 ? 1 : 0;
-        if (use_handle) cudaGraphSetConditional(h_wave, pending > 0 ? 1u : 0u);
-        *ticket = 0;
-    }
-}
-
-// One wavefront round of the greedy deletion (see delete_resolve_kernel), split at its grid barrier into two
-// ordinary kernels so that no cooperative launch is needed (a cooperative grid needs room on every SM at once,
-// which stalls the other lanes' kernels): every pending row stamps both endpoints with (round, ~row) ...
-__global__ void __launch_bounds__(kThreads) thin_wave_stamp_kernel(int n_host, const int* d_n,
-                                                                   const int32_t* __restrict__ knn_idx,
-                                                                   const uint8_t* __restrict__ rowstate,
-                                                                   unsigned long long* touch, const int* ctrs) {
-    const int n = d_n ? *d_n : n_host;
-    const unsigned long long hi = (unsigned long long)(unsigned int)ctrs[0] << 32;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (rowstate[i] != 1) continue;
-        const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
-        atomicMax(&touch[i], key);
-        atomicMax(&touch[knn_idx[2 * (size_t)i + 1]], key);
-    }
-}
-
-// ... and a row that owns both of its endpoints is resolved; the last block decides whether another round follows
-template <typename T>
-__global__ void __launch_bounds__(kThreads) thin_wave_resolve_kernel(int n_host, const int* d_n,
-                                                                     const double2* __restrict__ pos,
-                                                                     const int32_t* __restrict__ knn_idx,
-                                                                     uint8_t* rowstate, const unsigned long long* touch,
-                                                                     uint8_t* del, const T* __restrict__ Rb, int W, int H,
-                                                                     int* ctrs, int* ticket, RunCtl* ctl, int* status,
-                                                                     cudaGraphConditionalHandle h_wave, int use_handle) {
-    const int n = d_n ? *d_n : n_host;
-    const unsigned long long hi = (unsigned long long)(unsigned int)ctrs[0] << 32;
-    int pending = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (rowstate[i] != 1) continue;
-        const int to = knn_idx[2 * (size_t)i + 1];
-        const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)i);
-        if (touch[i] == key && touch[to] == key) {
-            // rows resolved in one round never share an endpoint: nobody else reads or writes del[i] / del[to] now
-            if (!del[i] && !del[to]) {
-                const double e1 = energy_at<T>(Rb, pos[i], W, H, status);
-                const double e2 = energy_at<T>(Rb, pos[to], W, H, status);
-                del[(e1 < e2) ? i : to] = 1;
-            }
-            rowstate[i] = 0;
-        } else {
-            ++pending;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) pending += __shfl_down_sync(0xffffffffu, pending, o);
-    if ((threadIdx.x & 31) == 0 && pending) atomicAdd(&ctrs[1], pending);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
-        __threadfence();
-        int left = atomicAdd(&ctrs[1], 0);
-        const int round = ctrs[0];
-        if (round >= 100000) { atomicOr(status, AOSLO_DEV_CAPACITY); left = 0; }      // cannot happen; never spin
-        ctrs[0] = round + 1;
-        ctrs[1] = 0;
-        ctl->wave_cond = left > 0 ? 1 : 0;
-        ctl->wave_rounds += 1;
-        if (use_handle) cudaGraphSetConditional(h_wave, left > 0 ? 1u : 0u);
-        *ticket = 0;
     }
 }
 
@@ -2050,8 +1961,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                                                                  ctx->d_link_geom, ctx->d_status);
             AOSLO_LAUNCH_CHECK();
             thin_map_rows_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n, d_n, W, H, map, ctx->d_link_geom,
-                                                              stencil, thr, d_thr, ctx->d_knn_idx, ctx->d_knn_d2, 0,
-                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0);
+                                                              stencil, thr, d_thr, ctx->d_knn_idx, ctx->d_knn_d2);
             AOSLO_LAUNCH_CHECK();
         } else {
             AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
@@ -2206,48 +2116,6 @@ int stage_count_stable(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_stable, 
     count_stable_kernel<<<ctx->nb, kThreads, 0, s>>>(d_stable, n, d_n, d_out);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
-}
-
-// ---- thinning round of aoslo_run in pieces: rows (pixel map) -> wavefront rounds -> compaction -------------------
-int stage_thin_rows(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, double thr, const double* d_thr,
-                    RunCtl* ctl, unsigned long long wave_handle, int use_handle) {
-    if (thr > 4.0) return AOSLO_ERR_UNSUPPORTED;          // stencil radius (the caller falls back to the cell search)
-    static const ThinStencil stencil = make_thin_stencil();
-    unsigned long long* map = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the resample
-    thin_map_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)ctx->d_pos[0], n_bound, d_n, ctx->W, ctx->H, map,
-                                                         ctx->d_map_epoch, ctx->d_link_epoch_ticket, ctx->d_link_geom,
-                                                         ctx->d_status);
-    AOSLO_LAUNCH_CHECK();
-    thin_map_rows_kernel<<<ctx->nb, kThreads, 0, s>>>(
-        (const double2*)ctx->d_pos[0], n_bound, d_n, ctx->W, ctx->H, map, ctx->d_link_geom, stencil, thr, d_thr,
-        ctx->d_knn_idx, ctx->d_knn_d2, 1, ctx->d_rowstate, ctx->d_del, ctx->d_touch, ctx->d_counters + 8,
-        ctx->d_link_epoch_ticket, ctl, (cudaGraphConditionalHandle)wave_handle, use_handle);
-    AOSLO_LAUNCH_CHECK();
-    return AOSLO_OK;
-}
-
-int stage_thin_wave(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, const void* d_Rb, int field_dtype,
-                    RunCtl* ctl, unsigned long long wave_handle, int use_handle) {
-    thin_wave_stamp_kernel<<<ctx->nb, kThreads, 0, s>>>(n_bound, d_n, ctx->d_knn_idx, ctx->d_rowstate, ctx->d_touch,
-                                                        ctx->d_counters + 8);
-    AOSLO_LAUNCH_CHECK();
-    if (field_dtype == AOSLO_F32)
-        thin_wave_resolve_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
-            n_bound, d_n, (const double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_rowstate, ctx->d_touch, ctx->d_del,
-            (const float*)d_Rb, ctx->W, ctx->H, ctx->d_counters + 8, ctx->d_link_epoch_ticket, ctl, ctx->d_status,
-            (cudaGraphConditionalHandle)wave_handle, use_handle);
-    else
-        thin_wave_resolve_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
-            n_bound, d_n, (const double2*)ctx->d_pos[0], ctx->d_knn_idx, ctx->d_rowstate, ctx->d_touch, ctx->d_del,
-            (const double*)d_Rb, ctx->W, ctx->H, ctx->d_counters + 8, ctx->d_link_epoch_ticket, ctl, ctx->d_status,
-            (cudaGraphConditionalHandle)wave_handle, use_handle);
-    AOSLO_LAUNCH_CHECK();
-    return AOSLO_OK;
-}
-
-int stage_thin_compact(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, int* d_n_out) {
-    KeepOp op{(const double2*)ctx->d_pos[0], ctx->d_stable[0], ctx->d_del, (double2*)ctx->d_pos[1], ctx->d_stable[1]};
-    return ordered_scan(ctx, s, op, n_bound, n_bound, d_n, d_n_out, nullptr, 0, nullptr);
 }
 
 // ---- host drivers of the run loop's tombstone / dual-structure scheme (aoslo_run, canonical tie order) ----
