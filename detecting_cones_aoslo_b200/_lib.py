@@ -84,7 +84,9 @@ SYMBOLS = {
     "aoslo_ctx_capacity": (_i, [_vp]),
     "aoslo_ctx_set_blocking_sync": (_i, [_vp, _i]),
     "aoslo_ctx_set_tuning": (_i, [_vp, C.c_char_p, _i]),
-    "aoslo_prepare_inputs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "aoslo_prepare_inputs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _i]),
+    "aoslo_stage_gt": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "aoslo_ctx_flush_host_work": (_i, [_vp]),
     "aoslo_blobness": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(_d), _ip, C.POINTER(_d), _i, _i, _i, _i, _vp, _vp]),
     "aoslo_grad_field": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "aoslo_seed": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _d, _vp, _i, _ip]),

@@ -269,6 +269,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
+    if (c->ev_upload) cudaEventDestroy(c->ev_upload);
     for (RunGraph& g : c->graphs) {
         if (g.exec) cudaGraphExecDestroy(g.exec);
         if (g.graph) cudaGraphDestroy(g.graph);
@@ -323,17 +324,51 @@ extern "C" int aoslo_ctx_clear_status(aoslo_ctx* ctx, void* stream) {
 
 extern "C" int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0,
                                     int pitch0_bytes, int x_min, int x_max, int y_min, int y_max, int bx, int by,
-                                    uint8_t* d_img_out, int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw,
-                                    double* d_gt_out, int* h_n_gt_out) {
+                                    uint8_t* d_img_out, int out_pitch_bytes, const double* d_gt, int n_gt_raw,
+                                    double* d_gt_out, int* h_n_gt_out, int gt_is_raw) {
     if (!ctx || !d_raw_img || !d_img_out) return AOSLO_ERR_INVALID;
-    if (n_gt_raw > 0 && (!d_gt_minus1 || !d_gt_out)) return AOSLO_ERR_INVALID;
+    if (n_gt_raw > 0 && (!d_gt || !d_gt_out)) return AOSLO_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     int* d_count = ctx->d_counters + 30;             // dedicated: aoslo_run(n_gt = -1) reads it on the device
     AOSLO_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), s));
     AOSLO_TRY(stage_prepare(ctx, s, d_raw_img, H0, W0, pitch0_bytes, x_min, x_max, y_min, y_max, bx, by, d_img_out,
-                            out_pitch_bytes, d_gt_minus1, n_gt_raw, d_gt_out, d_count));
+                            out_pitch_bytes, d_gt, n_gt_raw, d_gt_out, d_count, gt_is_raw));
     if (!h_n_gt_out) return AOSLO_OK;                // the caller does not need the count on the host: no sync
     return read_int(ctx, s, d_count, h_n_gt_out);
+}
+
+// Deferred host work: `h[i] += addend` on the caller's array, once the upload that read it has completed.
+// aoslo_run calls it between enqueueing its device work and waiting for it.
+static int run_deferred_host_work(aoslo_ctx* ctx) {
+    if (!ctx->defer_ptr) return AOSLO_OK;
+    double* h = ctx->defer_ptr;
+    const long long n = ctx->defer_n;
+    const double a = ctx->defer_add;
+    ctx->defer_ptr = nullptr;
+    AOSLO_CUDA(cudaEventSynchronize(ctx->ev_upload));
+    for (long long i = 0; i < n; ++i) h[i] += a;
+    return AOSLO_OK;
+}
+
+extern "C" int aoslo_stage_gt(aoslo_ctx* ctx, void* stream, double* h_gt, int n_gt_raw, double* d_gt_raw,
+                              int shift_in_place) {
+    if (!ctx || n_gt_raw < 0 || (n_gt_raw > 0 && (!h_gt || !d_gt_raw))) return AOSLO_ERR_INVALID;
+    AOSLO_TRY(run_deferred_host_work(ctx));          // an earlier staging that no run picked up
+    if (n_gt_raw == 0) return AOSLO_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    AOSLO_CUDA(cudaMemcpyAsync(d_gt_raw, h_gt, sizeof(double) * 2 * (size_t)n_gt_raw, cudaMemcpyHostToDevice, s));
+    if (!shift_in_place) return AOSLO_OK;
+    if (!ctx->ev_upload) AOSLO_CUDA(cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
+    AOSLO_CUDA(cudaEventRecord(ctx->ev_upload, s));
+    ctx->defer_ptr = h_gt;
+    ctx->defer_n = 2LL * n_gt_raw;
+    ctx->defer_add = -1.0;
+    return AOSLO_OK;
+}
+
+extern "C" int aoslo_ctx_flush_host_work(aoslo_ctx* ctx) {
+    if (!ctx) return AOSLO_ERR_INVALID;
+    return run_deferred_host_work(ctx);
 }
 
 extern "C" int aoslo_seed(aoslo_ctx* ctx, void* stream, const void* d_Rb, int field_dtype, int H, int W, int bx,
@@ -1010,7 +1045,8 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
         P.k_static = hit->static_kernels; P.k_thin = hit->thin_kernels; P.k_iter = hit->iter_kernels;
         P.k_res = hit->resample_kernels; P.k_met = hit->metrics_kernels;
     }
-    // ---- the one synchronisation of the run
+    // ---- host work that was waiting for a busy device (aoslo_stage_gt), then the one synchronisation of the run
+    AOSLO_TRY(run_deferred_host_work(ctx));
     AOSLO_TRY(stream_wait(ctx, s));
     const RunCtl& r = *ctx->h_ctl;
     h_summary->status |= ctx->h_pinned[2];
@@ -1246,6 +1282,10 @@ extern "C" int aoslo_run(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, 
     else
         st = run_sklearn(ctx, s, cfg, d_Rb, d_grad, field_dtype, d_gt, n_gt, h_records, max_records, h_summary,
                          h_stage_ms);
+    {
+        const int hw = run_deferred_host_work(ctx);      // error exits / the host-tree path: nothing stays pending
+        if (st == AOSLO_OK) st = hw;
+    }
     if (st != AOSLO_OK) return st;
     if (d_particles_out || d_stable_out)
         return aoslo_read_particles(ctx, stream, d_particles_out, d_stable_out, h_summary->n_particles);

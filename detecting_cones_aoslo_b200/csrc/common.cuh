@@ -183,6 +183,11 @@ struct aoslo_ctx {
     int* d_ns_list = nullptr;         // [cap] compact list of non-stable particles
     int blocking_sync = 0;            // 1: host waits sleep on a blocking event instead of spinning
     cudaEvent_t ev_block = nullptr;
+    // host work deferred behind the next run (aoslo_stage_gt: the reference's in-place GT shift)
+    cudaEvent_t ev_upload = nullptr;
+    double* defer_ptr = nullptr;
+    long long defer_n = 0;
+    double defer_add = 0.0;
     unsigned int epoch = 1;           // host-side upper estimate of *d_epoch
     unsigned int* d_epoch = nullptr;  // device call counter of the in-loop deletion (stamps `touch`)
     // cached CUDA graphs of the whole run (canonical tie order), keyed by the structural parameters
@@ -426,7 +431,7 @@ int stage_classify(aoslo_ctx*, cudaStream_t, const double* d_g2p, int n_gt, cons
                    int n, int bx, int by, int W, int H, double thr, uint8_t* gt_is_tp, uint8_t* particle_is_fp);
 int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t* d_raw, int H0, int W0, int pitch0, int x_min, int x_max,
                   int y_min, int y_max, int bx, int by, uint8_t* d_img_out, int out_pitch, const double* d_gt_raw,
-                  int n_gt_raw, double* d_gt_out, int* d_n_gt_out);
+                  int n_gt_raw, double* d_gt_out, int* d_n_gt_out, int gt_is_raw);
 int sqrt_inplace(cudaStream_t, double* a, size_t n);
 
 }  // namespace aoslo

@@ -2260,23 +2260,24 @@ __global__ void __launch_bounds__(kThreads) crop_pad_kernel(const uint8_t* __res
 }
 
 struct GtPrepOp {
-    const double2* gt;          // already shifted by -1 on the host (the reference mutates the caller's array)
+    const double2* gt;          // shift = 0: already shifted by -1 on the host (the reference mutates the caller's
+    double shift;               // array); shift = 1: the caller's raw 1-based array, GT_enumerate_from_zero applied here
     double x_min, x_max, y_min, y_max, bx, by;
     double2* out;
     __device__ int value(int i) const {
-        double gx = rint(gt[i].x), gy = rint(gt[i].y);   // np.round: half to even
+        double gx = rint(gt[i].x - shift), gy = rint(gt[i].y - shift);   // np.round: half to even
         return (gy > y_min && gy < y_max && gx > x_min && gx < x_max) ? 1 : 0;
     }
     __device__ void emit(int i, int v, int dst) const {
         if (!v) return;
-        double gx = rint(gt[i].x), gy = rint(gt[i].y);
+        double gx = rint(gt[i].x - shift), gy = rint(gt[i].y - shift);
         out[dst] = make_double2(gx - x_min + bx, gy - y_min + by);
     }
 };
 
 int stage_prepare(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_raw, int H0, int W0, int pitch0, int x_min,
                   int x_max, int y_min, int y_max, int bx, int by, uint8_t* d_img_out, int out_pitch,
-                  const double* d_gt_raw, int n_gt_raw, double* d_gt_out, int* d_n_gt_out) {
+                  const double* d_gt_raw, int n_gt_raw, double* d_gt_out, int* d_n_gt_out, int gt_is_raw) {
     if (x_min < 0 || y_min < 0 || x_max >= W0 || y_max >= H0) return AOSLO_ERR_INVALID;   // the reference's asserts
     const int wc = x_max - x_min, hc = y_max - y_min;
     if (wc < 1 || hc < 1 || bx < 0 || by < 0 || bx > wc || by > hc) return AOSLO_ERR_INVALID;
@@ -2286,7 +2287,7 @@ int stage_prepare(aoslo_ctx* ctx, cudaStream_t s, const uint8_t* d_raw, int H0, 
     crop_pad_kernel<<<grid, kThreads, 0, s>>>(d_raw, pitch0, x_min, y_min, wc, hc, bx, by, d_img_out, out_pitch, W, H);
     AOSLO_LAUNCH_CHECK();
     if (d_gt_raw && n_gt_raw > 0) {
-        GtPrepOp op{(const double2*)d_gt_raw, (double)x_min, (double)x_max, (double)y_min, (double)y_max,
+        GtPrepOp op{(const double2*)d_gt_raw, gt_is_raw ? 1.0 : 0.0, (double)x_min, (double)x_max, (double)y_min, (double)y_max,
                     (double)bx, (double)by, (double2*)d_gt_out};
         AOSLO_TRY(ordered_scan(ctx, s, op, n_gt_raw, n_gt_raw, nullptr, d_n_gt_out, nullptr, 0, nullptr));
     }

@@ -89,10 +89,13 @@ class Engine:
         view.copy_(torch.as_tensor(img), non_blocking=False)
         return view
 
-    def prepare_inputs(self, img, gt_minus1, region, boundary, sync=True):
+    def prepare_inputs(self, img, gt, region, boundary, sync=True, gt_is_raw=False):
         """Device-side np.round + crop_image + mirror_padding_image (reference
-        pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array; gt_minus1: (n,2) float64 host
-        array ALREADY shifted by -1 (the in-place side effect stays on the host).  Returns the padded
+        pipeline_with_delitions.py:27-33).  img: (H0,W0) uint8 host array (or a device uint8 tensor);
+        gt: (n,2) float64 host array -- gt_is_raw = False: ALREADY shifted by -1 by the caller (the reference's
+        in-place side effect); gt_is_raw = True: the caller's own 1-based array, which must be float64,
+        C-contiguous and writable: the device copy is shifted by the prepare kernel and the in-place shift of the
+        host array is deferred into the next run() (aoslo_stage_gt), or flush_host_work().  Returns the padded
         image view (pitch multiple of 16) and the cropped / shifted GT, both on the device."""
         on_device = isinstance(img, torch.Tensor)
         if not on_device:
@@ -110,34 +113,47 @@ class Engine:
         H0, W0 = img.shape
         assert (0 <= region['x_min']) and (0 <= region['y_min'])                       # image_transformation.py:7
         assert (W0 > region['x_max']) and (H0 > region['y_max'])                       # image_transformation.py:8
-        g = np.ascontiguousarray(gt_minus1, dtype=np.float64).reshape(-1, 2)
+        if gt_is_raw:
+            g = gt
+            if not (isinstance(g, np.ndarray) and g.dtype == np.float64 and g.flags.c_contiguous
+                    and g.flags.writeable and g.ndim == 2 and g.shape[1] == 2):
+                raise TypeError("gt_is_raw needs a writable C-contiguous (n,2) float64 array")
+        else:
+            g = np.ascontiguousarray(gt, dtype=np.float64).reshape(-1, 2)
         if g.shape[0] > self.gt_cap:
             raise MemoryError("GT capacity of the context exceeded")
         # context-owned device staging (stable addresses, no allocation per call); pageable host arrays go
         # through cudaMemcpyAsync's own staging, pinned ones (torch pin_memory) are true async copies
         if self._raw_bufs is None or self._raw_bufs[0].numel() < H0 * W0:
             self._raw_bufs = (self.empty((H0 * W0,), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
+        stream = self._stream()
         if on_device:
             d_raw = img                                    # already uploaded (batched pinned upload)
         else:
             d_raw = self._raw_bufs[0][: H0 * W0].view(H0, W0)
             d_raw.copy_(torch.from_numpy(img), non_blocking=True)
-        d_gt_raw = self._raw_bufs[1][: g.shape[0]]
-        d_gt_raw.copy_(torch.from_numpy(g), non_blocking=True)
+        d_gt_raw = self._raw_bufs[1]
+        check(lib.aoslo_stage_gt(self._h, stream, g.ctypes.data, g.shape[0], d_gt_raw.data_ptr(),
+                                 1 if gt_is_raw else 0), "aoslo_stage_gt")
         pitch = (self.W + 15) // 16 * 16
         if self._in_bufs is None:          # context-owned: stable addresses (CUDA-graph replay in aoslo_run)
             self._in_bufs = (self.empty((self.H, pitch), torch.uint8), self.empty((self.gt_cap, 2), torch.float64))
         buf, d_gt = self._in_bufs
-        check(lib.aoslo_prepare_inputs(self._h, self._stream(), self._p(d_raw), H0, W0, W0,
+        check(lib.aoslo_prepare_inputs(self._h, stream, self._p(d_raw), H0, W0, W0,
                                        int(region['x_min']), int(region['x_max']), int(region['y_min']),
                                        int(region['y_max']), int(boundary['x']), int(boundary['y']),
-                                       self._p(buf), pitch, self._p(d_gt_raw), g.shape[0], self._p(d_gt),
-                                       C.byref(self._n_out) if sync else None), "aoslo_prepare_inputs")
+                                       self._p(buf), pitch, d_gt_raw.data_ptr(), g.shape[0], d_gt.data_ptr(),
+                                       C.byref(self._n_out) if sync else None, 1 if gt_is_raw else 0),
+              "aoslo_prepare_inputs")
         if not sync:
             # the cropped GT count stays on the device (aoslo_run reads it there): no host synchronisation;
             # the returned view has the RAW length, only its first <count> rows are data
             return buf[:, :self.W], d_gt[: g.shape[0]]
         return buf[:, :self.W], d_gt[: self._n_out.value]
+
+    def flush_host_work(self):
+        """performs a deferred in-place GT shift now (after the upload) if no run() has picked it up"""
+        check(lib.aoslo_ctx_flush_host_work(self._h), "aoslo_ctx_flush_host_work")
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)

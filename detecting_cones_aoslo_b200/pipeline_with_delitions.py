@@ -153,27 +153,36 @@ def find_blobs(cur_config, GT_data, img, img_colorful, VERBOSE, USE_WANDB, exper
         raise ValueError('engine was created for a different padded shape / GT capacity')
     eng.clear_status()                                  # stream ordered; the word is read once, after the run
     # reference :26-33: GT -= 1 on the CALLER's array (host side effect), then round / crop / mirror
-    # padding -- on the device (aoslo_prepare_inputs)
-    GT_data = GT_enumerate_from_zero(GT_data)
+    # padding -- on the device (aoslo_prepare_inputs).
     # fused canonical run: the cropped GT count is only needed on the device, so nothing synchronises between the
-    # upload and the end of the run
+    # upload and the end of the run; the in-place shift of the caller's array (one pass over it on the host) is
+    # performed by the library while the device runs (aoslo_stage_gt), the device copy is shifted by the kernel
     lazy_gt = (mode == 'fused' and _get(cur_config, 'tie_mode', 'sklearn') == 'canonical'
                and cur_config['metric_algo'] == 'Chamfer' and GT_data.shape[0] > 0)
-    d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary, sync=not lazy_gt)
-    if d_gt.shape[0] < 1:
-        raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
-    Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype,
-                            out=eng.field_buffers(field_dtype))
-    if mode != 'fused':
-        eng.raise_on_status()                           # assert (eigs[0] > eigs[1]).all()  (:43)
-    # fused: the assert flag stays in the status word and is raised from the run's summary (one sync per call)
+    defer_shift = (lazy_gt and isinstance(GT_data, np.ndarray) and GT_data.dtype == np.float64
+                   and GT_data.flags.c_contiguous and GT_data.flags.writeable and GT_data.ndim == 2
+                   and GT_data.shape[1] == 2)
+    if not defer_shift:
+        GT_data = GT_enumerate_from_zero(GT_data)
+    try:
+        d_img, d_gt = eng.prepare_inputs(img, GT_data, region, boundary, sync=not lazy_gt, gt_is_raw=defer_shift)
+        if d_gt.shape[0] < 1:
+            raise ValueError("Found array with 0 sample(s) while a minimum of 1 is required by NearestNeighbors.")
+        Rb, grad = eng.blobness(d_img, formula, cur_config['gradient_type'], scales, field_dtype,
+                                out=eng.field_buffers(field_dtype))
+        if mode != 'fused':
+            eng.raise_on_status()                       # assert (eigs[0] > eigs[1]).all()  (:43)
+        # fused: the assert flag stays in the status word and is raised from the run's summary (one sync per call)
 
-    if mode == 'fused':
-        time_spended = _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
-                                  n_gt_on_device=lazy_gt)
-    else:
-        time_spended = _run_staged(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
-                                   trace)
+        if mode == 'fused':
+            time_spended = _run_fused(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
+                                      n_gt_on_device=lazy_gt)
+        else:
+            time_spended = _run_staged(eng, cur_config, Rb, grad, d_gt, result, USE_WANDB, experiment_idx, log_fn,
+                                       trace)
+    finally:
+        if defer_shift:
+            eng.flush_host_work()                       # error exits: the caller's array is shifted like the reference's
     result['time_spended'] = time.time() - t0
     return result, time_spended
 

@@ -282,18 +282,32 @@ def calc_acc_metrics(particles, GT_particles, gt_to_particles, particles_to_gt, 
     return out
 
 
+_NAN = np.float64('nan')
+
+
+def _ratio(num, den):
+    """num / den like NumPy scalars do it (0 / 0 -> nan instead of ZeroDivisionError); the counts are >= 0, so a
+    zero denominator implies a zero numerator in all three ratios below"""
+    return np.float64(num / den) if den else _NAN
+
+
 def metrics_from_record(rec):
-    """calc_acc_metrics dict + Chamfer summary from one device metrics record (aoslo_metrics_record)."""
+    """calc_acc_metrics dict + Chamfer summary from one device metrics record (aoslo_metrics_record).
+    Plain Python arithmetic on the integer counts (IEEE double, the same values NumPy's scalars give), wrapped into
+    the reference's result types at the end: ten records per run are on the latency path of find_blobs."""
     out = {}
+    tp, fp, fn = rec.tp, rec.fp, rec.fn
     for t, name in enumerate(('1', '2')):
-        TP, FP, FN = np.int64(rec.tp[t]), np.int64(rec.fp[t]), np.int64(rec.fn[t])
-        out[name] = {'TP': TP, 'FP': FP, 'FN': FN, 'dice': 2. * TP / (2. * TP + FP + FN),
-                     'recall': TP / (TP + FN + 0.), 'precision': TP / (TP + FP + 0.)}
+        TP, FP, FN = tp[t], fp[t], fn[t]
+        out[name] = {'TP': np.int64(TP), 'FP': np.int64(FP), 'FN': np.int64(FN),
+                     'dice': _ratio(2. * TP, 2. * TP + FP + FN),
+                     'recall': _ratio(TP, TP + FN + 0.), 'precision': _ratio(TP, TP + FP + 0.)}
     n, g = rec.n_particles, rec.n_gt
-    lsa_sum = rec.sum_p2g + rec.sum_g2p
-    lsa_mean = rec.sum_p2g / n + rec.sum_g2p / g
+    sum_p2g, sum_g2p = rec.sum_p2g, rec.sum_g2p
+    lsa_sum = sum_p2g + sum_g2p
+    lsa_mean = (sum_p2g / n if n else float('nan')) + (sum_g2p / g if g else float('nan'))
     lsa_var = rec.var_p2g + rec.var_g2p
-    return out, lsa_sum, lsa_mean, lsa_var, rec.blob_energy_sum / n
+    return out, lsa_sum, lsa_mean, lsa_var, (rec.blob_energy_sum / n if n else float('nan'))
 
 
 def calc_metrics(particles, GT_particles, gt_to_particles, particles_to_gt, mode='hangarian'):

@@ -141,16 +141,27 @@ int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value);
  * contexts run concurrently, one host thread each); 0 (default): lowest-latency spinning sync */
 int aoslo_ctx_set_blocking_sync(aoslo_ctx* ctx, int enable);
 
-/* ---- L1 pre-processing on the device: np.round of the (already -1 shifted) GT, crop_image
- * (image_transformation.py:6-21; the reference's region asserts -> AOSLO_ERR_INVALID) and
+/* ---- L1 pre-processing on the device: GT_enumerate_from_zero (utils.py:15-17) when gt_is_raw = 1, np.round of the
+ * GT, crop_image (image_transformation.py:6-21; the reference's region asserts -> AOSLO_ERR_INVALID) and
  * mirror_padding_image (:23-35).  d_raw_img: (H0,W0) u8; d_img_out: (H,W) u8 with the given pitch,
  * H = (y_max-y_min) + 2*by, W = (x_max-x_min) + 2*bx (must equal the context's shape);
+ * d_gt: (n_gt_raw,2) f64, gt_is_raw = 0: already shifted by -1 (the caller did the reference's in-place shift),
+ * gt_is_raw = 1: the caller's 1-based array as uploaded by aoslo_stage_gt;
  * GT rows kept when strictly inside the region, order preserved; count -> *h_n_gt_out (one host synchronisation),
  * or h_n_gt_out = NULL: the count stays on the device for aoslo_run(..., n_gt = -1) and nothing synchronises. */
 int aoslo_prepare_inputs(aoslo_ctx* ctx, void* stream, const uint8_t* d_raw_img, int H0, int W0, int pitch0_bytes,
                          int x_min, int x_max, int y_min, int y_max, int bx, int by, uint8_t* d_img_out,
-                         int out_pitch_bytes, const double* d_gt_minus1, int n_gt_raw, double* d_gt_out,
-                         int* h_n_gt_out);
+                         int out_pitch_bytes, const double* d_gt, int n_gt_raw, double* d_gt_out,
+                         int* h_n_gt_out, int gt_is_raw);
+
+/* Upload of the caller's (n_gt_raw,2) f64 ground truth (pinned or pageable host memory) into d_gt_raw.
+ * shift_in_place = 1: the reference shifts the CALLER's array by -1 (pipeline_with_delitions.py:26 -> utils.py:16);
+ * that host pass (one read + write of the array) is deferred: the next aoslo_run of this context performs it after
+ * it has enqueued its device work and before it waits (the upload has completed by then, checked with an event), so
+ * it costs no latency.  aoslo_ctx_flush_host_work performs it immediately if no run picked it up (error paths);
+ * aoslo_stage_gt itself flushes an older pending shift first.  The array must stay valid until then. */
+int aoslo_stage_gt(aoslo_ctx* ctx, void* stream, double* h_gt, int n_gt_raw, double* d_gt_raw, int shift_in_place);
+int aoslo_ctx_flush_host_work(aoslo_ctx* ctx);
 
 /* ---- L2 field: replaces skimage.hessian_matrix + hessian_matrix_eigvals + the blobness
  * formula + utils.calc_grad_field (pipeline_with_delitions.py:36-38, :60-68, :91;

@@ -489,6 +489,35 @@ def test_find_blobs_mutates_gt_like_reference_and_f32_mode():
         find_blobs(configs.main_config(), gt.copy(), img.astype(np.uint16), None, False, False)
 
 
+def test_deferred_gt_shift_is_the_reference_side_effect():
+    """Canonical fused path: the caller's GT array is uploaded as it is, shifted on the device, and the reference's
+    in-place `GT -= 1` (utils.py:16) happens on the host while the device runs (aoslo_stage_gt).  Same array contents
+    afterwards, same results as the host-first order, exactly one shift on the error path too."""
+    import torch
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+    img, gt = load_dataset()
+    cfg = configs.variant(configs.main_config(), tie_mode='canonical')
+    g = gt.copy()
+    res, _ = find_blobs(cfg, g, img, None, False, False)
+    np.testing.assert_array_equal(g, gt - 1.0)
+    # a Fortran-ordered array cannot be shifted by the library: host-first order, the same records
+    gf = np.asfortranarray(gt.copy())
+    ref, _ = find_blobs(cfg, gf, img, None, False, False)
+    np.testing.assert_array_equal(gf, gt - 1.0)
+    assert [bytes(r) for r in res["_records"]] == [bytes(r) for r in ref["_records"]]
+    np.testing.assert_array_equal(res["_final_particles"].cpu().numpy(), ref["_final_particles"].cpu().numpy())
+    # pinned host memory (a true asynchronous upload): the shift waits for the copy
+    gp = torch.from_numpy(gt.copy()).pin_memory().numpy()
+    res2, _ = find_blobs(cfg, gp, img, None, False, False)
+    np.testing.assert_array_equal(gp, gt - 1.0)
+    assert [bytes(r) for r in res2["_records"]] == [bytes(r) for r in ref["_records"]]
+    # error exit (the eigenvalue assert of a flat frame): shifted once, like the reference, which shifts first
+    g3 = gt.copy()
+    with pytest.raises(AssertionError):
+        find_blobs(cfg, g3, np.full_like(img, 90), None, False, False)
+    np.testing.assert_array_equal(g3, gt - 1.0)
+
+
 # ----------------------------------------------------------------------------------- more whole-run branches
 @pytest.mark.parametrize("over", [
     dict(step_mode="contin", lambda_blob=1.),
