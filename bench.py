@@ -334,6 +334,16 @@ class Lane:
         np.copyto(self.gt_scratch, self.gt)
 
 
+def pin_rank_to_core_slice(local, world):
+    """Every rank keeps its lane threads on its own slice of the host cores (set before the threads exist): 8 ranks x
+    8 lane threads on 32 cores otherwise migrate across all of them -- measured on the 8-GPU box: 6 689 -> 6 796
+    runs/s resident, 5 229 -> 6 014 end to end.  AOSLO_BENCH_AFFINITY=0 turns it off."""
+    if world > 1 and os.environ.get("AOSLO_BENCH_AFFINITY", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        avail = sorted(os.sched_getaffinity(0))
+        per = max(1, len(avail) // world)
+        os.sched_setaffinity(0, avail[local * per:(local + 1) * per] or avail)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -361,13 +371,7 @@ def run_gpu(args):
         st = _lib.lib.aoslo_set_wait_policy(local, int(policy))       # before the context is created
         if st != 0:
             sys.stderr.write("aoslo_set_wait_policy failed: %s\n" % _lib.lib.aoslo_last_cuda_error().decode())
-    # every rank keeps its lane threads on its own slice of the host cores (set before the threads exist): 8 ranks x
-    # 8 lane threads on 32 cores otherwise migrate across all of them -- measured on the 8-GPU box: 6 689 -> 6 796
-    # runs/s resident, 5 229 -> 6 014 end to end.  AOSLO_BENCH_AFFINITY=0 turns it off.
-    if world > 1 and os.environ.get("AOSLO_BENCH_AFFINITY", "1") != "0" and hasattr(os, "sched_setaffinity"):
-        avail = sorted(os.sched_getaffinity(0))
-        per = max(1, len(avail) // world)
-        os.sched_setaffinity(0, avail[local * per:(local + 1) * per] or avail)
+    pin_rank_to_core_slice(local, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -669,6 +673,7 @@ def run_units(args):
             print(json.dumps({"impl": "reference", "unavailable": "the CPU arm is defined for the run workloads "
                               "(default / cfg2 / cfg3); cfg4 / cfg5 are multiples of them"}))
         return 0
+    pin_rank_to_core_slice(local, world)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
