@@ -170,7 +170,6 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_counters, 32));
     if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_pinned, sizeof(int) * 32, cudaHostAllocDefault) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
-    A(alloc_cell_list(c->cl_p, H, W, cap, shift));
     A(alloc_cell_list(c->cl_g, H, W, gcap, shift));
     {
         int lshift = 0;                              // 0 = density adaptive
@@ -231,7 +230,10 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     if (st == AOSLO_OK && cudaHostAlloc((void**)&c->h_record, sizeof(aoslo_metrics_record), cudaHostAllocDefault) != cudaSuccess)
         st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_lut, 64 * 64));
-    A(dmalloc(&c->d_lut_packed, 12288));         // >= grav_table_words(63): rank table of the gravity gather
+    A(dmalloc(&c->d_lut_radial, 512));           // >= 2 * 15 * 15 + 1
+    A(dmalloc(&c->d_lut_flag, 1));
+    A(gravity_init());
+    A(dmalloc(&c->d_occ, (size_t)H * ((W + 31) / 32 + 2) + 4));   // + 4: the clear kernel stores whole uint4
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
     c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)
@@ -258,13 +260,13 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (!c) return AOSLO_OK;
     cudaSetDevice(c->device);
     cudaFree(c->d_status); cudaFree(c->d_counters); cudaFreeHost(c->h_pinned);
-    free_cell_list(c->cl_p); free_cell_list(c->cl_g);
+    free_cell_list(c->cl_g);
     cudaFree(c->lk_p.head); cudaFree(c->lk_p.next); cudaFree(c->d_pos_tmp); cudaFree(c->d_active); cudaFree(c->d_ns_list);
     cudaFree(c->d_knn_idx); cudaFree(c->d_knn_d2); cudaFree(c->d_block_sums); cudaFree(c->d_scan_ticket);
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
-    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_packed); cudaFree(c->d_field); cudaFree(c->d_win);
+    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_field); cudaFree(c->d_win);
     kd_free(c->kd); kd_free(c->kd2); cudaFreeHost(c->kd_stage);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -411,11 +413,11 @@ extern "C" int aoslo_dist_lut(aoslo_ctx* ctx, void* stream, int rfs, double mu, 
 
 extern "C" int aoslo_gravity_field(aoslo_ctx* ctx, void* stream, const double* d_particles, int n,
                                    const double* d_lut, int rfs, int H, int W, double* d_field) {
-    if (!ctx || !d_particles || !d_lut || !d_field || H != ctx->H || W != ctx->W || n < 0) return AOSLO_ERR_INVALID;
+    if (!ctx || (!d_particles && n > 0) || !d_lut || !d_field || H != ctx->H || W != ctx->W || n < 0)
+        return AOSLO_ERR_INVALID;
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     cudaStream_t s = (cudaStream_t)stream;
-    AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, d_particles, n, nullptr));
-    return stage_gravity(ctx, s, d_lut, rfs, H, W, d_field, false);
+    return stage_gravity(ctx, s, d_particles, n, nullptr, d_lut, rfs, H, W, d_field, false);
 }
 
 extern "C" int aoslo_add_particles(aoslo_ctx* ctx, void* stream, const double* d_field, int H, int W, int bx, int by,
@@ -745,8 +747,8 @@ int enqueue_resample(RunPlan& P, cudaStream_t q, bool first) {
     const int bound = c->cap;
     if (!first) AOSLO_TRY(stage_compact(c, q, bound, P.cnt0, P.cnt1, P.hint));
     AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], bound, 1, P.cnt0));
-    AOSLO_TRY(build_cell_list(c, q, c->cl_p, c->d_pos[0], bound, P.cnt0));
-    AOSLO_TRY(stage_gravity(c, q, c->d_lut, cfg->reception_field_size, cfg->H, cfg->W, c->d_field, !first));
+    AOSLO_TRY(stage_gravity(c, q, c->d_pos[0], bound, P.cnt0, c->d_lut, cfg->reception_field_size, cfg->H, cfg->W,
+                            c->d_field, !first));
     // the spine kernel reads the base count before it writes the total, so both may be the same scalar
     AOSLO_TRY(stage_add(c, q, c->d_field, cfg->H, cfg->W, cfg->bx, cfg->by, cfg->particle_call_window,
                         cfg->particle_call_threshold, c->d_pos[0], c->d_stable[0], bound, P.cnt0, c->cap, P.cnt0,
@@ -1154,12 +1156,12 @@ int run_sklearn(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const v
     // ---- all stable, gravity field, adding (:130-152)
     AOSLO_TRY(stage_lut(ctx, s, cfg->reception_field_size, cfg->mu_dist_func, cfg->sigma_dist_func,
                         cfg->lambda_dist_func, ctx->d_lut));
-    bool packed_ready = false;                       // rank-packed LUT: derived once per run
+    bool lut_ready = false;                          // radial table / flag of the LUT: derived once per run
     auto resample = [&]() -> int {
         AOSLO_TRY(stage_set_stable(ctx, s, ctx->d_stable[cur], n, 1, nullptr));
-        AOSLO_TRY(build_cell_list(ctx, s, ctx->cl_p, ctx->d_pos[cur], n, nullptr));
-        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_lut, cfg->reception_field_size, H, W, ctx->d_field, packed_ready));
-        packed_ready = true;
+        AOSLO_TRY(stage_gravity(ctx, s, ctx->d_pos[cur], n, nullptr, ctx->d_lut, cfg->reception_field_size, H, W,
+                                ctx->d_field, lut_ready));
+        lut_ready = true;
         AOSLO_TRY(stage_add(ctx, s, ctx->d_field, H, W, cfg->bx, cfg->by, cfg->particle_call_window,
                             cfg->particle_call_threshold, ctx->d_pos[cur], ctx->d_stable[cur], n, nullptr, cap,
                             d_cnt[cur]));

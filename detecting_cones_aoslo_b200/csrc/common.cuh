@@ -175,7 +175,6 @@ struct aoslo_ctx {
     int* d_status = nullptr;
     int* d_counters = nullptr;        // [32] device scalars (counts, round counters)
     int* h_pinned = nullptr;          // [32] pinned readback
-    aoslo::CellList cl_p;             // particles
     aoslo::CellList cl_g;             // ground truth
     aoslo::CellLinks lk_p;            // particles (kNN)
     double* d_pos_tmp = nullptr;      // [cap*2] moved positions (Jacobi move writes here)
@@ -230,7 +229,9 @@ struct aoslo_ctx {
     aoslo_metrics_record* h_records = nullptr;  // pinned
     int max_records = 0;
     double* d_lut = nullptr;          // [64*64]
-    uint32_t* d_lut_packed = nullptr; // [12288] 16-bit rank table of the gravity gather (lut_pack16_kernel)
+    double* d_lut_radial = nullptr;   // [2*15*15+1] LUT entry by squared distance (lut_radial_kernel)
+    int* d_lut_flag = nullptr;        // 1: the LUT is radial and non-increasing (nearest-particle gravity kernel)
+    uint32_t* d_occ = nullptr;        // [H][(W+31)/32 + 2] occupancy bitmap of the particles' pixels
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd, kd2;         // two cached trees (sklearn-order tie mode): typically particles and GT
@@ -398,8 +399,9 @@ int stage_seed(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int 
                double* d_pos, int cap, int* d_n_out, const double* d_thr = nullptr, bool clamp_count = false);
 int stage_lut(aoslo_ctx*, cudaStream_t, int rfs, double mu, double sigma, double lam, double* d_lut,
               const RunParams* rp = nullptr);
-int stage_gravity(aoslo_ctx*, cudaStream_t, const double* d_lut, int rfs, int H, int W, double* d_field,
-                  bool packed_ready);
+int gravity_init();
+int stage_gravity(aoslo_ctx*, cudaStream_t, const double* d_pos, int n_host, const int* d_n, const double* d_lut,
+                  int rfs, int H, int W, double* d_field, bool lut_ready);
 int stage_add(aoslo_ctx*, cudaStream_t, const double* d_field, int H, int W, int bx, int by, int window, double thr,
               double* d_pos, uint8_t* d_stable, int n_host, const int* d_n, int cap, int* d_n_out,
               const double* d_thr = nullptr, bool clamp_count = false);

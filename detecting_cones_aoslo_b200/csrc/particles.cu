@@ -918,99 +918,231 @@ __global__ void dist_lut_kernel(int rfs, double mu, double sigma, double lam, do
 }
 
 // =======================================================================================
-// gravity field (utils.py:310-333) as a per-pixel gather over the cell list
+// gravity field (utils.py:310-333) from an occupancy bitmap of the particles' pixels
 // =======================================================================================
-// field[y][x] = max(-0.48, max over particles p with |x-px|<=h, |y-py|<=h of T[y-py+h][x-px+h]).
-// The max of LUT ENTRIES is taken on their ranks (rank = number of strictly smaller entries, so an integer max
-// selects exactly the entry a float max would; ties have equal rank and equal value).  A thread owns kGravRows
-// consecutive rows of one column and keeps the running maxima of two rows per register as 16-bit ranks: sm_100a
-// has a per-halfword maximum (VIMNMX.U16x2), so one candidate particle updates all 16 rows with 8 LDS + 8 VIMNMX.
-// The rank table is laid out column major with kGravRows-1 zero rows above and below each LUT column, so a
-// candidate's 16 entries are 8 consecutive words and need no per-row range test; a second copy shifted by one
-// row serves the candidates whose first row is odd.  lut_pack16_kernel builds that layout once per LUT in global
-// memory ([2][rfs][ROWS] u16, then the index of one entry per rank), every CTA copies it with 128-bit loads.
-constexpr int kGravRows = 16;
-constexpr int kGravCols = 128;
+// field[y][x] = max(-0.48, max over particles p with |x-px|<=h, |y-py|<=h of LUT[y-py+h][x-px+h]), px = int(p[0]).
+// Only the pixel a particle sits on matters, so the particles are scattered into a bitmap (one bit per pixel, one
+// zero word on each side of a row) and a tile reads the (TY + 2h) x (128 + 2h) bits around it from shared memory.
+//
+// Nearest-particle path (gravity_nearest_kernel).  The reference's LUT is a function of the distance alone and, for
+// most parameters (all named configurations), non-increasing in it.  lut_radial_kernel checks both properties on
+// the LUT ENTRIES THEMSELVES -- bit-equal values for equal dx^2+dy^2, T[a] >= T[b] for consecutive attainable
+// a < b -- and then the maximum over the window is exactly the entry of the smallest squared distance: a
+// windowed squared-distance transform.  Row pass: the nearest set bit of a row within |dx| <= h is two bit scans
+// on the 2h+1 window bits.  Column pass: d2(y) = min over dy of r2(y+dy) + dy^2, two output rows per register as
+// 16-bit halves, one VIADDMNMX.U16x2 (min(a + imm, c) per halfword) per (source row, output row pair).
+// ~40 instructions per pixel instead of the 190 of the former per-candidate gather over a sorted cell list.
+//
+// General path (gravity_bits_kernel): any other LUT (a caller's table, sigma_dist_func < 0.83 where the pit
+// function jumps upwards at mu, h > 15).  Every set bit of a window row is a candidate; its TY entries for the
+// thread's output rows are consecutive in a column-major copy of the LUT padded with -inf rows.
+// Both kernels are always launched; the device flag written by lut_radial_kernel decides which one works.
+constexpr int kGravCols = 128;         // columns per tile = threads per CTA
+constexpr int kGravOccWords = 8;       // staged words per bitmap row: 6 cover [x0-32, x0+160), 2 zero words
+constexpr int kNearRows = 32;          // output rows per thread, nearest-particle path
+constexpr int kBitsRows = 16;          // output rows per thread, general path
+constexpr int kNearMaxH = 15;          // 2h+1 <= 31 window bits: one 32-bit funnel shift
+constexpr unsigned kD2Inf = 0x4000u;   // "no particle" in a 16-bit half; kD2Inf + kD2Inf does not wrap
 
-__host__ __device__ inline int grav_rows_stride(int rfs) {       // even, ROWS / 2 odd (bank spread), >= rows + 1
-    int r = rfs + 2 * (kGravRows - 1) + 1;
-    r += r & 1;
-    if (((r / 2) & 1) == 0) r += 2;
-    return r;
-}
-__host__ __device__ inline int grav_table_words(int rfs) {       // u32 words of the packed table (16-byte multiple)
-    int u16s = 2 * rfs * grav_rows_stride(rfs) + rfs * rfs + 1;
-    return ((u16s + 1) / 2 + 3) & ~3;
+__host__ __device__ inline int occ_words_per_row(int W) { return (W + 31) / 32 + 2; }
+
+__global__ void __launch_bounds__(kThreads) occ_clear_kernel(uint4* occ, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        occ[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// table must be zeroed before the launch
-__global__ void lut_pack16_kernel(const double* __restrict__ lut, int rfs, uint16_t* table) {
-    const int n = rfs * rfs, ROWS = grav_rows_stride(rfs), pad = kGravRows - 1;
-    uint16_t* idx_by_rank = table + 2 * rfs * ROWS;
+// positions must lie in [0, W) x [0, H): anything else is reported (the reference would raise IndexError or
+// silently wrap a negative index) and leaves no bit
+__global__ void __launch_bounds__(kThreads) occ_scatter_kernel(const double2* __restrict__ pos, int n_host,
+                                                               const int* d_n, int W, int H, int wpr, uint32_t* occ,
+                                                               int* status) {
+    int n = d_n ? *d_n : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double v = lut[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) rank += (lut[j] < v) ? 1 : 0;
-        const int ry = i / rfs, cx = i - ry * rfs;
-        const uint16_t rk = (uint16_t)(rank + 1);
-        table[cx * ROWS + ry + pad] = rk;                                  // copy A: padded row r at index r
-        table[rfs * ROWS + cx * ROWS + ry + pad - 1] = rk;                 // copy B: padded row r at index r - 1
-        idx_by_rank[rank + 1] = (uint16_t)i;                               // ties: equal values, any of them
+        double2 p = pos[i];
+        if (p.x != p.x || p.y != p.y) { atomicOr(status, AOSLO_DEV_NAN); continue; }
+        if (!(p.x >= 0.0) || !(p.y >= 0.0) || p.x >= (double)W || p.y >= (double)H) {
+            atomicOr(status, AOSLO_DEV_ESCAPED);
+            continue;
+        }
+        const int ix = (int)p.x, iy = (int)p.y;        // int(particle[0]) truncation
+        atomicOr(&occ[(size_t)iy * wpr + 1 + (ix >> 5)], 1u << (ix & 31));
     }
 }
 
-__global__ void __launch_bounds__(kGravCols) gravity_field_kernel(CellView cl, const double* __restrict__ lut,
-                                                                 const uint32_t* __restrict__ table, int rfs,
-                                                                 int H, int W, double* field) {
-    extern __shared__ __align__(16) uint32_t s_tab[];
-    const int h = rfs / 2;
-    const int pad = kGravRows - 1;
-    const int ROWS = grav_rows_stride(rfs);
-    {
-        const int nq = grav_table_words(rfs) / 4;
-        const uint4* src = reinterpret_cast<const uint4*>(table);
-        uint4* dst = reinterpret_cast<uint4*>(s_tab);
-        for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = __ldg(src + i);
+// T[d2] = the LUT entry of squared distance d2 (d2 <= 2 h^2); *flag = 1 iff the LUT is radial and non-increasing
+// over the attainable d2 and h fits the 32-bit window of the nearest-particle kernel
+__global__ void __launch_bounds__(1024) lut_radial_kernel(const double* __restrict__ lut, int rfs, double* T,
+                                                          int* flag) {
+    constexpr int kMaxT = 2 * kNearMaxH * kNearMaxH + 1;
+    __shared__ unsigned long long s_bits[kMaxT];
+    __shared__ unsigned char s_has[kMaxT];
+    __shared__ int s_ok;
+    const int h = rfs / 2, n = rfs * rfs, nT = 2 * h * h + 1;
+    if (h < 1 || h > kNearMaxH || (rfs & 1) == 0) {
+        if (threadIdx.x == 0) *flag = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i < nT; i += blockDim.x) { s_bits[i] = 0ull; s_has[i] = 0; }
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ky = i / rfs, kx = i - ky * rfs;
+        const int d2 = (kx - h) * (kx - h) + (ky - h) * (ky - h);
+        s_has[d2] = 1;
+        s_bits[d2] = (unsigned long long)__double_as_longlong(lut[i]);   // racing writers: checked below
     }
     __syncthreads();
-    const uint16_t* s_idx = reinterpret_cast<const uint16_t*>(s_tab) + 2 * rfs * ROWS;
-    const int x = blockIdx.x * kGravCols + threadIdx.x;
-    const int y0 = blockIdx.y * kGravRows;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ky = i / rfs, kx = i - ky * rfs;
+        const int d2 = (kx - h) * (kx - h) + (ky - h) * (ky - h);
+        if (s_bits[d2] != (unsigned long long)__double_as_longlong(lut[i])) s_ok = 0;
+    }
+    for (int a = threadIdx.x; a < nT - 1; a += blockDim.x) {
+        if (!s_has[a]) continue;
+        int b = a + 1;
+        while (b < nT && !s_has[b]) ++b;
+        if (b < nT && !(__longlong_as_double((long long)s_bits[a]) >= __longlong_as_double((long long)s_bits[b])))
+            s_ok = 0;                                   // NaN entries fail here too
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nT; i += blockDim.x)
+        T[i] = s_has[i] ? __longlong_as_double((long long)s_bits[i]) : -0.48;
+    if (threadIdx.x == 0) *flag = s_ok;
+}
+
+// the bitmap rows y0-h .. y0+rows-1+h of the tile, words (x0>>5)-1 .. (x0>>5)+4 of each (bit 0 of the staged row
+// is pixel x0-32); rows / words outside the image are zero
+__device__ __forceinline__ void stage_occ_rows(const uint32_t* __restrict__ occ, int wpr, int H, int x0, int y_first,
+                                               int rows, uint32_t* s_occ) {
+    const int gw0 = x0 >> 5;                            // padded row: word (x0>>5)-1 lives at index x0>>5
+    for (int i = threadIdx.x; i < rows * kGravOccWords; i += blockDim.x) {
+        const int r = i / kGravOccWords, w = i - r * kGravOccWords;
+        const int yy = y_first + r, gw = gw0 + w;
+        uint32_t v = 0u;
+        if (w < 6 && yy >= 0 && yy < H && gw < wpr) v = __ldg(occ + (size_t)yy * wpr + gw);
+        s_occ[i] = v;
+    }
+}
+
+template <int HH>
+__global__ void __launch_bounds__(kGravCols) gravity_nearest_kernel(const uint32_t* __restrict__ occ, int wpr,
+                                                                   const double* __restrict__ T,
+                                                                   const int* __restrict__ flag, int H, int W,
+                                                                   double* __restrict__ field) {
+    constexpr int TY = kNearRows, SR = TY + 2 * HH, NT = 2 * HH * HH + 1;
+    __shared__ uint32_t s_occ[SR * kGravOccWords];
+    __shared__ double s_T[NT + 1];
+    if (*flag == 0) return;
+    const int x0 = blockIdx.x * kGravCols, y0 = blockIdx.y * TY;
+    stage_occ_rows(occ, wpr, H, x0, y0 - HH, SR, s_occ);
+    for (int i = threadIdx.x; i <= NT; i += blockDim.x) {
+        const double t = (i < NT) ? T[i] : -0.48;
+        s_T[i] = (t > -0.48) ? t : -0.48;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
     if (x >= W) return;
-    uint32_t best[kGravRows / 2];
+    uint32_t best[TY / 2];
 #pragma unroll
-    for (int r = 0; r < kGravRows / 2; ++r) best[r] = 0u;
-    const int cxa = max(x - h, 0) >> cl.shift, cxb = min(min(x + h, W - 1) >> cl.shift, cl.gw - 1);
-    const int cya = max(y0 - h, 0) >> cl.shift;
-    const int cyb = min(min(y0 + kGravRows - 1 + h, H - 1) >> cl.shift, cl.gh - 1);
-    const int copy_b = rfs * ROWS;                    // u16 offset of the shifted copy
-    // (ncu r02: issue slots 71 % busy, 25.5 M warp instructions, LSU pipe 41 % -- the kernel is issue bound; fetching the
-    // cell-row bounds ahead and prefetching the next candidate's position was measured: 35 -> 39 us, reverted)
-    for (int cy = cya; cy <= cyb; ++cy) {
-        int p0 = cl.start[cy * cl.gw + cxa], p1 = cl.start[cy * cl.gw + cxb + 1];
-        for (int p = p0; p < p1; ++p) {
-            double2 pp = cl.sorted_pos[p];
-            int dx = x - (int)pp.x;                    // int(particle[0]) truncation
-            int dyb = y0 - (int)pp.y + h + pad;        // padded LUT row of this thread's row 0
-            if (dx < -h || dx > h || dyb < 0 || dyb > 2 * h + pad) continue;
-            // u16 index of the candidate's first entry: even by construction (ROWS even, odd dyb -> copy B at dyb-1)
-            const int e = (dx + h) * ROWS + (dyb & ~1) + (dyb & 1) * copy_b;
-            const uint32_t* col = s_tab + (e >> 1);
+    for (int j = 0; j < TY / 2; ++j) best[j] = kD2Inf * 0x10001u;
+    const int b = threadIdx.x + 32 - HH;               // staged bit of pixel x - HH
+    const uint32_t* row = s_occ + (b >> 5);
+    const int sh = b & 31;
 #pragma unroll
-            for (int r = 0; r < kGravRows / 2; ++r) best[r] = __vmaxu2(best[r], col[r]);
+    for (int s = 0; s < SR; ++s) {
+        // window bits 0 .. 2 HH = pixels x-HH .. x+HH of source row y0 - HH + s
+        const uint32_t w = __funnelshift_r(row[s * kGravOccWords], row[s * kGravOccWords + 1], sh);
+        const uint32_t wr = (w >> HH) & ((1u << (HH + 1)) - 1u);       // dx = 0 .. HH at bits 0 .. HH
+        const uint32_t wl = w & ((1u << HH) - 1u);                     // dx = -HH .. -1 at bits 0 .. HH-1
+        const unsigned rr = (unsigned)(__ffs((int)wr) - 1);            // none: 0xffffffff
+        const unsigned rl = (unsigned)(HH - 31 + __clz((int)wl));      // none: HH + 1
+        const unsigned r = rr < rl ? rr : rl;
+        const uint32_t r2 = (r <= (unsigned)HH) ? r * r : kD2Inf;
+        const uint32_t v = r2 * 0x10001u;
+#pragma unroll
+        for (int j = 0; j < TY / 2; ++j) {
+            // low half: output row y0 + 2j, high half: y0 + 2j + 1
+            const int da = s - HH - 2 * j, db = da - 1;
+            const bool ina = da >= -HH && da <= HH, inb = db >= -HH && db <= HH;
+            if (ina || inb) {
+                const uint32_t c = (ina ? (uint32_t)(da * da) : kD2Inf) | ((inb ? (uint32_t)(db * db) : kD2Inf) << 16);
+                best[j] = __viaddmin_u16x2(v, c, best[j]);
+            }
+        }
+    }
+    // s_T[NT] = -0.48 serves every "no particle in the window" value (>= kD2Inf)
+    double* out = field + (size_t)y0 * W + x;
+    if (y0 + TY <= H) {
+#pragma unroll
+        for (int r = 0; r < TY; ++r) {
+            const uint32_t d2 = (best[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+            *out = s_T[d2 < (uint32_t)NT ? d2 : (uint32_t)NT];
+            out += W;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < TY; ++r) {
+            if (y0 + r < H) {
+                const uint32_t d2 = (best[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+                out[(size_t)r * W] = s_T[d2 < (uint32_t)NT ? d2 : (uint32_t)NT];
+            }
+        }
+    }
+}
+
+__host__ __device__ inline int grav_bits_rows_stride(int rfs) { return rfs + 2 * (kBitsRows - 1); }   // odd
+inline size_t grav_bits_smem(int rfs) {
+    return sizeof(double) * (size_t)rfs * grav_bits_rows_stride(rfs) +
+           sizeof(uint32_t) * (size_t)(kBitsRows + rfs - 1) * kGravOccWords;
+}
+
+__global__ void __launch_bounds__(kGravCols) gravity_bits_kernel(const uint32_t* __restrict__ occ, int wpr,
+                                                                const double* __restrict__ lut, int rfs,
+                                                                const int* __restrict__ flag, int H, int W,
+                                                                double* __restrict__ field) {
+    constexpr int TY = kBitsRows, PAD = kBitsRows - 1;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    if (*flag != 0) return;
+    const int h = rfs / 2, ROWS = grav_bits_rows_stride(rfs), SR = TY + 2 * h;
+    double* s_tab = reinterpret_cast<double*>(s_raw);                  // [rfs][ROWS]: column kx, padded row PAD + ky
+    uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_tab + rfs * ROWS);
+    const int x0 = blockIdx.x * kGravCols, y0 = blockIdx.y * TY;
+    stage_occ_rows(occ, wpr, H, x0, y0 - h, SR, s_occ);
+    for (int i = threadIdx.x; i < rfs * ROWS; i += blockDim.x) {
+        const int kx = i / ROWS, ky = i - kx * ROWS - PAD;
+        s_tab[i] = (ky >= 0 && ky < rfs) ? lut[ky * rfs + kx] : -INFINITY;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= W) return;
+    double best[TY];
+#pragma unroll
+    for (int r = 0; r < TY; ++r) best[r] = -INFINITY;
+    const int b = threadIdx.x + 32 - h;                // staged bit of pixel x - h
+    const uint32_t* row = s_occ + (b >> 5);
+    const int sh = b & 31;
+    const unsigned long long mask = (1ull << (2 * h + 1)) - 1ull;      // 2h+1 <= 63
+    for (int s = 0; s < SR; ++s) {
+        const uint32_t w0 = row[s * kGravOccWords], w1 = row[s * kGravOccWords + 1], w2 = row[s * kGravOccWords + 2];
+        unsigned long long win = ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+        win &= mask;
+        // a particle at bit q sits on pixel x + q - h: kx = x - px + h = 2h - q; ky of output row r = 2h - s + r
+        const double* base = s_tab + PAD + 2 * h - s;
+        while (win) {
+            const int q = __ffsll((long long)win) - 1;
+            win &= win - 1ull;
+            const double* col = base + (2 * h - q) * ROWS;
+#pragma unroll
+            for (int r = 0; r < TY; ++r) {
+                const double t = col[r];
+                best[r] = (t > best[r]) ? t : best[r];
+            }
         }
     }
 #pragma unroll
-    for (int r = 0; r < kGravRows; ++r) {
-        int y = y0 + r;
-        if (y >= H) break;
-        const uint32_t rk = (best[r >> 1] >> (16 * (r & 1))) & 0xffffu;
-        double v = -0.48;
-        if (rk) {
-            double t = lut[s_idx[rk]];
-            v = (t > v) ? t : v;
-        }
-        field[(size_t)y * W + x] = v;
+    for (int r = 0; r < TY; ++r) {
+        const int y = y0 + r;
+        if (y < H) field[(size_t)y * W + x] = (best[r] > -0.48) ? best[r] : -0.48;
     }
 }
 
@@ -2017,22 +2149,54 @@ int stage_lut(aoslo_ctx*, cudaStream_t s, int rfs, double mu, double sigma, doub
     return AOSLO_OK;
 }
 
-// requires ctx->cl_p built on the particles; d_packed = rank-packed LUT (nullptr: derive it here)
-int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_lut, int rfs, int H, int W, double* d_field,
-                  bool packed_ready) {
+// once per context (device): 63 x 93 doubles + the bitmap rows of the general kernel exceed the 48 KB default
+int gravity_init() {
+    AOSLO_CUDA(cudaFuncSetAttribute(gravity_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)grav_bits_smem(63)));
+    return AOSLO_OK;
+}
+
+template <int HH>
+static void launch_nearest(dim3 grid, cudaStream_t s, const aoslo_ctx* ctx, int wpr, int H, int W, double* d_field) {
+    gravity_nearest_kernel<HH><<<grid, kGravCols, 0, s>>>(ctx->d_occ, wpr, ctx->d_lut_radial, ctx->d_lut_flag, H, W,
+                                                          d_field);
+}
+
+// lut_ready: the radial table / flag of this LUT are already in the context (derived once per run)
+int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, int n_host, const int* d_n,
+                  const double* d_lut, int rfs, int H, int W, double* d_field, bool lut_ready) {
     if (rfs < 1 || rfs > 64) return AOSLO_ERR_UNSUPPORTED;
     if ((rfs & 1) == 0) return AOSLO_ERR_INVALID;     // even rfs: shape mismatch in the reference (utils.py:329)
-    if (ctx->cl_p.shift < 1) return AOSLO_ERR_UNSUPPORTED;
-    const size_t tab_bytes = sizeof(uint32_t) * grav_table_words(rfs);
-    if (!packed_ready) {
-        AOSLO_CUDA(cudaMemsetAsync(ctx->d_lut_packed, 0, tab_bytes, s));
-        lut_pack16_kernel<<<(rfs * rfs + 127) / 128, 128, 0, s>>>(d_lut, rfs, reinterpret_cast<uint16_t*>(ctx->d_lut_packed));
+    if (H != ctx->H || W != ctx->W) return AOSLO_ERR_INVALID;
+    const int h = rfs / 2, wpr = occ_words_per_row(W);
+    if (!lut_ready) {
+        lut_radial_kernel<<<1, 1024, 0, s>>>(d_lut, rfs, ctx->d_lut_radial, ctx->d_lut_flag);
         AOSLO_LAUNCH_CHECK();
     }
-    dim3 grid((W + kGravCols - 1) / kGravCols, (H + kGravRows - 1) / kGravRows);
-    gravity_field_kernel<<<grid, kGravCols, tab_bytes, s>>>(view_of(ctx->cl_p), d_lut, ctx->d_lut_packed, rfs, H, W,
-                                                            d_field);
+    const int n16 = (int)(((size_t)H * wpr + 3) / 4);
+    occ_clear_kernel<<<ctx->num_sms, kThreads, 0, s>>>(reinterpret_cast<uint4*>(ctx->d_occ), n16);
     AOSLO_LAUNCH_CHECK();
+    occ_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, W, H, wpr, ctx->d_occ,
+                                                    ctx->d_status);
+    AOSLO_LAUNCH_CHECK();
+    if (h >= 1 && h <= kNearMaxH) {                   // otherwise the flag is 0 and the general kernel works
+        dim3 grid((W + kGravCols - 1) / kGravCols, (H + kNearRows - 1) / kNearRows);
+        switch (h) {
+#define AOSLO_NEAR_CASE(HH) case HH: launch_nearest<HH>(grid, s, ctx, wpr, H, W, d_field); break;
+            AOSLO_NEAR_CASE(1) AOSLO_NEAR_CASE(2) AOSLO_NEAR_CASE(3) AOSLO_NEAR_CASE(4) AOSLO_NEAR_CASE(5)
+            AOSLO_NEAR_CASE(6) AOSLO_NEAR_CASE(7) AOSLO_NEAR_CASE(8) AOSLO_NEAR_CASE(9) AOSLO_NEAR_CASE(10)
+            AOSLO_NEAR_CASE(11) AOSLO_NEAR_CASE(12) AOSLO_NEAR_CASE(13) AOSLO_NEAR_CASE(14) AOSLO_NEAR_CASE(15)
+#undef AOSLO_NEAR_CASE
+            default: break;
+        }
+        AOSLO_LAUNCH_CHECK();
+    }
+    {
+        dim3 grid((W + kGravCols - 1) / kGravCols, (H + kBitsRows - 1) / kBitsRows);
+        gravity_bits_kernel<<<grid, kGravCols, grav_bits_smem(rfs), s>>>(ctx->d_occ, wpr, d_lut, rfs, ctx->d_lut_flag,
+                                                                         H, W, d_field);
+        AOSLO_LAUNCH_CHECK();
+    }
     return AOSLO_OK;
 }
 

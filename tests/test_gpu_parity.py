@@ -364,6 +364,33 @@ def test_lut_gravity_adding_match_oracle(zoo_field):
                                    configs.variant(cfg, particle_call_window=5.5))
 
 
+@pytest.mark.parametrize("rfs", [1, 3, 5, 9, 19, 21, 31, 33, 47, 63])
+@pytest.mark.parametrize("shape", [(61, 97), (40, 129), (130, 260)])
+def test_gravity_field_kernels_any_lut(rfs, shape):
+    """Both gravity kernels against the oracle, bit exact: the reference's LUT (radial and non-increasing ->
+    nearest-particle kernel for rfs <= 31), the same with sigma < 0.83 (the pit function jumps upwards at mu ->
+    general kernel), a random table (general kernel; asymmetric, so the kx / ky orientation matters), a constant
+    table (ties) and one below the -0.48 floor; particles on the borders, clipped windows, fractional positions."""
+    H, W = shape
+    rng = np.random.default_rng(rfs * 1000 + H)
+    n = max(4, H * W // 35)
+    p = np.stack([rng.integers(0, W, n), rng.integers(0, H, n)], axis=1).astype(np.float64)
+    p = np.vstack([p, [[0., 0.], [W - 1., H - 1.], [0., H - 1.], [W - 1., 0.], [3.7, H - 1.2], [W - 0.5, 2.9]]])
+    cfg = configs.variant(configs.zoo_config(), reception_field_size=rfs)
+    luts = [orc.get_precomputed_dist_func(cfg),
+            orc.get_precomputed_dist_func(configs.variant(cfg, sigma_dist_func=0.5, mu_dist_func=5.6)),
+            rng.normal(size=(rfs, rfs)),
+            np.full((rfs, rfs), 0.25),
+            np.full((rfs, rfs), -0.75) + rng.random((rfs, rfs)) * 0.1]
+    for lut in luts:
+        np.testing.assert_array_equal(gpu_utils.calc_gravity_field_optim(lut, shape, p, cfg),
+                                      orc.calc_gravity_field_optim(lut, shape, p, cfg))
+    # no particle at all, and a single one
+    for q in (np.zeros((0, 2)), np.array([[W // 2 + 0.0, H // 2 + 0.0]])):
+        np.testing.assert_array_equal(gpu_utils.calc_gravity_field_optim(luts[0], shape, q, cfg),
+                                      orc.calc_gravity_field_optim(luts[0], shape, q, cfg))
+
+
 # ----------------------------------------------------------------------------------- force / move
 @pytest.mark.parametrize("tie_mode", ["canonical", "sklearn"])
 @pytest.mark.parametrize("k", [1, 3, 6])
@@ -525,6 +552,10 @@ def test_deferred_gt_shift_is_the_reference_side_effect():
     dict(gradient_type="sobel", lambda_blob=1.),
     dict(dist_n_neighbours=6, lambda_blob=1., lambda_dist=0.1),
     dict(early_stop=False, epoch_num=9, lambda_blob=1., lambda_dist=0.1, dist_n_neighbours=3),
+    # pit function jumps upwards at mu (sigma < 0.83): non-monotone LUT -> the general gravity kernel inside the run
+    dict(sigma_dist_func=0.5, mu_dist_func=5.6, lambda_blob=1., lambda_dist=0.1, dist_n_neighbours=3),
+    dict(reception_field_size=33, lambda_blob=1., lambda_dist=0.1),      # h = 16: beyond the 32-bit window path
+    dict(reception_field_size=9, particle_call_window=7, lambda_blob=1., lambda_dist=0.1),
 ])
 @pytest.mark.parametrize("tie_mode", ["sklearn", "canonical"])
 def test_find_blobs_fused_branches_match_oracle(over, tie_mode):
