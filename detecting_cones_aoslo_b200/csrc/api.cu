@@ -234,6 +234,8 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_lut_flag, 1));
     A(gravity_init());
     A(dmalloc(&c->d_occ, (size_t)H * ((W + 31) / 32 + 2) + 4));   // + 4: the clear kernel stores whole uint4
+    A(dmalloc(&c->d_occ_gt, (size_t)H * ((W + 31) / 32 + 2) + 4));
+    A(dmalloc(&c->d_occ_ok, 2));
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
     c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)
@@ -266,7 +268,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
-    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_field); cudaFree(c->d_win);
+    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_occ_gt); cudaFree(c->d_occ_ok); cudaFree(c->d_field); cudaFree(c->d_win);
     kd_free(c->kd); kd_free(c->kd2); cudaFreeHost(c->kd_stage);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -842,6 +844,7 @@ int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
                         cfg->lambda_dist_func, c->d_lut, rp));
     AOSLO_TRY(enqueue_resample(P, q, true));
     AOSLO_TRY(build_cell_list(c, q, c->cl_g, P.d_gt, P.n_gt, &rp->n_gt));
+    AOSLO_TRY(stage_gt_bitmap(c, q, P.d_gt, P.n_gt, &rp->n_gt));
     // ---- the epoch loop (:173-382)
     if (!P.dynamic_loop && graph) {
         // unrolled: the branches are static, no control kernels

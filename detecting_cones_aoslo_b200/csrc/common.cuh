@@ -232,6 +232,8 @@ struct aoslo_ctx {
     double* d_lut_radial = nullptr;   // [2*15*15+1] LUT entry by squared distance (lut_radial_kernel)
     int* d_lut_flag = nullptr;        // 1: the LUT is radial and non-increasing (nearest-particle gravity kernel)
     uint32_t* d_occ = nullptr;        // [H][(W+31)/32 + 2] occupancy bitmap of the particles' pixels
+    uint32_t* d_occ_gt = nullptr;     // same for the ground truth of the current run (stage_gt_bitmap)
+    int* d_occ_ok = nullptr;          // [2] particles / GT: every point is an in-image integer pixel
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd, kd2;         // two cached trees (sklearn-order tie mode): typically particles and GT
@@ -422,6 +424,7 @@ int stage_dual_step(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, int k
                     double p2, const void* d_grad, const void* d_Rb, int field_dtype, int H, int W, double lb, double ld,
                     int step_mode, double del_thr, const RunParams* rp, int phases);
 int stage_compact(aoslo_ctx*, cudaStream_t, int n_bound, int* d_n, int* d_n_scratch, int scan_hint);
+int stage_gt_bitmap(aoslo_ctx*, cudaStream_t, const double* d_gt, int n_gt, const int* d_n_gt);
 int stage_dual_metrics(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_n, const double* d_gt, int n_gt,
                        const void* d_Rb, int field_dtype, int H, int W, int bx, int by, int iteration,
                        aoslo_metrics_record* d_rec, const int* d_n_gt, int* d_rec_idx, const int* d_iteration);

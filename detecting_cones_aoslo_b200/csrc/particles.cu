@@ -946,27 +946,66 @@ constexpr unsigned kD2Inf = 0x4000u;   // "no particle" in a 16-bit half; kD2Inf
 
 __host__ __device__ inline int occ_words_per_row(int W) { return (W + 31) / 32 + 2; }
 
-__global__ void __launch_bounds__(kThreads) occ_clear_kernel(uint4* occ, int n16) {
+// `ok` (optional): set to 1 here; the scatter that follows clears it when a point is not an in-image integer pixel
+__global__ void __launch_bounds__(kThreads) occ_clear_kernel(uint4* occ, int n16, int* ok) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
         occ[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok && blockIdx.x == 0 && threadIdx.x == 0) *ok = 1;
 }
 
-// positions must lie in [0, W) x [0, H): anything else is reported (the reference would raise IndexError or
-// silently wrap a negative index) and leaves no bit
-__global__ void __launch_bounds__(kThreads) occ_scatter_kernel(const double2* __restrict__ pos, int n_host,
+// Gravity use (ok == nullptr): positions must lie in [0, W) x [0, H); anything else is reported (the reference
+// would raise IndexError or silently wrap a negative index) and leaves no bit; the pixel is int(particle[0]).
+// Nearest-distance use (ok != nullptr, metrics): the bitmap answers distance queries only if every point IS an
+// integer pixel inside the image; otherwise *ok = 0 and the caller keeps to its cell-list search.  Tombstones
+// (del[i] != 0) are skipped.
+__global__ void __launch_bounds__(kThreads) occ_scatter_kernel(const double2* __restrict__ pos,
+                                                               const uint8_t* __restrict__ del, int n_host,
                                                                const int* d_n, int W, int H, int wpr, uint32_t* occ,
-                                                               int* status) {
+                                                               int* status, int* ok) {
     int n = d_n ? *d_n : n_host;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (del && del[i]) continue;
         double2 p = pos[i];
-        if (p.x != p.x || p.y != p.y) { atomicOr(status, AOSLO_DEV_NAN); continue; }
-        if (!(p.x >= 0.0) || !(p.y >= 0.0) || p.x >= (double)W || p.y >= (double)H) {
-            atomicOr(status, AOSLO_DEV_ESCAPED);
+        const bool nan = p.x != p.x || p.y != p.y;
+        const bool out = !(p.x >= 0.0) || !(p.y >= 0.0) || p.x >= (double)W || p.y >= (double)H;
+        if (nan || out) {
+            if (ok) *ok = 0;
+            else atomicOr(status, nan ? AOSLO_DEV_NAN : AOSLO_DEV_ESCAPED);
             continue;
         }
         const int ix = (int)p.x, iy = (int)p.y;        // int(particle[0]) truncation
+        if (ok && ((double)ix != p.x || (double)iy != p.y)) *ok = 0;
         atomicOr(&occ[(size_t)iy * wpr + 1 + (ix >> 5)], 1u << (ix & 31));
     }
+}
+
+// Squared distance from the integer pixel (x, y) to the nearest set bit, searched in the rows y, y-+1, y-+2, ...
+// through the window |dx| <= 15; a result <= 15^2 is the global minimum (every point outside the window is farther
+// than 15), anything else returns -1 and the caller searches its cell list.  Distances between integer pixels are
+// exact in both searches, so sqrt() of either gives the same double.
+__device__ __forceinline__ int occ_nearest_d2(const uint32_t* __restrict__ occ, int wpr, int H, int x, int y) {
+    constexpr int R = 15;
+    const int b = x + 32 - R;                          // padded bit of pixel x - R
+    const int word = b >> 5, sh = b & 31;              // word + 1 <= wpr - 1 for every x < W
+    int best = 0x7fffffff;
+    for (int dy = 0; dy <= R; ++dy) {
+        if (dy * dy >= best) break;
+        for (int side = 0; side < (dy ? 2 : 1); ++side) {
+            const int yy = side ? y + dy : y - dy;
+            if (yy < 0 || yy >= H) continue;
+            const uint32_t* row = occ + (size_t)yy * wpr + word;
+            const uint32_t w = __funnelshift_r(__ldg(row), __ldg(row + 1), sh);      // bits 0..30 = x-15 .. x+15
+            const uint32_t wr = (w >> R) & 0xffffu, wl = w & 0x7fffu;
+            const unsigned rr = (unsigned)(__ffs((int)wr) - 1);
+            const unsigned rl = (unsigned)(R - 31 + __clz((int)wl));
+            const unsigned r = rr < rl ? rr : rl;
+            if (r <= (unsigned)R) {
+                const int c = (int)(r * r) + dy * dy;
+                best = c < best ? c : best;
+            }
+        }
+    }
+    return best <= R * R ? best : -1;
 }
 
 // T[d2] = the LUT entry of squared distance d2 (d2 <= 2 h^2); *flag = 1 iff the LUT is radial and non-increasing
@@ -1096,6 +1135,8 @@ inline size_t grav_bits_smem(int rfs) {
            sizeof(uint32_t) * (size_t)(kBitsRows + rfs - 1) * kGravOccWords;
 }
 
+constexpr int kBitsTilesPerCta = 4;    // row tiles per CTA of the general kernel (the LUT copy is staged once)
+
 __global__ void __launch_bounds__(kGravCols) gravity_bits_kernel(const uint32_t* __restrict__ occ, int wpr,
                                                                 const double* __restrict__ lut, int rfs,
                                                                 const int* __restrict__ flag, int H, int W,
@@ -1106,43 +1147,49 @@ __global__ void __launch_bounds__(kGravCols) gravity_bits_kernel(const uint32_t*
     const int h = rfs / 2, ROWS = grav_bits_rows_stride(rfs), SR = TY + 2 * h;
     double* s_tab = reinterpret_cast<double*>(s_raw);                  // [rfs][ROWS]: column kx, padded row PAD + ky
     uint32_t* s_occ = reinterpret_cast<uint32_t*>(s_tab + rfs * ROWS);
-    const int x0 = blockIdx.x * kGravCols, y0 = blockIdx.y * TY;
-    stage_occ_rows(occ, wpr, H, x0, y0 - h, SR, s_occ);
     for (int i = threadIdx.x; i < rfs * ROWS; i += blockDim.x) {
         const int kx = i / ROWS, ky = i - kx * ROWS - PAD;
         s_tab[i] = (ky >= 0 && ky < rfs) ? lut[ky * rfs + kx] : -INFINITY;
     }
-    __syncthreads();
-    const int x = x0 + threadIdx.x;
-    if (x >= W) return;
-    double best[TY];
-#pragma unroll
-    for (int r = 0; r < TY; ++r) best[r] = -INFINITY;
+    const int x0 = blockIdx.x * kGravCols, x = x0 + threadIdx.x;
     const int b = threadIdx.x + 32 - h;                // staged bit of pixel x - h
     const uint32_t* row = s_occ + (b >> 5);
     const int sh = b & 31;
     const unsigned long long mask = (1ull << (2 * h + 1)) - 1ull;      // 2h+1 <= 63
-    for (int s = 0; s < SR; ++s) {
-        const uint32_t w0 = row[s * kGravOccWords], w1 = row[s * kGravOccWords + 1], w2 = row[s * kGravOccWords + 2];
-        unsigned long long win = ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
-        win &= mask;
-        // a particle at bit q sits on pixel x + q - h: kx = x - px + h = 2h - q; ky of output row r = 2h - s + r
-        const double* base = s_tab + PAD + 2 * h - s;
-        while (win) {
-            const int q = __ffsll((long long)win) - 1;
-            win &= win - 1ull;
-            const double* col = base + (2 * h - q) * ROWS;
+    for (int t = 0; t < kBitsTilesPerCta; ++t) {
+        const int y0 = (blockIdx.y * kBitsTilesPerCta + t) * TY;
+        if (y0 >= H) break;
+        __syncthreads();                               // the previous tile's bitmap rows are no longer read
+        stage_occ_rows(occ, wpr, H, x0, y0 - h, SR, s_occ);
+        __syncthreads();
+        if (x >= W) continue;
+        double best[TY];
 #pragma unroll
-            for (int r = 0; r < TY; ++r) {
-                const double t = col[r];
-                best[r] = (t > best[r]) ? t : best[r];
+        for (int r = 0; r < TY; ++r) best[r] = -INFINITY;
+        for (int s = 0; s < SR; ++s) {
+            const uint32_t w0 = row[s * kGravOccWords], w1 = row[s * kGravOccWords + 1],
+                           w2 = row[s * kGravOccWords + 2];
+            unsigned long long win =
+                ((unsigned long long)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+            win &= mask;
+            // a particle at bit q sits on pixel x + q - h: kx = x - px + h = 2h - q; ky of output row r = 2h - s + r
+            const double* base = s_tab + PAD + 2 * h - s;
+            while (win) {
+                const int q = __ffsll((long long)win) - 1;
+                win &= win - 1ull;
+                const double* col = base + (2 * h - q) * ROWS;
+#pragma unroll
+                for (int r = 0; r < TY; ++r) {
+                    const double v = col[r];
+                    best[r] = (v > best[r]) ? v : best[r];
+                }
             }
         }
-    }
 #pragma unroll
-    for (int r = 0; r < TY; ++r) {
-        const int y = y0 + r;
-        if (y < H) field[(size_t)y * W + x] = (best[r] > -0.48) ? best[r] : -0.48;
+        for (int r = 0; r < TY; ++r) {
+            const int y = y0 + r;
+            if (y < H) field[(size_t)y * W + x] = (best[r] > -0.48) ? best[r] : -0.48;
+        }
     }
 }
 
@@ -1870,10 +1917,14 @@ __global__ void __launch_bounds__(kThreads) dual_metrics_kernel(
     CellView cl_g, DualView dv, const uint8_t* __restrict__ stable, const uint8_t* __restrict__ del, int n_host,
     const int* d_n, const int* d_n_dead, const double2* __restrict__ gt, int n_gt, const T* __restrict__ Rb, int H, int W,
     int bx, int by, int* icount /*[9]: 8 counts + block ticket*/, MetricsPartial* partials, int iteration,
-    aoslo_metrics_record* rec, int* status, const int* d_n_gt, int* d_rec_idx, const int* d_iteration) {
+    aoslo_metrics_record* rec, int* status, const int* d_n_gt, int* d_rec_idx, const int* d_iteration,
+    const uint32_t* __restrict__ occ_p, const uint32_t* __restrict__ occ_g, int wpr, const int* __restrict__ occ_ok) {
     const int n = d_n ? *d_n : n_host;
     if (d_n_gt) n_gt = *d_n_gt;
     const int total = n + n_gt;
+    // nearest distances between integer pixels come from the occupancy bitmaps (occ_nearest_d2); a set that is not
+    // all integer pixels (occ_ok = 0), a query that is not one, or a neighbour beyond 15 px takes the cell search
+    const bool bits_p = occ_ok[0] != 0, bits_g = occ_ok[1] != 0;
     int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tp1 tp2 fn1 fn2 fp1 fp2 nin nst
     Moments mp, mg;
     mp.init(); mg.init();
@@ -1883,9 +1934,20 @@ __global__ void __launch_bounds__(kThreads) dual_metrics_kernel(
         if (i < n) {
             if (del[i]) continue;
             const double2 p = dv.pos[i];
-            knn_cells_query<1>(cl_g, p.x, p.y, top);
-            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-            const double d = sqrt(top.d2[0]);
+            int q2 = -1;
+            if (bits_g) {
+                const int ix = (int)p.x, iy = (int)p.y;
+                if ((double)ix == p.x && (double)iy == p.y && ix >= 0 && ix < W && iy >= 0 && iy < H)
+                    q2 = occ_nearest_d2(occ_g, wpr, H, ix, iy);
+            }
+            double d;
+            if (q2 >= 0) {
+                d = sqrt((double)q2);
+            } else {
+                knn_cells_query<1>(cl_g, p.x, p.y, top);
+                if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+                d = sqrt(top.d2[0]);
+            }
             const bool inside = ((double)bx < p.x) && (p.x < (double)(W - bx)) && ((double)by < p.y) &&
                                 (p.y < (double)(H - by));
             c[6] += inside;
@@ -1896,9 +1958,20 @@ __global__ void __launch_bounds__(kThreads) dual_metrics_kernel(
             energy += energy_at<T>(Rb, p, W, H, status);
         } else {
             const double2 g = gt[i - n];
-            knn_dual_query<1>(dv, g.x, g.y, top);
-            if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
-            const double d = sqrt(top.d2[0]);
+            int q2 = -1;
+            if (bits_p) {
+                const int ix = (int)g.x, iy = (int)g.y;
+                if ((double)ix == g.x && (double)iy == g.y && ix >= 0 && ix < W && iy >= 0 && iy < H)
+                    q2 = occ_nearest_d2(occ_p, wpr, H, ix, iy);
+            }
+            double d;
+            if (q2 >= 0) {
+                d = sqrt((double)q2);
+            } else {
+                knn_dual_query<1>(dv, g.x, g.y, top);
+                if (top.idx[0] == 0x7fffffff) atomicOr(status, AOSLO_DEV_KNN_SHORT);
+                d = sqrt(top.d2[0]);
+            }
             c[0] += (d <= 1.42); c[2] += (d > 1.42);
             c[1] += (d <= 2.83); c[3] += (d > 2.83);
             mg.add(d);
@@ -2174,10 +2247,10 @@ int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, int n_hos
         AOSLO_LAUNCH_CHECK();
     }
     const int n16 = (int)(((size_t)H * wpr + 3) / 4);
-    occ_clear_kernel<<<ctx->num_sms, kThreads, 0, s>>>(reinterpret_cast<uint4*>(ctx->d_occ), n16);
+    occ_clear_kernel<<<ctx->num_sms, kThreads, 0, s>>>(reinterpret_cast<uint4*>(ctx->d_occ), n16, nullptr);
     AOSLO_LAUNCH_CHECK();
-    occ_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n_host, d_n, W, H, wpr, ctx->d_occ,
-                                                    ctx->d_status);
+    occ_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, nullptr, n_host, d_n, W, H, wpr,
+                                                    ctx->d_occ, ctx->d_status, nullptr);
     AOSLO_LAUNCH_CHECK();
     if (h >= 1 && h <= kNearMaxH) {                   // otherwise the flag is 0 and the general kernel works
         dim3 grid((W + kGravCols - 1) / kGravCols, (H + kNearRows - 1) / kNearRows);
@@ -2192,7 +2265,8 @@ int stage_gravity(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, int n_hos
         AOSLO_LAUNCH_CHECK();
     }
     {
-        dim3 grid((W + kGravCols - 1) / kGravCols, (H + kBitsRows - 1) / kBitsRows);
+        const int row_tiles = (H + kBitsRows - 1) / kBitsRows;
+        dim3 grid((W + kGravCols - 1) / kGravCols, (row_tiles + kBitsTilesPerCta - 1) / kBitsTilesPerCta);
         gravity_bits_kernel<<<grid, kGravCols, grav_bits_smem(rfs), s>>>(ctx->d_occ, wpr, d_lut, rfs, ctx->d_lut_flag,
                                                                          H, W, d_field);
         AOSLO_LAUNCH_CHECK();
@@ -2363,6 +2437,24 @@ int stage_compact(aoslo_ctx* ctx, cudaStream_t s, int n_bound, int* d_n, int* d_
     return AOSLO_OK;
 }
 
+// occupancy bitmap for nearest-distance queries: *ok = 1 iff every (surviving) point is an in-image integer pixel
+static int occ_build(aoslo_ctx* ctx, cudaStream_t s, uint32_t* occ, const double2* pos, const uint8_t* del, int n_host,
+                     const int* d_n, int H, int W, int* ok) {
+    const int wpr = occ_words_per_row(W);
+    const int n16 = (int)(((size_t)H * wpr + 3) / 4);
+    occ_clear_kernel<<<ctx->num_sms, kThreads, 0, s>>>(reinterpret_cast<uint4*>(occ), n16, ok);
+    AOSLO_LAUNCH_CHECK();
+    occ_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>(pos, del, n_host, d_n, W, H, wpr, occ, ctx->d_status, ok);
+    AOSLO_LAUNCH_CHECK();
+    return AOSLO_OK;
+}
+
+// once per run: the ground truth's bitmap for the particle -> nearest GT distances of stage_dual_metrics
+int stage_gt_bitmap(aoslo_ctx* ctx, cudaStream_t s, const double* d_gt, int n_gt, const int* d_n_gt) {
+    return occ_build(ctx, s, ctx->d_occ_gt, (const double2*)d_gt, nullptr, n_gt, d_n_gt, ctx->H, ctx->W,
+                     ctx->d_occ_ok + 1);
+}
+
 int stage_dual_metrics(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d_n, const double* d_gt, int n_gt,
                        const void* d_Rb, int field_dtype, int H, int W, int bx, int by, int iteration,
                        aoslo_metrics_record* d_rec, const int* d_n_gt, int* d_rec_idx, const int* d_iteration) {
@@ -2372,16 +2464,19 @@ int stage_dual_metrics(aoslo_ctx* ctx, cudaStream_t s, int n_bound, const int* d
     AOSLO_CUDA(cudaMemsetAsync(icount, 0, sizeof(int) * 9, s));
     MetricsPartial* partials = (MetricsPartial*)ctx->d_partials;
     const DualView dv = dual_view(ctx);
+    // bitmap of the survivors (the GT bitmap is per run: stage_gt_bitmap)
+    const int wpr = occ_words_per_row(W);
+    AOSLO_TRY(occ_build(ctx, s, ctx->d_occ, dv.pos, ctx->d_del, n_bound, d_n, H, W, ctx->d_occ_ok));
     if (field_dtype == AOSLO_F32)
         dual_metrics_kernel<float><<<ctx->nb, kThreads, 0, s>>>(
             view_of(ctx->cl_g), dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, ctx->d_counters + 7,
             (const double2*)d_gt, n_gt, (const float*)d_Rb, H, W, bx, by, icount, partials, iteration, d_rec,
-            ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
+            ctx->d_status, d_n_gt, d_rec_idx, d_iteration, ctx->d_occ, ctx->d_occ_gt, wpr, ctx->d_occ_ok);
     else
         dual_metrics_kernel<double><<<ctx->nb, kThreads, 0, s>>>(
             view_of(ctx->cl_g), dv, ctx->d_stable[0], ctx->d_del, n_bound, d_n, ctx->d_counters + 7,
             (const double2*)d_gt, n_gt, (const double*)d_Rb, H, W, bx, by, icount, partials, iteration, d_rec,
-            ctx->d_status, d_n_gt, d_rec_idx, d_iteration);
+            ctx->d_status, d_n_gt, d_rec_idx, d_iteration, ctx->d_occ, ctx->d_occ_gt, wpr, ctx->d_occ_ok);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
 }
