@@ -181,8 +181,6 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_link_epoch, 1));
     A(dmalloc(&c->d_link_epoch_ticket, 1));
     A(dmalloc(&c->d_link_epoch_n, 1));
-    A(dmalloc(&c->d_map_epoch, 1));
-    if (st == AOSLO_OK && cudaMemset(c->d_map_epoch, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     A(dmalloc(&c->d_head_n, c->lk_p.ncell));
     if (st == AOSLO_OK && cudaMemset(c->d_link_epoch_n, 0, sizeof(unsigned int)) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK && cudaMemset(c->d_head_n, 0, sizeof(unsigned long long) * c->lk_p.ncell) != cudaSuccess)
@@ -236,6 +234,9 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_occ, (size_t)H * ((W + 31) / 32 + 2) + 4));   // + 4: the clear kernel stores whole uint4
     A(dmalloc(&c->d_occ_gt, (size_t)H * ((W + 31) / 32 + 2) + 4));
     A(dmalloc(&c->d_occ_ok, 2));
+    A(dmalloc(&c->d_thin, (size_t)7 * H * ((W + 31) / 32 + 2)));
+    A(dmalloc(&c->d_thin_ctr, 8));
+    c->coop_blocks_thin = coop_blocks_for_thin(c->num_sms);
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
     c->kd.cap = 0;   // sklearn-order KD tree mirrors are allocated on first use (aoslo::kd_reserve)
@@ -268,7 +269,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
-    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_occ_gt); cudaFree(c->d_occ_ok); cudaFree(c->d_field); cudaFree(c->d_win);
+    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_occ_gt); cudaFree(c->d_occ_ok); cudaFree(c->d_thin); cudaFree(c->d_thin_ctr); cudaFree(c->d_field); cudaFree(c->d_win);
     kd_free(c->kd); kd_free(c->kd2); cudaFreeHost(c->kd_stage);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -282,7 +283,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
     if (c->cap_stream3) cudaStreamDestroy(c->cap_stream3);
     cudaFree(c->d_link_geom); cudaFree(c->d_link_epoch); cudaFree(c->d_link_epoch_ticket);
-    cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_map_epoch); cudaFree(c->d_ctl); cudaFree(c->d_params);
+    cudaFree(c->d_link_epoch_n); cudaFree(c->d_head_n); cudaFree(c->d_ctl); cudaFree(c->d_params);
     cudaFreeHost(c->h_ctl); cudaFreeHost(c->h_params);
     cudaFree(c->d_epoch);
     cudaGetLastError();
@@ -705,7 +706,7 @@ int new_cond_handle(cudaStream_t q, cudaGraphConditionalHandle* h) {
 
 struct RunKey {                      // everything baked into the nodes of a cached run graph
     int H, W, bx, by, fdt, k_class, energy, step_mode, rfs, window;
-    int dynamic_loop, timing, epoch_num, fix_freq, metric_freq, max_rec, hint, has_records;
+    int dynamic_loop, timing, epoch_num, fix_freq, metric_freq, max_rec, hint, has_records, thin_pixels;
     const void *Rb, *grad, *gt, *records;
 };
 
@@ -721,6 +722,7 @@ struct RunPlan {
     int max_records;
     bool timing;
     bool dynamic_loop;               // WHILE / IF nodes (early stop) instead of the unrolled loop
+    bool thin_pixels;                // seeds + thinning in the pixel domain (thinning threshold <= 4 px)
     int inner;                       // inner pixels: upper bound of the seed count
     int hint;                        // launch-size hint of the in-loop compaction
     int* cnt0;
@@ -734,7 +736,7 @@ int enqueue_thin_round(RunPlan& P, cudaStream_t q, cudaGraphConditionalHandle h,
     const aoslo_config* cfg = P.cfg;
     AOSLO_TRY(stage_delete(c, q, c->d_pos[0], c->d_stable[0], P.inner, P.d_Rb, P.fdt, cfg->H, cfg->W,
                            cfg->thinning_threshold, AOSLO_TIE_CANONICAL, c->d_pos[1], c->d_stable[1], nullptr, P.cnt1,
-                           nullptr, P.cnt0, 3, &c->d_params->thin_thr, 0));
+                           nullptr, P.cnt0, 0, &c->d_params->thin_thr, 0));
     thin_swap_kernel<<<c->nb, kThreads, 0, q>>>((const double2*)c->d_pos[1], c->d_stable[1], P.cnt1,
                                                 (double2*)c->d_pos[0], c->d_stable[0], P.cnt0, c->d_ctl, h, use_handle);
     AOSLO_LAUNCH_CHECK();
@@ -816,26 +818,33 @@ int enqueue_run(RunPlan& P, cudaStream_t q, bool graph) {
     };
     run_begin_kernel<<<1, 32, 0, q>>>(ctl, c->d_status, c->d_counters);
     AOSLO_LAUNCH_CHECK();
-    // ---- seeds (:101), flags (:113)
-    AOSLO_TRY(stage_seed(c, q, P.d_Rb, P.fdt, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold, c->d_pos[0], c->cap,
-                         P.cnt0, &rp->seed_thr, true));
-    AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], P.inner, 0, P.cnt0));
-    // ---- thinning to the fixpoint (:115-120)
-    if (graph) {
-        CondNode thin;
-        AOSLO_TRY(new_cond_handle(q, &thin.handle));
-        after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, thin.handle, 1);
-        AOSLO_LAUNCH_CHECK();
-        AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &thin));
-        AOSLO_TRY(capture_body(c->cap_stream2, thin.body, &P.k_thin,
-                               [&]() { return enqueue_thin_round(P, c->cap_stream2, thin.handle, 1); }));
+    if (P.thin_pixels) {
+        // ---- seeds (:101) and thinning to the fixpoint (:115-120) in the pixel domain: one cooperative kernel + the
+        // ordered listing of the survivors
+        AOSLO_TRY(stage_thin_pixels(c, q, P.d_Rb, P.fdt, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold,
+                                    cfg->thinning_threshold, rp, ctl, c->d_pos[0], c->d_stable[0], P.cnt0));
     } else {
-        after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, 0, 0);
-        AOSLO_LAUNCH_CHECK();
-        for (;;) {
-            AOSLO_TRY(read_ctl());
-            if (!c->h_ctl->thin_cond) break;
-            AOSLO_TRY(enqueue_thin_round(P, q, 0, 0));
+        // ---- seeds (:101), flags (:113)
+        AOSLO_TRY(stage_seed(c, q, P.d_Rb, P.fdt, H, W, cfg->bx, cfg->by, cfg->init_blob_threshold, c->d_pos[0], c->cap,
+                             P.cnt0, &rp->seed_thr, true));
+        AOSLO_TRY(stage_set_stable(c, q, c->d_stable[0], P.inner, 0, P.cnt0));
+        // ---- thinning to the fixpoint (:115-120)
+        if (graph) {
+            CondNode thin;
+            AOSLO_TRY(new_cond_handle(q, &thin.handle));
+            after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, thin.handle, 1);
+            AOSLO_LAUNCH_CHECK();
+            AOSLO_TRY(add_cond_node(q, cudaGraphCondTypeWhile, &thin));
+            AOSLO_TRY(capture_body(c->cap_stream2, thin.body, &P.k_thin,
+                                   [&]() { return enqueue_thin_round(P, c->cap_stream2, thin.handle, 1); }));
+        } else {
+            after_seed_kernel<<<1, 32, 0, q>>>(ctl, P.cnt0, 0, 0);
+            AOSLO_LAUNCH_CHECK();
+            for (;;) {
+                AOSLO_TRY(read_ctl());
+                if (!c->h_ctl->thin_cond) break;
+                AOSLO_TRY(enqueue_thin_round(P, q, 0, 0));
+            }
         }
     }
     // ---- all stable, LUT, gravity field, adding (:130-152), first resample period; GT cell list once per run
@@ -948,6 +957,7 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
     P.max_records = P.want_records ? max_records : 0;
     P.timing = h_stage_ms != nullptr;
     P.dynamic_loop = cfg->early_stop != 0 || ctx->no_graph;
+    P.thin_pixels = cfg->thinning_threshold <= 4.0;
     P.inner = (H - 2 * cfg->by) * (W - 2 * cfg->bx);
     if (P.inner < 1) return AOSLO_ERR_INVALID;
     if (P.inner > ctx->cap) P.inner = ctx->cap;
@@ -991,7 +1001,7 @@ int run_canonical(aoslo_ctx* ctx, cudaStream_t s, const aoslo_config* cfg, const
         key.k_class = k_class_of(cfg->dist_n_neighbours + 1); key.energy = cfg->dist_energy_type;
         key.step_mode = cfg->step_mode; key.rfs = cfg->reception_field_size; key.window = cfg->particle_call_window;
         key.dynamic_loop = P.dynamic_loop; key.timing = P.timing; key.hint = P.hint;
-        key.has_records = P.want_records;
+        key.has_records = P.want_records; key.thin_pixels = P.thin_pixels;
         if (!P.dynamic_loop) {
             key.epoch_num = cfg->epoch_num; key.fix_freq = cfg->fix_particles_frequency;
             key.metric_freq = cfg->metric_measure_freq; key.max_rec = P.max_records;

@@ -202,7 +202,6 @@ struct aoslo_ctx {
     int* d_link_geom = nullptr;          // [8] shift, gw, gh, ncell, tag of lk_p
     unsigned int* d_link_epoch = nullptr;   // build counter = tag of the last build
     unsigned int* d_link_epoch_n = nullptr; // same for the non-stable structure N of the run loop
-    unsigned int* d_map_epoch = nullptr;    // tag counter of the thinning rounds' pixel map (lives in d_field)
     unsigned long long* d_head_n = nullptr; // [ncell of the finest grid] heads of N
     int* d_link_epoch_ticket = nullptr;
     int loop_hint = 0;                   // launch-size hint of the in-loop compaction (performance only)
@@ -234,6 +233,9 @@ struct aoslo_ctx {
     uint32_t* d_occ = nullptr;        // [H][(W+31)/32 + 2] occupancy bitmap of the particles' pixels
     uint32_t* d_occ_gt = nullptr;     // same for the ground truth of the current run (stage_gt_bitmap)
     int* d_occ_ok = nullptr;          // [2] particles / GT: every point is an in-image integer pixel
+    uint32_t* d_thin = nullptr;       // [7][H * wpr] pixel-domain thinning: six stencil bit planes + pending rows
+    int* d_thin_ctr = nullptr;        // [8] its counters
+    int coop_blocks_thin = 0;         // co-resident blocks of thin_pixels_kernel
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd, kd2;         // two cached trees (sklearn-order tie mode): typically particles and GT
@@ -432,6 +434,10 @@ int stage_dual_count_stable(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t* d_stable, int n, uint8_t v, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t* d_stable, int n, int* d_out, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
+int coop_blocks_for_thin(int num_sms);
+int stage_thin_pixels(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
+                      double seed_thr, double thin_thr, const RunParams* rp, RunCtl* ctl, double* d_pos,
+                      uint8_t* d_stable, int* d_n_out);
 int stage_classify(aoslo_ctx*, cudaStream_t, const double* d_g2p, int n_gt, const double* d_p2g, const double* d_pos,
                    int n, int bx, int by, int W, int H, double thr, uint8_t* gt_is_tp, uint8_t* particle_is_fp);
 int stage_prepare(aoslo_ctx*, cudaStream_t, const uint8_t* d_raw, int H0, int W0, int pitch0, int x_min, int x_max,

@@ -680,80 +680,256 @@ __global__ void __launch_bounds__(kCoopThreads) delete_resolve_kernel(DeletePara
     if (tid == 0 && p.rounds_out) *p.rounds_out = round;
 }
 
-// ---- thinning rounds (aoslo_run): nearest neighbour through a PIXEL MAP ---------------------------------------
-// During the thinning (:115-120) the particles are the seeds: distinct integer pixels in raster order, and the
-// order-preserving compaction keeps them in raster order.  So (1) a pixel -> index map answers "who is at (x, y)" with
-// one load, (2) a row is only active when its neighbour is closer than the threshold (3 px), i.e. within a fixed
-// stencil, and (3) the canonical (d^2, index) order among equidistant neighbours is the raster order of their pixels.
-// Walking the stencil offsets sorted by (d^2, dy, dx) and stopping at the first occupied pixel therefore yields exactly
-// the row (self, nearest, d^2) the cell-list search yields, with coalesced loads instead of chained ones; a row without
-// a neighbour inside the stencil is inactive and gets to = -1.  Map words are (tag << 32) | index (no clearing).
-constexpr int kThinMaxD2 = 16;                 // stencil for thresholds <= 4 px
-struct ThinStencil { int n; signed char dx[64], dy[64], d2[64]; };
+// ---- thinning to the fixpoint (aoslo_run, canonical order) in the PIXEL DOMAIN -----------------------------------
+// reference :101-120: seeds = inner pixels with R_b > threshold in raster order, then `while deleted:
+// del_close_particles(thr = 3)`.  The seeds are distinct integer pixels, the order-preserving compaction keeps them in
+// raster order, and a round only ever looks at neighbours closer than the threshold -- so the whole loop can be stated
+// on a bitmap of alive pixels, without particle indices and without a compaction per round:
+//   * row order = raster order of the pixels; the canonical (d^2, index) order among equidistant neighbours is the
+//     raster order of their pixels, i.e. the stencil offsets sorted by (d^2, dy, dx);
+//   * phase R (per round): the nearest alive neighbour of all 32 pixels of a bitmap word at once -- for every stencil
+//     offset, in order, `center & shifted(row y+dy by dx) & ~found`; the offset's number goes into six bit planes;
+//   * wavefront resolution of the greedy walk (utils.py:249-263) exactly as in delete_resolve_kernel: every pending
+//     row stamps both endpoints with (wave, ~pixel) by atomicMax, a row owning both endpoints acts, the victim's bit
+//     is cleared; the waves of all rounds run inside ONE cooperative kernel (grid barriers), a round without a
+//     deletion ends the loop;
+//   * the survivors are listed once, at the end (ordered scan over the bitmap words).
+// Replaces, per run: the seed compaction (2 kernels over the R_b field), and per round (5 on the benchmark frame)
+// a pixel-map scatter, a row kernel, the cooperative resolve, a compaction (2 kernels) and a copy.
+constexpr int kThinOffsets = 44;               // |d| < 4: thresholds up to 4 px
+constexpr int kThinPlanes = 6;
+constexpr int kThinThreads = 512;
+constexpr int kThinMaxWaves = 20000;
+__constant__ signed char c_thin_dx[kThinOffsets] = {0, -1, 1, 0, -1, 1, -1, 1, 0, -2, 2, 0, -1, 1, -2, 2, -2, 2, -1, 1, -2, 2,
+                                                    -2, 2, 0, -3, 3, 0, -1, 1, -3, 3, -3, 3, -1, 1, -2, 2, -3, 3, -3, 3, -2, 2};
+__constant__ signed char c_thin_dy[kThinOffsets] = {-1, 0, 0, 1, -1, -1, 1, 1, -2, 0, 0, 2, -2, -2, -1, -1, 1, 1, 2, 2, -2, -2,
+                                                    2, 2, -3, 0, 0, 3, -3, -3, -1, -1, 1, 1, 3, 3, -3, -3, -2, -2, 2, 2, 3, 3};
+struct ThinOff { int dx, dy, d2; };
+__host__ __device__ constexpr ThinOff thin_off(int k) {
+    constexpr int dx[kThinOffsets] = {0, -1, 1, 0, -1, 1, -1, 1, 0, -2, 2, 0, -1, 1, -2, 2, -2, 2, -1, 1, -2, 2,
+                                      -2, 2, 0, -3, 3, 0, -1, 1, -3, 3, -3, 3, -1, 1, -2, 2, -3, 3, -3, 3, -2, 2};
+    constexpr int dy[kThinOffsets] = {-1, 0, 0, 1, -1, -1, 1, 1, -2, 0, 0, 2, -2, -2, -1, -1, 1, 1, 2, 2, -2, -2,
+                                      2, 2, -3, 0, 0, 3, -3, -3, -1, -1, 1, 1, 3, 3, -3, -3, -2, -2, 2, 2, 3, 3};
+    return ThinOff{dx[k], dy[k], dx[k] * dx[k] + dy[k] * dy[k]};
+}
 
-static ThinStencil make_thin_stencil() {
-    ThinStencil t{};
-    t.n = 0;
-    for (int d2 = 1; d2 < kThinMaxD2; ++d2)
-        for (int dy = -3; dy <= 3; ++dy)
-            for (int dx = -3; dx <= 3; ++dx)
-                if (dx * dx + dy * dy == d2) {
-                    t.dx[t.n] = (signed char)dx; t.dy[t.n] = (signed char)dy; t.d2[t.n] = (signed char)d2;
-                    ++t.n;
+struct ThinParams {
+    int H, W, bx, by, wpr, cap;
+    double seed_thr, thin_thr;
+    const RunParams* rp;            // device-resident thresholds of the graph path (override the two above)
+    uint32_t* alive;                // [H][wpr] bitmap of the alive pixels, bit x at word 1 + x / 32
+    uint32_t* planes;               // [kThinPlanes][H * wpr] stencil number of every pending pixel's neighbour
+    uint32_t* pend;                 // [H * wpr] rows still pending in the current round
+    unsigned long long* touch;      // [H * W] wavefront stamps per pixel
+    int* ctr;                       // [8], zero at launch: 0..2 rotating pending counts, 3 deletions, 4 seeds
+    RunCtl* ctl;
+    int* status;
+};
+
+// neighbour mask of a bitmap word: bit b = pixel (x + dx) of the row whose words around this column are L, C, R
+template <int DX>
+__device__ __forceinline__ uint32_t thin_shift(uint32_t L, uint32_t C, uint32_t R) {
+    if (DX > 0) return __funnelshift_r(C, R, DX);
+    if (DX < 0) return __funnelshift_l(L, C, -DX);
+    return C;
+}
+
+template <int K>
+struct ThinScan {      // offsets K .. kThinOffsets-1, in order
+    __device__ static __forceinline__ void run(const uint32_t (&L)[7], const uint32_t (&C)[7], const uint32_t (&R)[7],
+                                               int lim, uint32_t center, uint32_t& found, uint32_t (&pl)[kThinPlanes]) {
+        constexpr ThinOff o = thin_off(K);
+        if (K < lim) {
+            const uint32_t m = center & thin_shift<o.dx>(L[o.dy + 3], C[o.dy + 3], R[o.dy + 3]) & ~found;
+            found |= m;
+#pragma unroll
+            for (int b = 0; b < kThinPlanes; ++b)
+                if ((K >> b) & 1) pl[b] |= m;
+        }
+        ThinScan<K + 1>::run(L, C, R, lim, center, found, pl);
+    }
+};
+template <>
+struct ThinScan<kThinOffsets> {
+    __device__ static __forceinline__ void run(const uint32_t (&)[7], const uint32_t (&)[7], const uint32_t (&)[7], int,
+                                               uint32_t, uint32_t&, uint32_t (&)[kThinPlanes]) {}
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThinThreads) thin_pixels_kernel(ThinParams p, const T* __restrict__ Rb) {
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int H = p.H, W = p.W, wpr = p.wpr, nwords = H * wpr;
+    const size_t fp = fpitch(W);
+    const double seed_thr = p.rp ? p.rp->seed_thr : p.seed_thr;
+    const double thin_thr = p.rp ? p.rp->thin_thr : p.thin_thr;
+    __shared__ int s_pending, s_deleted;
+
+    // ---- seeds (utils.py:359-375): a warp per bitmap word, a lane per pixel
+    {
+        int nseed = 0;
+        for (int t = tid >> 5; t < nwords; t += nthr >> 5) {
+            const int y = t / wpr, x = (t - y * wpr - 1) * 32 + lane;
+            bool sd = false;
+            if (x >= p.bx && x < W - p.bx && y >= p.by && y < H - p.by) {
+                sd = (double)Rb[(size_t)y * fp + x] > seed_thr;
+                if (sd) p.touch[(size_t)y * W + x] = 0ull;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, sd);
+            if (lane == 0) { p.alive[t] = m; nseed += __popc(m); }
+        }
+        if (nseed) atomicAdd(&p.ctr[4], nseed);
+    }
+    grid.sync();
+    const int n_seeds = __ldcg(&p.ctr[4]);
+    int lim = 0;                                  // offsets with d^2 < thr^2 (exact: small integers)
+    {
+        const double thr2 = thin_thr * thin_thr;
+        for (int k = 0; k < kThinOffsets; ++k) {
+            const int dx = c_thin_dx[k], dy = c_thin_dy[k];
+            if ((double)(dx * dx + dy * dy) < thr2) lim = k + 1;
+        }
+    }
+    int rounds = 0, wave = 0, deleted_before = 0;
+    bool overflow = false;
+    while (n_seeds >= 2) {
+        // ---- phase R: nearest alive neighbour of every alive pixel, 32 pixels at a time
+        for (int t = tid; t < nwords; t += nthr) {
+            const uint32_t center = __ldcg(&p.alive[t]);     // L2: cleared by other SMs' atomics in earlier waves
+            uint32_t found = 0u, pl[kThinPlanes];
+#pragma unroll
+            for (int b = 0; b < kThinPlanes; ++b) pl[b] = 0u;
+            if (center) {                          // never a pad word: 1 <= t % wpr <= wpr - 2
+                const int y = t / wpr;
+                uint32_t L[7], C[7], R[7];
+#pragma unroll
+                for (int d = 0; d < 7; ++d) {
+                    const int yy = y + d - 3;
+                    const bool in = yy >= 0 && yy < H;
+                    const uint32_t* row = p.alive + t + (d - 3) * wpr;
+                    L[d] = in ? __ldcg(row - 1) : 0u;
+                    C[d] = in ? __ldcg(row) : 0u;
+                    R[d] = in ? __ldcg(row + 1) : 0u;
                 }
-    return t;
+                ThinScan<0>::run(L, C, R, lim, center, found, pl);
+            }
+            p.pend[t] = found;
+#pragma unroll
+            for (int b = 0; b < kThinPlanes; ++b) p.planes[(size_t)b * nwords + t] = pl[b];
+        }
+        // ---- wavefront rounds of this thinning round (phase R wrote only this thread's own words)
+        for (;;) {
+            ++wave;
+            const unsigned long long hi = (unsigned long long)(unsigned)wave << 32;
+            for (int t = tid; t < nwords; t += nthr) {
+                uint32_t pm = p.pend[t];
+                if (!pm) continue;
+                const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
+                uint32_t pl[kThinPlanes];
+#pragma unroll
+                for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
+                while (pm) {
+                    const int b = __ffs((int)pm) - 1;
+                    pm &= pm - 1u;
+                    int code = 0;
+#pragma unroll
+                    for (int k = 0; k < kThinPlanes; ++k) code |= (int)((pl[k] >> b) & 1u) << k;
+                    const int pix = y * W + x0 + b;
+                    const int q = pix + c_thin_dy[code] * W + c_thin_dx[code];
+                    const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)pix);
+                    atomicMax(&p.touch[pix], key);
+                    atomicMax(&p.touch[q], key);
+                }
+            }
+            if (tid == 0) p.ctr[(wave + 1) % 3] = 0;
+            if (threadIdx.x == 0) { s_pending = 0; s_deleted = 0; }
+            grid.sync();
+            int pending = 0, deleted = 0;
+            for (int t = tid; t < nwords; t += nthr) {
+                const uint32_t pm0 = p.pend[t];
+                if (!pm0) continue;
+                uint32_t pm = pm0, keep = pm0;
+                const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
+                uint32_t pl[kThinPlanes];
+#pragma unroll
+                for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
+                while (pm) {
+                    const int b = __ffs((int)pm) - 1;
+                    pm &= pm - 1u;
+                    int code = 0;
+#pragma unroll
+                    for (int k = 0; k < kThinPlanes; ++k) code |= (int)((pl[k] >> b) & 1u) << k;
+                    const int dx = c_thin_dx[code], dy = c_thin_dy[code];
+                    const int x = x0 + b, pix = y * W + x, q = pix + dy * W + dx;
+                    const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)pix);
+                    if (__ldcg(&p.touch[pix]) == key && __ldcg(&p.touch[q]) == key) {
+                        const int tq = (y + dy) * wpr + 1 + ((x + dx) >> 5), bq = (x + dx) & 31;
+                        const bool a_from = (__ldcg(&p.alive[t]) >> b) & 1u;
+                        const bool a_to = (__ldcg(&p.alive[tq]) >> bq) & 1u;
+                        if (a_from && a_to) {
+                            const double e1 = (double)Rb[(size_t)y * fp + x];
+                            const double e2 = (double)Rb[(size_t)(y + dy) * fp + x + dx];
+                            if (e1 < e2) atomicAnd(&p.alive[t], ~(1u << b));
+                            else atomicAnd(&p.alive[tq], ~(1u << bq));
+                            ++deleted;
+                        }
+                        keep &= ~(1u << b);
+                    } else {
+                        ++pending;
+                    }
+                }
+                p.pend[t] = keep;
+            }
+            if (pending) atomicAdd(&s_pending, pending);
+            if (deleted) atomicAdd(&s_deleted, deleted);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (s_pending) atomicAdd(&p.ctr[wave % 3], s_pending);
+                if (s_deleted) atomicAdd(&p.ctr[3], s_deleted);
+            }
+            grid.sync();
+            if (__ldcg(&p.ctr[wave % 3]) == 0) break;
+            if (wave >= kThinMaxWaves) { overflow = true; break; }
+        }
+        ++rounds;
+        const int deleted_total = __ldcg(&p.ctr[3]);
+        const bool none = deleted_total == deleted_before;
+        deleted_before = deleted_total;
+        if (none || overflow) break;
+    }
+    if (tid == 0) {
+        p.ctl->n_seeds = n_seeds;
+        p.ctl->n_after_thinning = n_seeds - deleted_before;
+        p.ctl->thin_rounds = rounds;
+        p.ctl->thin_cond = 0;
+        // the reference's particle list would not fit (seeds), or the wavefront did not terminate (never observed)
+        if (n_seeds > p.cap || overflow) atomicOr(p.status, AOSLO_DEV_CAPACITY);
+    }
 }
 
-__global__ void __launch_bounds__(kThreads) thin_map_scatter_kernel(const double2* __restrict__ pos, int n_host,
-                                                                    const int* d_n, int W, int H,
-                                                                    unsigned long long* map, unsigned int* epoch,
-                                                                    int* ticket, int* geom, int* status) {
-    const int n = d_n ? *d_n : n_host;
-    const unsigned int tag = *epoch + 1u;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double2 p = pos[i];
-        const int x = (int)p.x, y = (int)p.y;
-        if (!(p.x >= 0.0 && p.y >= 0.0 && x < W && y < H)) { atomicOr(status, AOSLO_DEV_ESCAPED); continue; }
-        map[(size_t)y * W + x] = ((unsigned long long)tag << 32) | (unsigned long long)(unsigned int)i;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
-            geom[6] = (int)tag;
-            *epoch = tag;
-            *ticket = 0;
+struct AliveEmitOp {               // the survivors in raster order -> particle rows, not stable
+    const uint32_t* alive;
+    int wpr;
+    double2* pos;
+    uint8_t* stable;
+    int cap;
+    int* status;
+    __device__ int value(int t) const { return __popc(alive[t]); }
+    __device__ void emit(int t, int v, int dst) const {
+        if (!v) return;
+        const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
+        uint32_t m = alive[t];
+        while (m) {
+            const int b = __ffs((int)m) - 1;
+            m &= m - 1u;
+            if (dst >= cap) { atomicOr(status, AOSLO_DEV_CAPACITY); return; }
+            pos[dst] = make_double2((double)(x0 + b), (double)y);
+            stable[dst] = 0;
+            ++dst;
         }
     }
-}
-
-__global__ void __launch_bounds__(kThreads) thin_map_rows_kernel(const double2* __restrict__ pos, int n_host,
-                                                                 const int* d_n, int W, int H,
-                                                                 const unsigned long long* __restrict__ map,
-                                                                 const int* __restrict__ geom, ThinStencil st,
-                                                                 double thr, const double* d_thr, int32_t* knn_idx,
-                                                                 double* knn_d2) {
-    const int n = d_n ? *d_n : n_host;
-    if (d_thr) thr = *d_thr;
-    const unsigned int tag = (unsigned int)geom[6];
-    const double thr2 = thr * thr;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double2 p = pos[i];
-        const int x = (int)p.x, y = (int)p.y;
-        int to = -1, d2 = 0;
-        for (int o = 0; o < st.n; ++o) {
-            if ((double)st.d2[o] >= thr2) break;                 // dist < thr  <=>  d^2 < thr^2 (exact: small integers)
-            const int xx = x + st.dx[o], yy = y + st.dy[o];
-            if (xx < 0 || yy < 0 || xx >= W || yy >= H) continue;
-            const unsigned long long w = map[(size_t)yy * W + xx];
-            if ((unsigned int)(w >> 32) == tag) { to = (int)(unsigned int)w; d2 = st.d2[o]; break; }
-        }
-        knn_idx[2 * (size_t)i] = i;
-        knn_idx[2 * (size_t)i + 1] = to;
-        knn_d2[2 * (size_t)i] = 0.0;
-        knn_d2[2 * (size_t)i + 1] = (to >= 0) ? (double)d2 : INFINITY;
-    }
-}
+};
 
 // kNN(k=2) rows of the deletion step on the linked cells + compact list of the active rows
 // (rows whose `from` is not stable and whose neighbour is closer than the threshold)
@@ -2121,8 +2297,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
                    const T* d_Rb, int H, int W, double thr, int tie_mode, double* d_pos_out, uint8_t* d_stable_out,
                    uint8_t* d_deleted_out, int* d_n_out, int* d_rounds_out, const int* d_n, int mode,
                    const double* d_thr, int scan_hint) {
-    // mode 0: cooperative all-rows resolve (3: with the pixel-map neighbour search of aoslo_run's thinning rounds);
-    // 1: compact active list + one resolving block (the sklearn-order run loop)
+    // mode 0: cooperative all-rows resolve; 1: compact active list + one resolving block (the sklearn-order run loop)
     if (n > ctx->cap) return AOSLO_ERR_CAPACITY;
     if (n < 2) return AOSLO_ERR_INVALID;   // sklearn: n_neighbors=2 > n_samples
     if (d_n && d_n == d_n_out) return AOSLO_ERR_INVALID;   // the count is double-buffered
@@ -2157,20 +2332,7 @@ int stage_delete_t(aoslo_ctx* ctx, cudaStream_t s, const double* d_pos, const ui
         AOSLO_LAUNCH_CHECK();
         return AOSLO_OK;
     } else {
-        if (mode == 3 && thr <= 4.0) {
-            // thinning round of aoslo_run: seeds are distinct integer pixels in raster order (see thin_map_rows_kernel)
-            static const ThinStencil stencil = make_thin_stencil();
-            unsigned long long* map = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the resample
-            thin_map_scatter_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n, d_n, W, H, map,
-                                                                 ctx->d_map_epoch, ctx->d_link_epoch_ticket,
-                                                                 ctx->d_link_geom, ctx->d_status);
-            AOSLO_LAUNCH_CHECK();
-            thin_map_rows_kernel<<<ctx->nb, kThreads, 0, s>>>((const double2*)d_pos, n, d_n, W, H, map, ctx->d_link_geom,
-                                                              stencil, thr, d_thr, ctx->d_knn_idx, ctx->d_knn_d2);
-            AOSLO_LAUNCH_CHECK();
-        } else {
-            AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
-        }
+        AOSLO_TRY(stage_knn(ctx, s, d_pos, n, d_pos, n, 2, tie_mode, ctx->d_knn_idx, ctx->d_knn_d2, true, d_n));
         DeleteParams p;
         p.pos = (const double2*)d_pos; p.stable = d_stable; p.n_host = n; p.d_n = d_n;
         p.knn_idx = ctx->d_knn_idx; p.knn_d2 = ctx->d_knn_d2; p.thr = thr; p.d_thr = d_thr; p.W = W; p.H = H;
@@ -2581,6 +2743,48 @@ int stage_classify(aoslo_ctx* ctx, cudaStream_t s, const double* d_g2p, int n_gt
                                                  gt_is_tp, particle_is_fp);
     AOSLO_LAUNCH_CHECK();
     return AOSLO_OK;
+}
+
+int coop_blocks_for_thin(int num_sms) {
+    int per_sm_f = 0, per_sm_d = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, thin_pixels_kernel<float>, kThinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, thin_pixels_kernel<double>, kThinThreads, 0);
+    int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;        // 1024 threads per SM: the grid barrier costs per block
+    return per_sm * num_sms;
+}
+
+// seeds + thinning to the fixpoint of aoslo_run (canonical order, threshold <= 4 px): the survivors land in
+// d_pos / d_stable, their count in *d_n_out (clamped to cap), n_seeds / n_after_thinning / thin_rounds in *ctl
+int stage_thin_pixels(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
+                      double seed_thr, double thin_thr, const RunParams* rp, RunCtl* ctl, double* d_pos,
+                      uint8_t* d_stable, int* d_n_out) {
+    if (H != ctx->H || W != ctx->W || W - 2 * bx <= 0 || H - 2 * by <= 0) return AOSLO_ERR_INVALID;
+    if (!(thin_thr <= 4.0)) return AOSLO_ERR_UNSUPPORTED;
+    ThinParams p;
+    p.H = H; p.W = W; p.bx = bx; p.by = by; p.wpr = occ_words_per_row(W); p.cap = ctx->cap;
+    p.seed_thr = seed_thr; p.thin_thr = thin_thr; p.rp = rp;
+    const size_t nwords = (size_t)H * p.wpr;
+    p.alive = ctx->d_occ;                                   // free until the first resample
+    p.planes = ctx->d_thin;
+    p.pend = ctx->d_thin + (size_t)kThinPlanes * nwords;
+    p.touch = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the first resample
+    p.ctr = ctx->d_thin_ctr;
+    p.ctl = ctl;
+    p.status = ctx->d_status;
+    AOSLO_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(int) * 8, s));
+    int blocks = ctx->coop_blocks_thin;
+    const int need = (int)((nwords + kThinThreads - 1) / kThinThreads);
+    if (need < blocks) blocks = need < 1 ? 1 : need;
+    void* args[] = {&p, (void*)&d_Rb};
+    if (field_dtype == AOSLO_F32)
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<float>, dim3(blocks), dim3(kThinThreads), args, 0, s));
+    else
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<double>, dim3(blocks), dim3(kThinThreads), args, 0, s));
+    count_launch();
+    AliveEmitOp op{ctx->d_occ, p.wpr, (double2*)d_pos, d_stable, ctx->cap, ctx->d_status};
+    return ordered_scan(ctx, s, op, (int)nwords, (int)nwords, nullptr, d_n_out, nullptr, 0, nullptr, ctx->cap);
 }
 
 int coop_blocks_for_delete(int num_sms) {
