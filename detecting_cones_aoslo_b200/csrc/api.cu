@@ -236,6 +236,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_occ_ok, 2));
     A(dmalloc(&c->d_thin, (size_t)7 * H * ((W + 31) / 32 + 2)));
     A(dmalloc(&c->d_thin_ctr, 8));
+    A(dmalloc(&c->d_thin_touch, (size_t)H * W));
     c->coop_blocks_thin = coop_blocks_for_thin(c->num_sms);
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));
@@ -269,7 +270,7 @@ extern "C" int aoslo_ctx_destroy(aoslo_ctx* c) {
     cudaFree(c->d_touch); cudaFree(c->d_del); cudaFree(c->d_rowstate); cudaFree(c->d_force);
     cudaFree(c->d_pos[0]); cudaFree(c->d_pos[1]); cudaFree(c->d_stable[0]); cudaFree(c->d_stable[1]);
     cudaFree(c->d_dist_p2g); cudaFree(c->d_dist_g2p); cudaFree(c->d_partials); cudaFree(c->d_record);
-    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_occ_gt); cudaFree(c->d_occ_ok); cudaFree(c->d_thin); cudaFree(c->d_thin_ctr); cudaFree(c->d_field); cudaFree(c->d_win);
+    cudaFreeHost(c->h_record); cudaFree(c->d_records); cudaFreeHost(c->h_records); cudaFree(c->d_lut); cudaFree(c->d_lut_radial); cudaFree(c->d_lut_flag); cudaFree(c->d_occ); cudaFree(c->d_occ_gt); cudaFree(c->d_occ_ok); cudaFree(c->d_thin); cudaFree(c->d_thin_ctr); cudaFree(c->d_thin_touch); cudaFree(c->d_field); cudaFree(c->d_win);
     kd_free(c->kd); kd_free(c->kd2); cudaFreeHost(c->kd_stage);
     for (int i = 0; i < 12; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);

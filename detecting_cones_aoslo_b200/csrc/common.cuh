@@ -235,6 +235,7 @@ struct aoslo_ctx {
     int* d_occ_ok = nullptr;          // [2] particles / GT: every point is an in-image integer pixel
     uint32_t* d_thin = nullptr;       // [7][H * wpr] pixel-domain thinning: six stencil bit planes + pending rows
     int* d_thin_ctr = nullptr;        // [8] its counters
+    unsigned long long* d_thin_touch = nullptr;   // [H * W] second wavefront stamp buffer (the first lives in d_field)
     int coop_blocks_thin = 0;         // co-resident blocks of thin_pixels_kernel
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles

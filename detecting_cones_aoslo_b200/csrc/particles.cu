@@ -691,8 +691,8 @@ __global__ void __launch_bounds__(kCoopThreads) delete_resolve_kernel(DeletePara
 //     offset, in order, `center & shifted(row y+dy by dx) & ~found`; the offset's number goes into six bit planes;
 //   * wavefront resolution of the greedy walk (utils.py:249-263) exactly as in delete_resolve_kernel: every pending
 //     row stamps both endpoints with (wave, ~pixel) by atomicMax, a row owning both endpoints acts, the victim's bit
-//     is cleared; the waves of all rounds run inside ONE cooperative kernel (grid barriers), a round without a
-//     deletion ends the loop;
+//     is cleared; the waves of all rounds run inside ONE cooperative kernel (one grid barrier per wave, stamp
+//     buffers alternating), a round without a deletion ends the loop;
 //   * the survivors are listed once, at the end (ordered scan over the bitmap words).
 // Replaces, per run: the seed compaction (2 kernels over the R_b field), and per round (5 on the benchmark frame)
 // a pixel-map scatter, a row kernel, the cooperative resolve, a compaction (2 kernels) and a copy.
@@ -720,8 +720,8 @@ struct ThinParams {
     uint32_t* alive;                // [H][wpr] bitmap of the alive pixels, bit x at word 1 + x / 32
     uint32_t* planes;               // [kThinPlanes][H * wpr] stencil number of every pending pixel's neighbour
     uint32_t* pend;                 // [H * wpr] rows still pending in the current round
-    unsigned long long* touch;      // [H * W] wavefront stamps per pixel
-    int* ctr;                       // [8], zero at launch: 0..2 rotating pending counts, 3 deletions, 4 seeds
+    unsigned long long* touch[2];   // [H * W] wavefront stamps per pixel, waves alternate between the two
+    int* ctr;                       // [8], zero at launch: 0..3 rotating pending counts, 4 deletions, 5 seeds
     RunCtl* ctl;
     int* status;
 };
@@ -755,6 +755,59 @@ struct ThinScan<kThinOffsets> {
                                                uint32_t, uint32_t&, uint32_t (&)[kThinPlanes]) {}
 };
 
+// One bitmap word of a wave.  CHECK = false: every pending row of the word stamps its two endpoints for wave `wave`.
+// CHECK = true: every pending row tests whether it owns both endpoints in wave `wave`; an owner acts (the endpoint with
+// the lower blobness dies unless one is dead already, utils.py:257-263) and leaves the pending set, the others stamp
+// for wave + 1.
+template <typename T, bool CHECK>
+__device__ __forceinline__ void thin_wave_word(const ThinParams& p, const T* __restrict__ Rb, int t, int wave,
+                                               int* pending, int* deleted) {
+    const uint32_t pm0 = p.pend[t];
+    if (!pm0) return;
+    const int W = p.W, wpr = p.wpr;
+    const size_t nwords = (size_t)p.H * wpr, fp = fpitch(W);
+    uint32_t pm = pm0, keep = pm0;
+    const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
+    uint32_t pl[kThinPlanes];
+#pragma unroll
+    for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
+    const unsigned long long hi = (unsigned long long)(unsigned)wave << 32;
+    unsigned long long* cur = p.touch[wave & 1];
+    unsigned long long* nxt = p.touch[(wave + 1) & 1];
+    while (pm) {
+        const int b = __ffs((int)pm) - 1;
+        pm &= pm - 1u;
+        int code = 0;
+#pragma unroll
+        for (int k = 0; k < kThinPlanes; ++k) code |= (int)((pl[k] >> b) & 1u) << k;
+        const int dx = c_thin_dx[code], dy = c_thin_dy[code];
+        const int x = x0 + b, pix = y * W + x, q = pix + dy * W + dx;
+        const unsigned long long low = (unsigned long long)(0xffffffffu - (unsigned)pix);
+        if (!CHECK) {
+            atomicMax(&cur[pix], hi | low);
+            atomicMax(&cur[q], hi | low);
+        } else if (__ldcg(&cur[pix]) == (hi | low) && __ldcg(&cur[q]) == (hi | low)) {
+            const int tq = (y + dy) * wpr + 1 + ((x + dx) >> 5), bq = (x + dx) & 31;
+            const bool a_from = (__ldcg(&p.alive[t]) >> b) & 1u;
+            const bool a_to = (__ldcg(&p.alive[tq]) >> bq) & 1u;
+            if (a_from && a_to) {
+                const double e1 = (double)Rb[(size_t)y * fp + x];
+                const double e2 = (double)Rb[(size_t)(y + dy) * fp + x + dx];
+                if (e1 < e2) atomicAnd(&p.alive[t], ~(1u << b));
+                else atomicAnd(&p.alive[tq], ~(1u << bq));
+                ++*deleted;
+            }
+            keep &= ~(1u << b);
+        } else {
+            const unsigned long long key = ((unsigned long long)(unsigned)(wave + 1) << 32) | low;
+            atomicMax(&nxt[pix], key);
+            atomicMax(&nxt[q], key);
+            ++*pending;
+        }
+    }
+    if (CHECK) p.pend[t] = keep;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThinThreads) thin_pixels_kernel(ThinParams p, const T* __restrict__ Rb) {
     cg::grid_group grid = cg::this_grid();
@@ -774,15 +827,15 @@ __global__ void __launch_bounds__(kThinThreads) thin_pixels_kernel(ThinParams p,
             bool sd = false;
             if (x >= p.bx && x < W - p.bx && y >= p.by && y < H - p.by) {
                 sd = (double)Rb[(size_t)y * fp + x] > seed_thr;
-                if (sd) p.touch[(size_t)y * W + x] = 0ull;
+                if (sd) { p.touch[0][(size_t)y * W + x] = 0ull; p.touch[1][(size_t)y * W + x] = 0ull; }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, sd);
             if (lane == 0) { p.alive[t] = m; nseed += __popc(m); }
         }
-        if (nseed) atomicAdd(&p.ctr[4], nseed);
+        if (nseed) atomicAdd(&p.ctr[5], nseed);
     }
     grid.sync();
-    const int n_seeds = __ldcg(&p.ctr[4]);
+    const int n_seeds = __ldcg(&p.ctr[5]);
     int lim = 0;                                  // offsets with d^2 < thr^2 (exact: small integers)
     {
         const double thr2 = thin_thr * thin_thr;
@@ -818,82 +871,31 @@ __global__ void __launch_bounds__(kThinThreads) thin_pixels_kernel(ThinParams p,
 #pragma unroll
             for (int b = 0; b < kThinPlanes; ++b) p.planes[(size_t)b * nwords + t] = pl[b];
         }
-        // ---- wavefront rounds of this thinning round (phase R wrote only this thread's own words)
+        // ---- wavefront rounds of this thinning round.  One grid barrier per wave: a row that is still pending after
+        // its check of wave w stamps for wave w+1 right away, into the OTHER stamp buffer (checks of wave w read buffer
+        // w & 1, which nobody writes between the two barriers); "rows pending after wave w" is read after the next
+        // barrier.  Stamps carry the wave number, so the stale ones of wave w-1 in a buffer lose against wave w+1.
+        const int w_first = wave + 1;
+        for (int t = tid; t < nwords; t += nthr) thin_wave_word<T, false>(p, Rb, t, wave + 1, nullptr, nullptr);
         for (;;) {
             ++wave;
-            const unsigned long long hi = (unsigned long long)(unsigned)wave << 32;
-            for (int t = tid; t < nwords; t += nthr) {
-                uint32_t pm = p.pend[t];
-                if (!pm) continue;
-                const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
-                uint32_t pl[kThinPlanes];
-#pragma unroll
-                for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
-                while (pm) {
-                    const int b = __ffs((int)pm) - 1;
-                    pm &= pm - 1u;
-                    int code = 0;
-#pragma unroll
-                    for (int k = 0; k < kThinPlanes; ++k) code |= (int)((pl[k] >> b) & 1u) << k;
-                    const int pix = y * W + x0 + b;
-                    const int q = pix + c_thin_dy[code] * W + c_thin_dx[code];
-                    const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)pix);
-                    atomicMax(&p.touch[pix], key);
-                    atomicMax(&p.touch[q], key);
-                }
-            }
-            if (tid == 0) p.ctr[(wave + 1) % 3] = 0;
+            if (tid == 0) p.ctr[(wave + 1) & 3] = 0;     // added to during wave - 3, read during wave - 2
             if (threadIdx.x == 0) { s_pending = 0; s_deleted = 0; }
             grid.sync();
+            if (wave > w_first && __ldcg(&p.ctr[(wave - 1) & 3]) == 0) break;   // nothing was stamped for this wave
+            if (wave - w_first >= kThinMaxWaves) { overflow = true; break; }
             int pending = 0, deleted = 0;
-            for (int t = tid; t < nwords; t += nthr) {
-                const uint32_t pm0 = p.pend[t];
-                if (!pm0) continue;
-                uint32_t pm = pm0, keep = pm0;
-                const int y = t / wpr, x0 = (t - y * wpr - 1) * 32;
-                uint32_t pl[kThinPlanes];
-#pragma unroll
-                for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
-                while (pm) {
-                    const int b = __ffs((int)pm) - 1;
-                    pm &= pm - 1u;
-                    int code = 0;
-#pragma unroll
-                    for (int k = 0; k < kThinPlanes; ++k) code |= (int)((pl[k] >> b) & 1u) << k;
-                    const int dx = c_thin_dx[code], dy = c_thin_dy[code];
-                    const int x = x0 + b, pix = y * W + x, q = pix + dy * W + dx;
-                    const unsigned long long key = hi | (unsigned long long)(0xffffffffu - (unsigned)pix);
-                    if (__ldcg(&p.touch[pix]) == key && __ldcg(&p.touch[q]) == key) {
-                        const int tq = (y + dy) * wpr + 1 + ((x + dx) >> 5), bq = (x + dx) & 31;
-                        const bool a_from = (__ldcg(&p.alive[t]) >> b) & 1u;
-                        const bool a_to = (__ldcg(&p.alive[tq]) >> bq) & 1u;
-                        if (a_from && a_to) {
-                            const double e1 = (double)Rb[(size_t)y * fp + x];
-                            const double e2 = (double)Rb[(size_t)(y + dy) * fp + x + dx];
-                            if (e1 < e2) atomicAnd(&p.alive[t], ~(1u << b));
-                            else atomicAnd(&p.alive[tq], ~(1u << bq));
-                            ++deleted;
-                        }
-                        keep &= ~(1u << b);
-                    } else {
-                        ++pending;
-                    }
-                }
-                p.pend[t] = keep;
-            }
+            for (int t = tid; t < nwords; t += nthr) thin_wave_word<T, true>(p, Rb, t, wave, &pending, &deleted);
             if (pending) atomicAdd(&s_pending, pending);
             if (deleted) atomicAdd(&s_deleted, deleted);
             __syncthreads();
             if (threadIdx.x == 0) {
-                if (s_pending) atomicAdd(&p.ctr[wave % 3], s_pending);
-                if (s_deleted) atomicAdd(&p.ctr[3], s_deleted);
+                if (s_pending) atomicAdd(&p.ctr[wave & 3], s_pending);
+                if (s_deleted) atomicAdd(&p.ctr[4], s_deleted);
             }
-            grid.sync();
-            if (__ldcg(&p.ctr[wave % 3]) == 0) break;
-            if (wave >= kThinMaxWaves) { overflow = true; break; }
         }
         ++rounds;
-        const int deleted_total = __ldcg(&p.ctr[3]);
+        const int deleted_total = __ldcg(&p.ctr[4]);
         const bool none = deleted_total == deleted_before;
         deleted_before = deleted_total;
         if (none || overflow) break;
@@ -2751,7 +2753,11 @@ int coop_blocks_for_thin(int num_sms) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, thin_pixels_kernel<double>, kThinThreads, 0);
     int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;        // 1024 threads per SM: the grid barrier costs per block
+    // one 512-thread block per SM by default: the grid barrier costs per block, and 28 k registers per SM leave room
+    // for the kernels of the other lanes (two blocks take 57 k of the 64 k)
+    int want = 1;
+    if (const char* e = getenv("AOSLO_THIN_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 4) want = v; }
+    if (per_sm > want) per_sm = want;
     return per_sm * num_sms;
 }
 
@@ -2769,7 +2775,8 @@ int stage_thin_pixels(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int fiel
     p.alive = ctx->d_occ;                                   // free until the first resample
     p.planes = ctx->d_thin;
     p.pend = ctx->d_thin + (size_t)kThinPlanes * nwords;
-    p.touch = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the first resample
+    p.touch[0] = reinterpret_cast<unsigned long long*>(ctx->d_field);   // free until the first resample
+    p.touch[1] = ctx->d_thin_touch;
     p.ctr = ctx->d_thin_ctr;
     p.ctl = ctl;
     p.status = ctx->d_status;
