@@ -299,6 +299,7 @@ class Lane:
         self.k1_events = []
         self.last = None
         self.collect_times = False       # stage timings off: aoslo_run replays its cached CUDA graph
+        self._gt_steps = []
 
     def run_resident(self, time_k1=False):
         """frame + GT resident in HBM: aoslo_blobness + aoslo_run (the whole loop)."""
@@ -320,13 +321,23 @@ class Lane:
         self.last = (summ, recs, ms)
         return summ
 
-    def run_e2e(self, **over):
+    def run_e2e(self, gt_host=None, **over):
         """the reference-facing call with HOST buffers (H2D of the raw frame + GT, device crop/pad, run, D2H of the
         records)."""
         from detecting_cones_aoslo_b200.pipeline_with_delitions import find_blobs
+        gt_host = self.gt_scratch if gt_host is None else gt_host
         with self.torch.cuda.stream(self.stream):
-            res, _ = find_blobs(dict(self.cfg, **over), self.gt_scratch, self.img, None, False, False, engine=self.eng)
+            res, _ = find_blobs(dict(self.cfg, **over), gt_host, self.img, None, False, False, engine=self.eng)
         return res
+
+    def prep_e2e_steps(self, k):
+        """host inputs of k consecutive end-to-end steps without a barrier in between: k pinned GT copies (find_blobs
+        shifts its GT argument in place), made before the timed region"""
+        while len(self._gt_steps) < k:
+            self._gt_steps.append(self.torch.from_numpy(self.gt.copy()).pin_memory())
+        for t in self._gt_steps[:k]:
+            np.copyto(t.numpy(), self.gt)
+        return [t.numpy() for t in self._gt_steps[:k]]
 
     def prep_e2e(self):
         """this step's host input: find_blobs shifts the caller's GT array in place (reference :26), so the bench
@@ -422,6 +433,30 @@ def run_gpu(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
+    def timed_steps(fn, active, k):
+        """k steps back to back inside ONE bracket (the contract's form): every lane runs its k frames one after the
+        other, no barrier and no L2 flush between steps -- the lanes' working sets (8 x ~250 MB written per run)
+        are far larger than the 126 MB L2, so every run reads its frame from HBM.  fn(lane, step_index).  Returns
+        device ms of the whole region (CUDA events on `main`, lane streams forked from / joined to it)."""
+        evict_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for ln in active:
+            ln.stream.wait_event(e0)
+
+        def loop(ln):
+            for i in range(k):
+                fn(ln, i)
+        for f in [pool.submit(loop, ln) for ln in active]:
+            f.result()
+        for ln in active:
+            d = torch.cuda.Event()
+            d.record(ln.stream)
+            main.wait_event(d)
+        e1.record(main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
     # ---- warm-up (all lanes), then the throughput pass: K steps of B concurrent runs
     sampler = ClockSampler(local)
     sampler.start()
@@ -430,6 +465,9 @@ def run_gpu(args):
     barrier()
     t_timed = time.perf_counter()
     launches0 = _lib.lib.aoslo_launch_count()
+    region_ms = timed_steps(lambda ln, i: ln.run_resident(), lanes, args.steps)
+    launches_region = _lib.lib.aoslo_launch_count() - launches0
+    # the same K steps one by one, a barrier + L2 flush between them (how rounds 1 / 2 timed the step): `stepwise`
     step_ms = [timed_step(lambda ln: ln.run_resident(), lanes) for _ in range(args.steps)]
     # the sweep's only exchange: all-gather of the per-run metric records (tiny, latency only)
     rows = []
@@ -448,14 +486,15 @@ def run_gpu(args):
         gathered = [rec_t]
     g1.record()
     barrier()
-    launches = _lib.lib.aoslo_launch_count() - launches0
+    launches = launches_region
     clocks = sampler.stop(t_timed)
-    total_ms = float(sum(step_ms)) + g0.elapsed_time(g1)
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    tt = torch.tensor([region_ms + g0.elapsed_time(g1), float(sum(step_ms)) + g0.elapsed_time(g1)],
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt.item())
+    total_ms, stepwise_ms = float(tt[0].item()), float(tt[1].item())
     value = world * args.steps * B / (total_ms / 1e3)
+    value_stepwise = world * args.steps * B / (stepwise_ms / 1e3)
 
     # ---- latency pass: one lane alone (single stream, spinning waits), K1 timed inside the step
     lane0 = lanes[0]
@@ -475,11 +514,15 @@ def run_gpu(args):
     for _ in range(min(2, args.warmup)):
         timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e)
     barrier()
+    gt_steps = {id(ln): ln.prep_e2e_steps(args.steps) for ln in lanes}       # untimed, like the L2 flush
+    e2e_region_ms = timed_steps(lambda ln, i: ln.run_e2e(gt_steps[id(ln)][i]), lanes, args.steps)
+    barrier()
     e2e_ms = [timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e) for _ in range(args.steps)]
-    te = torch.tensor([float(sum(e2e_ms))], dtype=torch.float64, device=dev)
+    te = torch.tensor([e2e_region_ms, float(sum(e2e_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * B / (float(te.item()) / 1e3)
+    e2e_value = world * args.steps * B / (float(te[0].item()) / 1e3)
+    e2e_stepwise = world * args.steps * B / (float(te[1].item()) / 1e3)
     e2e_lat = [timed_step(lambda ln: ln.run_e2e(), [lane0], Lane.prep_e2e) for _ in range(args.steps)]
     d2h = summ.n_records * 88 + 32 + 4
 
@@ -596,17 +639,27 @@ def run_gpu(args):
                        "tie_order": "canonical (distance, index) order: the all-GPU mode, pinned by the oracle's canonical "
                                     "variant (same order in the CPU arm); the as-is reference order (sklearn KD tree) "
                                     "is the `faithful` key",
-                       "step": "one step = %d frames run concurrently (one CUDA stream + context each)" % B,
+                       "step": "one step = %d frames run concurrently (one CUDA stream + context each); the K timed "
+                               "steps run back to back inside one barrier + synchronize bracket (every lane runs its "
+                               "K frames one after the other); `stepwise` = the same K steps with a barrier and an L2 "
+                               "flush after every step (the timing of rounds 1 / 2)" % B,
                        "padded_shape": [H, W], "n_gt": lane0.n_gt,
                        "n_particles_final": int(summ.n_particles), "n_seeds": int(summ.n_seeds),
                        "iterations": int(summ.n_iterations), "thinning_rounds": int(summ.n_thinning_rounds),
-                       "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "l2": "inputs larger than L2: %d lanes x ~250 MB written per run >> 126 MB, so every run reads its "
+                             "frame from HBM (e2e: from the host); flushed before the region and between the "
+                             "`stepwise` steps (256 MiB write, untimed)" % B,
                        "parallelism": "one frame per lane, %d lanes per rank, NCCL all-gather of metric records" % B,
                        "host": {"cores": cores, "wait_policy": {"": "spin (default)", "1": "spin", "2": "yield",
                                                                  "3": "blocking"}.get(policy, policy),
                                 "cores_of_this_rank": (len(os.sched_getaffinity(0))
                                                        if hasattr(os, "sched_getaffinity") else cores)}},
             "clocks": clocks,
+            "stepwise": {"value": value_stepwise, "e2e": e2e_stepwise, "unit": "runs/s",
+                         "ms_per_step": stepwise_ms / args.steps,
+                         "what": "barrier + L2 flush after every step: the ramp (host->device copies of all lanes "
+                                 "queue up before the first kernel) and the tail (the last lane finishes alone) of "
+                                 "every step are inside"},
             "latency_ms_single_run": latency_ms,
             "e2e": {"value": e2e_value, "unit": "runs/s", "h2d_bytes_per_step": int(lane0.h2d * B),
                     "d2h_bytes_per_step": int(d2h * B), "latency_ms_single_run": float(np.mean(e2e_lat))},

@@ -237,6 +237,7 @@ struct aoslo_ctx {
     int* d_thin_ctr = nullptr;        // [8] its counters
     unsigned long long* d_thin_touch = nullptr;   // [H * W] second wavefront stamp buffer (the first lives in d_field)
     int coop_blocks_thin = 0;         // co-resident blocks of thin_pixels_kernel
+    int thin_threads = 128;           // its block size (AOSLO_THIN_THREADS, read once at context creation)
     double* d_field = nullptr;        // [H*W]
     int32_t* d_win = nullptr;         // [H*W] window candidates of adding_particles
     aoslo::KdTreeDev kd, kd2;         // two cached trees (sklearn-order tie mode): typically particles and GT
@@ -435,7 +436,8 @@ int stage_dual_count_stable(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t* d_stable, int n, uint8_t v, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t* d_stable, int n, int* d_out, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
-int coop_blocks_for_thin(int num_sms);
+int thin_threads_default();
+int coop_blocks_for_thin(int num_sms, int threads);
 int stage_thin_pixels(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
                       double seed_thr, double thin_thr, const RunParams* rp, RunCtl* ctl, double* d_pos,
                       uint8_t* d_stable, int* d_n_out);

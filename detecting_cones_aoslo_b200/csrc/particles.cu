@@ -772,8 +772,8 @@ __device__ __forceinline__ void thin_wave_word(const ThinParams& p, const T* __r
 #pragma unroll
     for (int b = 0; b < kThinPlanes; ++b) pl[b] = p.planes[(size_t)b * nwords + t];
     const unsigned long long hi = (unsigned long long)(unsigned)wave << 32;
-    unsigned long long* cur = p.touch[wave & 1];
-    unsigned long long* nxt = p.touch[(wave + 1) & 1];
+    unsigned long long* cur = (wave & 1) ? p.touch[1] : p.touch[0];      // no dynamic index into the parameters
+    unsigned long long* nxt = (wave & 1) ? p.touch[0] : p.touch[1];
     while (pm) {
         const int b = __ffs((int)pm) - 1;
         pm &= pm - 1u;
@@ -2747,15 +2747,22 @@ int stage_classify(aoslo_ctx* ctx, cudaStream_t s, const double* d_g2p, int n_gt
     return AOSLO_OK;
 }
 
-int coop_blocks_for_thin(int num_sms) {
+int thin_threads_default() {
+    // 2 x 128 threads per SM: the smaller the footprint of the cooperative kernel, the more of the other lanes'
+    // kernels run beside it (8 lanes, runs/s resident: 512 x 1: 1 308, 256 x 2: 1 293, 256 x 1: 1 350, 128 x 2:
+    // 1 353; single-run latency 2.03 / 2.02 / 2.15 / 2.16 ms)
+    int t = 128;
+    if (const char* e = getenv("AOSLO_THIN_THREADS")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) t = v; }
+    return t;
+}
+
+int coop_blocks_for_thin(int num_sms, int threads) {
     int per_sm_f = 0, per_sm_d = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, thin_pixels_kernel<float>, kThinThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, thin_pixels_kernel<double>, kThinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, thin_pixels_kernel<float>, threads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, thin_pixels_kernel<double>, threads, 0);
     int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
     if (per_sm < 1) per_sm = 1;
-    // one 512-thread block per SM by default: the grid barrier costs per block, and 28 k registers per SM leave room
-    // for the kernels of the other lanes (two blocks take 57 k of the 64 k)
-    int want = 1;
+    int want = 2;
     if (const char* e = getenv("AOSLO_THIN_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v <= 4) want = v; }
     if (per_sm > want) per_sm = want;
     return per_sm * num_sms;
@@ -2782,13 +2789,14 @@ int stage_thin_pixels(aoslo_ctx* ctx, cudaStream_t s, const void* d_Rb, int fiel
     p.status = ctx->d_status;
     AOSLO_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(int) * 8, s));
     int blocks = ctx->coop_blocks_thin;
-    const int need = (int)((nwords + kThinThreads - 1) / kThinThreads);
+    const int threads = ctx->thin_threads;
+    const int need = (int)((nwords + threads - 1) / threads);
     if (need < blocks) blocks = need < 1 ? 1 : need;
     void* args[] = {&p, (void*)&d_Rb};
     if (field_dtype == AOSLO_F32)
-        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<float>, dim3(blocks), dim3(kThinThreads), args, 0, s));
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<float>, dim3(blocks), dim3(threads), args, 0, s));
     else
-        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<double>, dim3(blocks), dim3(kThinThreads), args, 0, s));
+        AOSLO_CUDA(cudaLaunchCooperativeKernel((void*)thin_pixels_kernel<double>, dim3(blocks), dim3(threads), args, 0, s));
     count_launch();
     AliveEmitOp op{ctx->d_occ, p.wpr, (double2*)d_pos, d_stable, ctx->cap, ctx->d_status};
     return ordered_scan(ctx, s, op, (int)nwords, (int)nwords, nullptr, d_n_out, nullptr, 0, nullptr, ctx->cap);
