@@ -61,7 +61,6 @@ def main():
         ("M=30, metrics at iteration 0 only", dict(metric_measure_freq=1000)),
         ("M=30, no resample in the loop", dict(fix_particles_frequency=1000)),
         ("M=30, no resample, metrics at iteration 0 only", dict(fix_particles_frequency=1000, metric_measure_freq=1000)),
-        ("seed threshold 5.3 (few seeds: thinning nearly free)", dict(init_blob_threshold=5.3)),
     ]
     out = {}
     for name, over in variants:
