@@ -237,7 +237,7 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     A(dmalloc(&c->d_thin, (size_t)7 * H * ((W + 31) / 32 + 2)));
     A(dmalloc(&c->d_thin_ctr, 8));
     A(dmalloc(&c->d_thin_touch, (size_t)H * W));
-    c->thin_threads = thin_threads_default();
+    c->thin_threads = thin_threads_default(H, W, c->num_sms);
     c->coop_blocks_thin = coop_blocks_for_thin(c->num_sms, c->thin_threads);
     A(dmalloc(&c->d_field, (size_t)H * W));
     A(dmalloc(&c->d_win, (size_t)H * W));

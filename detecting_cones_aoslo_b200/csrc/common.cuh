@@ -436,7 +436,7 @@ int stage_dual_count_stable(aoslo_ctx*, cudaStream_t, int n_bound, const int* d_
 int stage_set_stable(aoslo_ctx*, cudaStream_t, uint8_t* d_stable, int n, uint8_t v, const int* d_n);
 int stage_count_stable(aoslo_ctx*, cudaStream_t, const uint8_t* d_stable, int n, int* d_out, const int* d_n);
 int coop_blocks_for_delete(int num_sms);
-int thin_threads_default();
+int thin_threads_default(int H, int W, int num_sms);
 int coop_blocks_for_thin(int num_sms, int threads);
 int stage_thin_pixels(aoslo_ctx*, cudaStream_t, const void* d_Rb, int field_dtype, int H, int W, int bx, int by,
                       double seed_thr, double thin_thr, const RunParams* rp, RunCtl* ctl, double* d_pos,
