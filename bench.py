@@ -49,7 +49,7 @@ WORKLOADS = {
                     metric="detection runs/s (full pipeline, 2048^2 image)"),
     'cfg2': dict(size=1024, pitch=11.0, epochs=100, scales=(1.0, 1.5, 2.0, 2.5, 3.0), lanes=8,
                  metric="detection runs/s (cfg2: 1024^2, 5 blobness scales, M=100)"),
-    'cfg3': dict(size=4096, pitch=11.4, epochs=30, scales=(1.0,), lanes=2,
+    'cfg3': dict(size=4096, pitch=11.4, epochs=30, scales=(1.0,), lanes=4,
                  metric="detection runs/s (cfg3: 4096^2 montage)"),
     'batch': dict(size=512, pitch=5.8, epochs=30, scales=(1.0,), lanes=8, units=256,
                   metric="frames/s (cfg4: batch of 256 synthetic 512^2 frames, sharded by image)"),

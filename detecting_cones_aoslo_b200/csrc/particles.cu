@@ -2751,10 +2751,10 @@ int thin_threads_default(int H, int W, int num_sms) {
     // Two blocks per SM; block size by bitmap words per SM, about four words per thread.  The smaller the footprint
     // of the cooperative kernel, the more of the other lanes' kernels run beside it (2077^2, 8 lanes, runs/s
     // resident: 512 x 1: 1 308, 256 x 2: 1 293, 256 x 1: 1 350, 128 x 2: 1 353; single-run latency 2.03 / 2.02 /
-    // 2.15 / 2.16 ms) -- but a 4126^2 frame on 2 x 128 threads per SM walks 14 words per thread (6.0 ms per run
-    // instead of 4.3).
+    // 2.15 / 2.16 ms) -- but a 4126^2 frame on 2 x 128 threads per SM walks 14 words per thread (4126^2, 2 lanes,
+    // block size 128 / 256 / 512: 235 / 265 / 254 runs/s, 6.03 / 5.09 / 4.70 ms; 4 lanes: 256 -> 282, 512 -> 269).
     const long long words_per_sm = ((long long)H * occ_words_per_row(W) + num_sms - 1) / (num_sms > 0 ? num_sms : 1);
-    int t = words_per_sm <= 1024 ? 128 : (words_per_sm <= 2048 ? 256 : 512);
+    int t = words_per_sm <= 1024 ? 128 : 256;
     if (const char* e = getenv("AOSLO_THIN_THREADS")) { int v = atoi(e); if (v == 128 || v == 256 || v == 512) t = v; }
     return t;
 }
