@@ -254,8 +254,6 @@ extern "C" int aoslo_ctx_create(aoslo_ctx** out, int device, int H, int W, int p
     if (st == AOSLO_OK && cudaMemset(c->d_touch, 0, sizeof(unsigned long long) * cap) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st == AOSLO_OK) { unsigned int one = 1u; if (cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice) != cudaSuccess) st = AOSLO_ERR_CUDA; }
     if (st == AOSLO_OK && cudaMemset(c->d_counters, 0, sizeof(int) * 32) != cudaSuccess) st = AOSLO_ERR_CUDA;
-    // d_field doubles as the thinning rounds' pixel map ((tag << 32) | index words): tag 0 is never valid
-    if (st == AOSLO_OK && cudaMemset(c->d_field, 0, sizeof(double) * (size_t)H * W) != cudaSuccess) st = AOSLO_ERR_CUDA;
     if (st != AOSLO_OK) { aoslo_ctx_destroy(c); return st; }
     *out = c;
     return AOSLO_OK;
@@ -541,7 +539,8 @@ extern "C" int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* c
 // adding, the epoch loop, the final reads -- is ONE CUDA graph with no host decision inside.  The
 // particles always live in buffer 0 (the compaction of a step reads the moved copies); the count is a
 // device scalar; every decision the reference takes in Python is taken by a one-thread kernel:
-//   * thinning `while deleted: del_close_particles(thr=3)` (:115-120)  -> WHILE conditional graph node;
+//   * seeds + thinning `while deleted: del_close_particles(thr=3)` (:101-120) -> one cooperative kernel on a bitmap of
+//     alive pixels (stage_thin_pixels); thinning thresholds above 4 px: a WHILE conditional graph node of thinning rounds;
 //   * the epoch loop -> unrolled kernel nodes when the early stop is off; with the early stop (:381-382) a
 //     WHILE node whose body carries IF nodes for the resample (:256) and metrics (:320) branches;
 //   * all value parameters (thresholds, lambdas, energy parameters, frequencies, GT count) are read from a

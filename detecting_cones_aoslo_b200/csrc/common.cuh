@@ -97,7 +97,7 @@ constexpr int kLinkBiasDense = 6;     // link_shift_for bias: thinning rounds (d
 constexpr int kLinkBiasSteady = 3;    // steady state of the loop / metrics
 
 // ---- whole-run control block (device resident, mirrored to pinned memory once at the end of a run) ----
-// aoslo_run enqueues seeding, thinning (a WHILE conditional graph node), resampling and the epoch loop
+// aoslo_run enqueues seeding + thinning (one cooperative kernel on the alive-pixel bitmap), resampling and the epoch loop
 // (unrolled, or a WHILE node with IF nodes for the resample / metrics branches when the early stop is on)
 // as ONE CUDA graph; every decision the reference takes on the host is taken by a 1-thread kernel here.
 struct RunCtl {

@@ -3,14 +3,14 @@
 // because the loop's decisions are discrete and amplify rounding differences).
 //
 // Kernels (reference file:line each one replaces):
-//   cell_count / cell_scatter        uniform-grid cell list (replaces sklearn KDTree.fit, utils.py:29, :218)
+//   cell_count / cell_scatter        uniform-grid cell list of the ground truth (replaces sklearn KDTree.fit, utils.py:218)
 //   knn_cells_kernel                 exact kNN, canonical (d^2, index) order          (utils.py:30, :219)
 //   knn_sklearn_kernel               exact kNN in sklearn's depth-first tie order     (same call sites)
 //   seed (ordered compaction)        utils.initialize_high_prop_location             (utils.py:359-375)
 //   delete_resolve_kernel            utils.del_close_particles greedy loop           (utils.py:249-263)
 //   keep-compaction                  utils.del_close_particles compaction            (utils.py:265-273)
 //   dist_lut_kernel                  utils.get_precomputed_dist_func                 (utils.py:95-109)
-//   gravity_field_kernel             utils.calc_gravity_field_optim                  (utils.py:310-333)
+//   gravity_nearest / gravity_bits   utils.calc_gravity_field_optim                  (utils.py:310-333)
 //   window_argmin_kernel + append    utils.adding_particles                          (utils.py:336-356)
 //   dist_force_kernel                utils.calc_dist_energy_pit(_optim) / calc_dist_energy (utils.py:112-134, :43-58)
 //   move_kernel                      the move step                 (pipeline_with_delitions.py:215-245)
@@ -18,7 +18,8 @@
 //                                    calc_metrics('Chamfer'), calc_blob_energy (utils.py:214-242, :378-418, :137-144)
 // The whole-run loop of aoslo_run (canonical tie order) works on a tombstone + two-structure layout of the same
 // arithmetic (period_begin / dual_force_move / ns_relink / dual_rows / dual_metrics, "The run loop's particle
-// structure" below); its thinning rounds find their neighbours through a pixel map (thin_map_*).
+// structure" below); its seeds + thinning rounds run in the pixel domain (thin_pixels_kernel), its gravity field and
+// metrics distances come from occupancy bitmaps (gravity_nearest_kernel, occ_nearest_d2).
 #include <cooperative_groups.h>
 
 #include "common.cuh"

@@ -249,8 +249,9 @@ int aoslo_iterate(aoslo_ctx* ctx, void* stream, const aoslo_config* cfg, const v
  * per-evaluation metric records, the final particles and a summary.  Stage timings (ms) in
  * h_stage_ms[5] (may be NULL): dist_energy_calc, moving_particles, deleting_particles, fix_resample,
  * metrics_logging (the reference's `time_spended` keys, :165-171).
- * AOSLO_TIE_CANONICAL: the whole run is one cached CUDA graph (conditional WHILE / IF nodes for the thinning
- * fixpoint, the early stop and the resample / metrics branches); the host synchronises once, at the end.
+ * AOSLO_TIE_CANONICAL: the whole run is one cached CUDA graph (seeds + thinning to the fixpoint in one cooperative
+ * kernel on a bitmap of alive pixels; conditional WHILE / IF nodes for the early stop and the resample / metrics
+ * branches); the host synchronises once, at the end.
  * All value parameters of `cfg` are uploaded per call, so runs that differ only in values (a sweep) share the
  * graph; d_Rb, d_grad, d_gt must be stable addresses for the graph to be reused.
  * AOSLO_TIE_SKLEARN: stage calls with one host round trip per kNN (host-built tree).

@@ -1,8 +1,9 @@
 """SASS mnemonic counts per kernel of the built library (cuobjdump -sass): the static evidence for the Blackwell
 specific instructions (UTMALDG / UTMASTG = TMA tensor load / store, FFMA2 / FADD2 / FMUL2 = packed FP32,
-VIMNMX = the gravity gather's per-halfword maximum) and for what each kernel is made of.
+VIMNMX / VIADDMNMX = per-halfword maximum / min(a + b, c), the column pass of the gravity distance transform; FLO / SHF =
+the bit scans and funnel shifts of the bitmap kernels) and for what each kernel is made of.
 
-    python scripts/sass_table.py > profiles/r02_sass.md
+    python scripts/sass_table.py > profiles/r02c_sass.md
 """
 import collections
 import os
@@ -12,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "detecting_cones_aoslo_b200", "libaoslo_b200.so")
-WANT = ['UTMALDG', 'UTMASTG', 'FFMA2', 'FADD2', 'FMUL2', 'VIMNMX', 'DFMA', 'DADD', 'DMUL', 'MUFU', 'LDS', 'STS',
+WANT = ['UTMALDG', 'UTMASTG', 'FFMA2', 'FADD2', 'FMUL2', 'VIMNMX', 'VIADDMNMX', 'FLO', 'SHF', 'DFMA', 'DADD', 'DMUL', 'MUFU', 'LDS', 'STS',
         'ATOMG', 'SYNCS', 'LDGSTS', 'BAR']
 
 
@@ -33,7 +34,7 @@ def main():
         short = re.sub(r'\(.*', '', name).replace('void ', '').replace('aoslo::', '')
         rows.append((short, sum(counts[mangled].values()), counts[mangled]))
     rows.sort(key=lambda r: -r[1])
-    print("# r02: SASS mnemonics per kernel (`cuobjdump -sass libaoslo_b200.so`, sm_100a; static instruction counts)\n")
+    print("# r02c: SASS mnemonics per kernel (`cuobjdump -sass libaoslo_b200.so`, sm_100a; static instruction counts)\n")
     print("| kernel | SASS instr | " + " | ".join(WANT) + " |")
     print("|---|---:|" + "---:|" * len(WANT))
     for short, tot, c in rows:
