@@ -1,8 +1,7 @@
+# last GPU call of the round: the parity suite on the final build, the default bench, one full ncu capture of the thinning kernel
 set -x
-for cfg in "128 2" "256 2" "512 2" "256 4" "512 4"; do
-set -- $cfg
-AOSLO_THIN_THREADS=$1 timeout 300 python bench.py --workload cfg3 --batch $2 --steps 5 --warmup 3 --no-cpu --no-faithful > gpurun_out/bench_cfg3_$1_$2.json 2> gpurun_out/bench_cycle.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/bench_cfg3_$1_$2.json').read().strip().splitlines()[-1]);print('thin threads $1 lanes $2:', d['value'], d['stepwise']['value'], d['latency_ms_single_run'], d['e2e']['value'], d['e2e']['latency_ms_single_run'])"
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_r2c_final2.json 2> gpurun_out/bench_r2c_final2.err
+tail -2 gpurun_out/bench_r2c_final2.err
+AOSLO_NO_GRAPH=1 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"thin_pixels" -c 1 -f -o gpurun_out/r02c_thin python bench.py --steps 1 --warmup 1 --no-cpu --no-faithful --batch 1 > gpurun_out/ncu_thin.log 2>&1
+tail -2 gpurun_out/ncu_thin.log

@@ -948,6 +948,41 @@ def test_run_graph_equals_eager_path(early_stop):
     eng_e.close()
 
 
+@pytest.mark.parametrize("no_graph", [0, 1])
+def test_seeds_and_thinning_in_the_pixel_domain_match_oracle(no_graph, zoo_field):
+    """aoslo_run's seeds + thinning to the fixpoint: the cooperative pixel-domain kernel (thinning threshold <= 4 px:
+    bit-plane stencil of 8 / 24 / 36 / 44 offsets, wavefront rounds with alternating stamp buffers) and the WHILE-node
+    fallback of index-domain rounds (threshold > 4 px), in the graph and on the eager path, f64 and f32 fields,
+    against the oracle's loop `while deleted: del_close_particles(thr)` (reference :115-120): seed count, survivors
+    after the fixpoint, number of rounds -- and, with no iterations after it, the survivors themselves."""
+    from detecting_cones_aoslo_b200.engine import Engine
+    from detecting_cones_aoslo_b200.pipeline_with_delitions import make_config_struct
+    cfg, img, gt, Rb, grad = zoo_field
+    H, W = img.shape
+    eng = Engine(H, W, gt_capacity=max(65536, gt.shape[0]))
+    eng.set_tuning(no_graph=no_graph)
+    d_gt = eng.dev(gt, torch.float64)
+    for fdt in (torch.float64, torch.float32):
+        d_rb, d_grad = eng.blobness(eng.upload_image(img), 'custom', 'np_grad', (1.0,), fdt)
+        rb_host = d_rb.cpu().numpy().astype(np.float64)        # the decisions read the stored values, widened
+        for thr, seed_thr in ((3.0, 5.0), (2.0, 4.95), (3.5, 5.0), (4.0, 5.01), (4.5, 5.0)):
+            c = configs.variant(cfg, tie_mode='canonical', init_blob_threshold=seed_thr, epoch_num=1, early_stop=False)
+            p = orc.initialize_high_prop_location(rb_host, seed_thr, rb_host.shape, c)
+            n_seeds, st, rounds = p.shape[0], [0] * p.shape[0], 0
+            while True:
+                p, deleted, st = orc.del_close_particles(p, st, rb_host, c, threshold_dist=thr, tie_mode='canonical')
+                rounds += 1
+                if int(np.sum(deleted)) == 0:
+                    break
+            cs = make_config_struct(c, H, W)
+            cs.thinning_threshold = thr
+            eng.clear_status()
+            summ, recs, pos, stab, ms = eng.run(cs, d_rb, d_grad, d_gt, collect_times=False)
+            assert summ.status == 0
+            assert (summ.n_seeds, summ.n_after_thinning, summ.n_thinning_rounds) == (n_seeds, p.shape[0], rounds), thr
+    eng.close()
+
+
 def test_run_capacity_overflow_is_reported_not_corrupting():
     """A context with too small a particle capacity: the device count is clamped where it is produced, the run
     reports MemoryError, and nothing is written past the buffers (a later run on a proper context still agrees
