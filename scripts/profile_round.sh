@@ -12,8 +12,8 @@ AOSLO_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 22
     --log-file gpurun_out/launches_r02.csv $B > gpurun_out/ncu_launches.log 2>&1
 # 3. full captures of the top kernels
 AOSLO_NO_GRAPH=1 ncu --set full --clock-control none --import-source on \
-    -k regex:"dual_metrics|dual_force_move|dual_rows|gravity_field|thin_map_rows|ns_relink|period_begin|delete_resolve_kernel" \
-    --launch-skip 12 -c 14 -f -o gpurun_out/r02_kernels $B > gpurun_out/ncu_kernels.log 2>&1
+    -k regex:"thin_pixels|dual_metrics|dual_force_move|dual_rows|gravity_nearest|occ_scatter|window_argmin|ns_relink|period_begin" \
+    --launch-skip 0 -c 16 -f -o gpurun_out/r02_kernels $B > gpurun_out/ncu_kernels.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"blobness_dtile|blobness_pair" --launch-skip 6 -c 2 -f \
     -o gpurun_out/r02_k1 python scripts/k1_bench.py --variants f64:32:2,f32:auto > gpurun_out/ncu_k1.log 2>&1
 # 4. K1 variants, FP64 pipe and conditional-node probes
