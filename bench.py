@@ -333,11 +333,21 @@ class Lane:
     def prep_e2e_steps(self, k):
         """host inputs of k consecutive end-to-end steps without a barrier in between: k pinned GT copies (find_blobs
         shifts its GT argument in place), made before the timed region"""
+        k = min(k, self.MAX_GT_COPIES)
         while len(self._gt_steps) < k:
             self._gt_steps.append(self.torch.from_numpy(self.gt.copy()).pin_memory())
         for t in self._gt_steps[:k]:
             np.copyto(t.numpy(), self.gt)
         return [t.numpy() for t in self._gt_steps[:k]]
+
+    MAX_GT_COPIES = 32       # pinned memory bound: beyond 32 steps a copy is restored inside the timed loop (counted)
+
+    def e2e_step(self, copies, i):
+        """step i of the end-to-end region on this lane"""
+        g = copies[i % len(copies)]
+        if i >= len(copies):
+            np.copyto(g, self.gt)
+        return self.run_e2e(g)
 
     def prep_e2e(self):
         """this step's host input: find_blobs shifts the caller's GT array in place (reference :26), so the bench
@@ -515,7 +525,7 @@ def run_gpu(args):
         timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e)
     barrier()
     gt_steps = {id(ln): ln.prep_e2e_steps(args.steps) for ln in lanes}       # untimed, like the L2 flush
-    e2e_region_ms = timed_steps(lambda ln, i: ln.run_e2e(gt_steps[id(ln)][i]), lanes, args.steps)
+    e2e_region_ms = timed_steps(lambda ln, i: ln.e2e_step(gt_steps[id(ln)], i), lanes, args.steps)
     barrier()
     e2e_ms = [timed_step(lambda ln: ln.run_e2e(), lanes, Lane.prep_e2e) for _ in range(args.steps)]
     te = torch.tensor([e2e_region_ms, float(sum(e2e_ms))], dtype=torch.float64, device=dev)
