@@ -135,7 +135,9 @@ int aoslo_ctx_capacity(aoslo_ctx* ctx);
 /* implementation knobs (defaults come from the environment once, at aoslo_ctx_create): "k1_tma" 0|1|2,
  * "pair_th", "pair_occ", "dtile_th", "dtile_occ" (0 = automatic), "dtile_split" 0|1,
  * "k1_kernel" 0 auto | 1 generic tile | 2 band | 3 f64 tile,
- * "no_graph" 1 = run aoslo_run's canonical path eagerly (debugging / profiling).  Results do not depend on them. */
+ * "no_graph" 1 = run aoslo_run's canonical path eagerly (debugging / profiling).  Results do not depend on them.
+ * Environment only, read at aoslo_ctx_create: AOSLO_THIN_THREADS (128 | 256 | 512) and AOSLO_THIN_BLOCKS_PER_SM (1..4),
+ * the shape of the cooperative thinning kernel; AOSLO_CELL_SHIFT / AOSLO_LINK_SHIFT, the cell edges of the searches. */
 int aoslo_ctx_set_tuning(aoslo_ctx* ctx, const char* key, int value);
 /* 1: host-side waits of this context sleep on a blocking-sync event instead of spinning (use when many
  * contexts run concurrently, one host thread each); 0 (default): lowest-latency spinning sync */
